@@ -1,0 +1,133 @@
+"""TEST INFRASTRUCTURE -- generator of tests/golden/*.npz.
+
+Runs the UNMODIFIED reference scripts (FP64-promoted, see oracle/ref_harness.py) on the
+deterministic toy worlds of spectra_without_windows_b200/synthetic.py and stores their
+outputs.  Must be run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden [world ...]
+
+A second, shipped-precision (complex64) run of the same scripts is stored under the
+`c64_` prefix to document the ~1e-7 gap between the reference as shipped and its FP64
+promotion (SURVEY.md finding 1).
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as rh  # noqa: E402
+from spectra_without_windows_b200 import synthetic as syn  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def parse_txt(path):
+    return np.loadtxt(path, comments="#")
+
+
+def run_world(name, fp64=True):
+    w = syn.make_world(name)
+    root = tempfile.mkdtemp(prefix="sww_gold_")
+    out = {}
+    try:
+        p = syn.write_world_files(w, root)
+        ou, cp = rh.bind_world(w, fp64=fp64)
+        mc, od = root + "/mc/", root + "/out/"
+        # ---- pk Fisher realisations (pk/compute_pk_randoms.py), then data (pk/compute_pk_data.py)
+        for r in range(1, w.N_mc + 1):
+            cnt = rh.run_script("pk/compute_pk_randoms.py", r, p)
+            out["pk_nfft"] = np.asarray(cnt)
+            out["pk_qbar_%d" % r] = np.load(glob.glob(mc + "*%d_FKP_pk_q-bar_a_*.npy" % r)[0])
+            out["pk_fish_%d" % r] = np.load(glob.glob(mc + "*%d_FKP_pk_fish_a_*.npy" % r)[0])
+        rh.run_script("pk/compute_pk_data.py", 1, p)
+        out["pk_bias_comb"] = np.load(glob.glob(od + "bias-pk_*.npy")[0])
+        out["pk_fish_comb"] = np.load(glob.glob(od + "fisher-pk_*.npy")[0])
+        f = glob.glob(od + "pk_*.txt")[0]
+        out["pk_txt_name"] = np.asarray(os.path.basename(f))
+        out["pk_txt"] = np.asarray(open(f).read())
+        out["pk_p"] = parse_txt(f)
+        # ---- function-level q_alpha (the script does not save it): pk/compute_pk_data.py:137-206
+        if fp64:
+            out.update(function_level(w, ou, cp))
+        # ---- bk Fisher pair r=1 (seeds 2,3) then bk data
+        cnt = rh.run_script("bk/compute_bk_randoms.py", 1, p)
+        out["bk_nfft"] = np.asarray(cnt)
+        out["bk_fish_1"] = np.load(glob.glob(mc + "*1_FKP_bk_fish_alpha_beta_*.npy")[0])
+        z = np.load(glob.glob(mc + "*2_FKP_bk_bias_alpha_*.npz")[0])
+        ga, tga = z["g_a"], z["tilde_g_a"]
+        out["bk_g_dtype"] = np.asarray(str(ga.dtype))
+        out["bk_g_shape"] = np.asarray(ga.shape)
+        # a thin sample of the saved maps: the z=3 plane of every (l, bin)
+        out["bk_g_plane"] = np.real(ga[:, :, :, :, 3])
+        out["bk_tg_plane"] = np.real(tga[:, :, :, :, 3])
+        out["bk_g_maximag"] = np.asarray(np.abs(ga.imag).max() / np.abs(ga.real).max())
+        rh.run_script("bk/compute_bk_data.py", 1, p)
+        out["bk_fish_comb"] = np.load(glob.glob(od + "fisher-bk_*.npy")[0])
+        f = glob.glob(od + "bk_*.txt")[0]
+        out["bk_txt_name"] = np.asarray(os.path.basename(f))
+        out["bk_txt"] = np.asarray(open(f).read())
+        out["bk_p"] = parse_txt(f)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return out
+
+
+def function_level(w, ou, cp):
+    """Reference src/ functions called directly, following pk/compute_pk_data.py:137-206 and
+    bk/compute_bk_data.py:250-283,350-367, to pin q_alpha (never written to disk by the scripts)
+    and single operator outputs."""
+    out = {}
+    box, grid = np.asarray(w.box, float), np.asarray(w.grid, int)
+    data = ou.load_data(1, None, None)
+    rand = ou.load_randoms(None, None)
+    diff, density = ou.grid_data(data, rand, box, grid, MAS="TSC", return_randoms=False)
+    alpha, shot = w.alpha, w.shot_fac
+    nbar = w.nbar_r * alpha
+    k_grids, r_grids = ou.load_coord_grids(box, grid, density)
+    k_norm = np.sqrt(np.sum(k_grids ** 2.0, axis=0))
+    k_grids /= (1e-12 + k_norm)
+    r_grids /= (1e-12 + np.sqrt(np.sum(r_grids ** 2.0, axis=0)))
+    MAS = ou.load_MAS(box, grid)
+    v_cell = 1.0 * box.prod() / (1.0 * grid.prod())
+    out["diff_sum"] = np.asarray([diff.sum(), (diff ** 2).sum(), diff[1, 2, 3], diff[-1, 0, 5]])
+    out["diff_plane"] = diff[:, :, 2]
+    out["MAS_plane"] = MAS[:, :, 3]
+    for tag, (kmin, kmax, dk, lmax) in (("pk", w.pk_bins), ("bk", w.bk_bins)):
+        Y = ou.compute_spherical_harmonic_functions(lmax)
+        filt = ou.compute_filters(kmin, kmax, dk)
+        n_k = int((kmax - kmin) / dk)
+        Cinv_d = cp.applyCinv_fkp(diff, nbar, MAS, v_cell, shot, include_pix=False)
+        if tag == "pk":
+            C_a = cp.applyC_alpha(Cinv_d, nbar, MAS, Y, k_grids, r_grids, v_cell, filt, k_norm, n_k, lmax,
+                                  include_pix=False, data=True)
+            out["pk_q"] = np.asarray([np.real_if_close(np.sum(Cinv_d * c)) / 2.0 for c in C_a]).real
+            # one derivative map of a GRF through applyC_alpha_single, a plane of it
+            np.random.seed(7)
+            a = np.random.normal(size=tuple(grid))
+            m = cp.applyC_alpha_single(a, nbar, MAS, Y, k_grids, r_grids, v_cell, filt, k_norm, 1, 2,
+                                       include_pix=False, data=False)
+            out["pk_Calpha_l2_a2_plane"] = np.real(m[:, :, 1])
+    return out
+
+
+def main(argv):
+    names = argv[1:] or ["toyA", "toyB", "toyC"]
+    os.makedirs(GOLD, exist_ok=True)
+    for n in names:
+        g = run_world(n, fp64=True)
+        c = run_world(n, fp64=False)
+        for k in ("pk_fish_1", "pk_qbar_1", "pk_p", "bk_fish_1", "bk_p"):
+            g["c64_" + k] = c[k]
+        np.savez_compressed(os.path.join(GOLD, n + ".npz"), **g)
+        print(n, "pk nfft", g["pk_nfft"], "bk nfft", g["bk_nfft"], "n_b pk", g["pk_fish_1"].shape,
+              "bk", g["bk_fish_1"].shape, "g dtype", g["bk_g_dtype"], "im/re", g["bk_g_maximag"])
+
+
+if __name__ == "__main__":
+    main(sys.argv)

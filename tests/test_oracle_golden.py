@@ -1,0 +1,82 @@
+"""Pins the CPU oracle (oracle/sww_oracle.py) against the golden vectors produced by the
+UNMODIFIED reference scripts (oracle/make_golden.py, FP64-promoted mode).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import sww_oracle as orc
+
+WORLDS = ["toyA", "toyB", "toyC"]
+TOL = 1e-12      # two FP64 evaluations of the same algorithm
+
+
+def setup_for(w, which):
+    kmin, kmax, dk, lmax = w.pk_bins if which == "pk" else w.bk_bins
+    return orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax)
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_pk_fisher_matches_reference_script(name, world, golden):
+    w, g = world(name), golden(name)
+    S = setup_for(w, "pk")
+    for r in (1, 2):
+        qbar, F = orc.pk_fisher_realisation(S, S.grf(r))
+        assert relerr(F, g["pk_fish_%d" % r]) < TOL
+        assert relerr(qbar, g["pk_qbar_%d" % r]) < TOL
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_paint_and_pk_data(name, world, golden):
+    w, g = world(name), golden(name)
+    S = setup_for(w, "pk")
+    diff, _ = orc.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box, w.grid, w.box_center)
+    assert relerr(diff[:, :, 2], g["diff_plane"]) < TOL
+    assert relerr(S.MAS[:, :, 3], g["MAS_plane"]) < 1e-15
+    q = orc.pk_data_q(S, diff)
+    assert relerr(q, g["pk_q"]) < TOL
+    p = orc.pk_solve(g["pk_fish_comb"], q, g["pk_bias_comb"])
+    n_k = S.n_k
+    p_txt = g["pk_p"][:, 1:].T.ravel()           # text rows are k | P0 P2 P4 -> alpha = l*n_k + a
+    assert p.size == n_k * S.n_l
+    assert relerr(p, p_txt) < 2e-8               # limited by the '%.8e' text format
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_applyC_alpha_single(name, world, golden):
+    w, g = world(name), golden(name)
+    S = setup_for(w, "pk")
+    np.random.seed(7)
+    a = np.random.normal(size=tuple(w.grid))
+    maps = S.applyC_alpha(a)
+    m = np.real(maps[1 * S.n_k + 2])
+    assert relerr(m[:, :, 1], g["pk_Calpha_l2_a2_plane"]) < TOL
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_bk_fisher_and_data(name, world, golden):
+    w, g = world(name), golden(name)
+    S = setup_for(w, "bk")
+    F, (gA, tgA), (gB, tgB) = orc.bk_fisher_pair(S, S.grf(2), S.grf(3), return_g=True)
+    assert F.shape == g["bk_fish_1"].shape
+    assert relerr(F, g["bk_fish_1"]) < 1e-11
+    gplane = np.asarray([[np.real(m[:, :, 3]) for m in row] for row in gA])
+    assert relerr(gplane, g["bk_g_plane"]) < TOL
+    tgplane = np.asarray([[np.real(m[:, :, 3]) for m in row] for row in tgA])
+    assert relerr(tgplane, g["bk_tg_plane"]) < TOL
+    diff, _ = orc.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box, w.grid, w.box_center)
+    q = orc.bk_data_q(S, diff, mc_maps=[(gA, tgA), (gB, tgB)], N_mc=2)
+    p = np.matmul(np.linalg.inv(g["bk_fish_comb"]), q)
+    nt = len(orc.triangle_bins(S.kmin, S.kmax, S.dk, S.n_k))
+    p_txt = g["bk_p"][:, 3:].T.ravel()
+    assert p.size == nt * S.n_l
+    assert relerr(p, p_txt) < 2e-8
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_shipped_precision_gap_documented(name, golden):
+    """The reference as shipped (complex64) differs from its FP64 promotion at the ~1e-7..1e-5
+    level; this is why the 1e-9 parity target is stated against the promoted run."""
+    g = golden(name)
+    for k in ("pk_fish_1", "pk_qbar_1", "bk_fish_1"):
+        e = relerr(g["c64_" + k], g[k])
+        assert 1e-10 < e < 1e-4, (k, e)
