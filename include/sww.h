@@ -1,0 +1,135 @@
+/* sww.h -- C ABI of libsww.so: the B200 (sm_100a) implementation of the Monte-Carlo Fisher /
+ * quadratic + cubic estimator hot path of Spectra-Without-Windows.
+ *
+ * The reference has no FFI layer: its "operator API" is the set of Python functions the four
+ * driver scripts import by name (pk/compute_pk_randoms.py:12-13, pk/compute_pk_data.py:12-13,
+ * bk/compute_bk_randoms.py:12, bk/compute_bk_data.py:13).  Each entry point below states the
+ * reference function / script lines it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on error; sww_last_error() returns a
+ *     thread-local message (the Python layer raises the bare `Exception` the scripts use);
+ *   - device pointers are passed as 64-bit integers (tensor.data_ptr()); the caller owns all
+ *     large buffers (one workspace, bound once) and the library never frees caller memory;
+ *   - all work is asynchronous on the context's stream (sww_ctx_set_stream);
+ *   - real maps are double[nx][ny][nz] (C order); spectra are the R2C half-spectrum
+ *     double2[nx][ny][nz/2+1]; full complex maps (ft/ift mirrors only) are double2[nx][ny][nz];
+ *   - one sww_ctx per process and GPU; a context is not thread-safe.
+ */
+#ifndef SWW_H
+#define SWW_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWW_ABI_VERSION 1
+
+typedef struct sww_ctx sww_ctx;
+typedef uint64_t sww_devptr; /* device address */
+typedef uint64_t sww_stream; /* cudaStream_t   */
+
+/* Geometry and binning, built on the host with the reference's own expressions so that bin
+ * membership and the MAS window are bit-identical:
+ *   rax  : src/opt_utilities.py:428-430 (fft-ordered mesh coordinate + BoxCenter + half a cell)
+ *   kax  : src/opt_utilities.py:420-422
+ *   mas  : src/opt_utilities.py:448-463 (1-D factors, float32 pi/N prefactor)
+ *   k_lo/k_hi : src/opt_utilities.py:485-487 (np.arange edges)                              */
+typedef struct {
+  int32_t grid[3];
+  double box[3];
+  int32_t lmax; /* even, <= 4 */
+  int32_t n_k;
+  const double* k_lo;
+  const double* k_hi;
+  const double* rax[3];
+  const double* kax[3];
+  const double* mas[3];
+  int32_t device;
+} sww_geometry;
+
+/* workspace selectors for sww_workspace_bytes */
+enum { SWW_WS_OPS = 0, SWW_WS_PK_FISHER = 1, SWW_WS_PK_DATA = 2, SWW_WS_BK_FISHER = 3, SWW_WS_BK_DATA = 4 };
+
+const char* sww_last_error(void);
+int sww_abi_version(void);
+
+int sww_ctx_create(const sww_geometry* g, sww_ctx** out);
+int sww_ctx_destroy(sww_ctx* c);
+int sww_ctx_set_stream(sww_ctx* c, sww_stream s);
+/* bytes of caller-owned workspace needed for a pipeline (includes the cuFFT work area) */
+int sww_workspace_bytes(sww_ctx* c, int what, uint64_t* bytes);
+int sww_bind_workspace(sww_ctx* c, sww_devptr ws, uint64_t bytes);
+/* number of kernel launches (own kernels, cuFFT calls) issued by this context so far */
+int sww_launch_counts(sww_ctx* c, uint64_t* own_kernels, uint64_t* fft_calls);
+/* choose the FFT backend: 0 = cuFFT, 1 = hand-written sm_100a passes (power-of-two meshes) */
+int sww_set_fft_backend(sww_ctx* c, int backend);
+
+/* n(r) maps: nbar (load_nbar(...,alpha_ran) or painted randoms), nbar_weight, nbar_A
+ * (pk/compute_pk_randoms.py:135-136,160,173-179).  Borrowed device pointers, double[N]. */
+int sww_set_fields(sww_ctx* c, sww_devptr nbar, sww_devptr nbar_weight, sww_devptr nbar_A,
+                   double shot_fac, double P_fkp);
+
+/* ---- drop-in operators (mirrors of src/opt_utilities.py and src/covariances_pk.py) ---- */
+/* ft / ift  (src/opt_utilities.py:502-555) in complex128; inverse normalised by 1/N. */
+int sww_fft_c2c(sww_ctx* c, sww_devptr in, sww_devptr out, int inverse);
+/* real-to-half-spectrum and back (unnormalised forward, 1/N inverse). c2r destroys `in`. */
+int sww_fft_r2c(sww_ctx* c, sww_devptr in, sww_devptr out);
+int sww_fft_c2r(sww_ctx* c, sww_devptr in, sww_devptr out);
+/* applyCinv_fkp, include_pix=False (src/covariances_pk.py:153-164): out = x v_cell/(n(nP+s)) on n>0 */
+int sww_apply_cinv_fkp(sww_ctx* c, sww_devptr x, sww_devptr nbar_w, double v_cell, double shot_fac,
+                       double P_fkp, sww_devptr out);
+/* applyN, include_pix=False (src/covariances_pk.py:124) */
+int sww_apply_n(sww_ctx* c, sww_devptr x, sww_devptr nbar, double v_cell, double shot_fac, sww_devptr out);
+/* sum_m Y_lm(k^) FT[x Y_lm(r^)] * MAS^mas_power for every even l <= lmax
+ * (src/covariances_pk.py:378-389; NOT yet multiplied by 4pi/(2l+1)).  out: double2[n_l][Nc]. */
+int sww_ylm_project(sww_ctx* c, sww_devptr x, int mas_power, sww_devptr out);
+/* applyC_alpha_single, include_pix=False (src/covariances_pk.py:404-466): one derivative map */
+int sww_apply_c_alpha_single(sww_ctx* c, sww_devptr x, sww_devptr nbar, double v_cell, int l_i, int a,
+                             int data, sww_devptr out);
+/* device bin-index map (uint8[nx][ny][nz/2+1], 255 = outside every bin) -- compute_filters */
+int sww_get_binmap(sww_ctx* c, sww_devptr out);
+
+/* ---- painting (src/opt_utilities.py:219-267, pmesh TSC / CIC without compensation) ---- */
+/* out[cell] += scale * sum_p w_p W(x_p - cell); pos double[n][3], w double[n] (device).
+ * scheme: 2 = CIC, 3 = TSC. */
+int sww_paint(sww_ctx* c, sww_devptr pos, sww_devptr w, uint64_t n, const double box_center[3],
+              int scheme, double scale, sww_devptr out);
+
+/* ---- P_l(k) pipelines ---- */
+/* One Gaussian realisation `a` (double[N], device) -> q-bar_alpha [n_b] and the symmetrised
+ * F_ab [n_b*n_b] (device, double).  Replaces pk/compute_pk_randoms.py:206-281. */
+int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a, sww_devptr fish_out, sww_devptr qbar_out);
+/* q_alpha [n_b] of a painted (n_g - alpha n_r)/V_cell map.  Replaces pk/compute_pk_data.py:191-206. */
+int sww_pk_data_q(sww_ctx* c, sww_devptr diff, sww_devptr q_out);
+
+/* ---- B_l(k1,k2,k3) pipelines ---- */
+/* triangle list (a<=b<=c) set by the host from test_bin (bk/compute_bk_randoms.py:186-211) */
+int sww_bk_set_triangles(sww_ctx* c, const int32_t* tris /*[n_tri][3]*/, int32_t n_tri);
+/* g_i^l and tilde-g_i^l maps of one field (bk/compute_bk_randoms.py:222-267).  data!=0 applies the
+ * extra MAS factor of bk/compute_bk_data.py:270 and skips tilde-g.  Outputs double[n_l][n_k][N]. */
+int sww_bk_gmaps(sww_ctx* c, sww_devptr a, int data, sww_devptr g_out, sww_devptr tg_out);
+/* Fisher contribution of a pair of realisations (bk/compute_bk_randoms.py:269-517) given Delta_abc
+ * [n_b] (device).  fish_out double[n_b*n_b].  g/tilde-g maps of both fields are left in
+ * gA,tgA,gB,tgB (double[n_l][n_k][N] each, device) for the 1-field term of the data script. */
+int sww_bk_fisher_pair(sww_ctx* c, sww_devptr aA, sww_devptr aB, sww_devptr delta, sww_devptr gA,
+                       sww_devptr tgA, sww_devptr gB, sww_devptr tgB, sww_devptr fish_out);
+/* Delta_abc degeneracy factors (bk/compute_bk_randoms.py:427-473), data independent. */
+int sww_bk_delta(sww_ctx* c, sww_devptr delta_out);
+/* 3-field term sum_x g_a^0 g_b^0 g_c^l for every triangle and l (bk/compute_bk_data.py:350-367);
+ * q_out double[n_tri][n_l]. */
+int sww_bk_q3(sww_ctx* c, sww_devptr g, sww_devptr q_out);
+/* 1-field term of one MC simulation (bk/compute_bk_data.py:380-403): q_out[t][l] -= 0.5/N_mc * (...) */
+int sww_bk_q1_accumulate(sww_ctx* c, sww_devptr g, sww_devptr g_mc, sww_devptr tg_mc, double inv_two_nmc,
+                         sww_devptr q_inout);
+/* C[i][j] = sum_x A[i][x] B[j][x]  (FP64 tensor-core Gram, the dense contraction of
+ * bk/compute_bk_randoms.py:489-497);  accumulate!=0 adds into C.  A: [m][N], B: [n][N], C: [m][n]. */
+int sww_gram_f64(sww_ctx* c, sww_devptr A, sww_devptr B, int32_t m, int32_t n, uint64_t N, int accumulate,
+                 sww_devptr C);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWW_H */

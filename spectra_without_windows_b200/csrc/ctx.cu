@@ -1,0 +1,207 @@
+// Context life-cycle, workspace layout and the small C-ABI entry points of libsww.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "sww_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void sww_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* sww_last_error(void) { return g_err; }
+extern "C" int sww_abi_version(void) { return SWW_ABI_VERSION; }
+
+static int max_abs_index_below(const double* kax, int n, double kmax) {
+  // largest |signed index| whose |k| can fall below kmax (modes at or above kmax are in no bin)
+  int best = 0;
+  for (int i = 0; i < n; ++i) {
+    int s = (i >= n / 2.0) ? i - n : i;
+    if (std::fabs(kax[i]) < kmax) best = std::max(best, std::abs(s));
+  }
+  return best;
+}
+
+extern "C" int sww_ctx_create(const sww_geometry* geo, sww_ctx** out) {
+  SWW_REQUIRE(geo && out, "null argument");
+  SWW_REQUIRE(geo->lmax >= 0 && geo->lmax % 2 == 0 && geo->lmax <= 2 * (SWW_MAX_L - 1),
+              "l-max must be even and <= %d", 2 * (SWW_MAX_L - 1));
+  SWW_REQUIRE(geo->n_k >= 1 && geo->n_k <= SWW_MAX_BINS, "n_k must be in [1,%d]", SWW_MAX_BINS);
+  for (int d = 0; d < 3; ++d) SWW_REQUIRE(geo->grid[d] >= 4, "grid too small");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  SWW_REQUIRE(e == cudaSuccess && ndev > 0, "no CUDA device: libsww has no CPU path (%s)", cudaGetErrorString(e));
+  SWW_CUDA(cudaSetDevice(geo->device));
+  sww_ctx* c = new sww_ctx();
+  c->device = geo->device;
+  Geo& g = c->g;
+  g.nx = geo->grid[0];
+  g.ny = geo->grid[1];
+  g.nz = geo->grid[2];
+  g.nzh = g.nz / 2 + 1;
+  g.N = (long long)g.nx * g.ny * g.nz;
+  g.Nc = (long long)g.nx * g.ny * g.nzh;
+  g.n_k = geo->n_k;
+  for (int d = 0; d < 3; ++d) c->box[d] = geo->box[d];
+  c->v_cell = 1.0 * (geo->box[0] * geo->box[1] * geo->box[2]) / (1.0 * ((double)g.nx * g.ny * g.nz));
+  c->lmax = geo->lmax;
+  c->n_l = geo->lmax / 2 + 1;
+  c->n_lm = 0;
+  for (int l = 0; l <= geo->lmax; l += 2) c->n_lm += 2 * l + 1;
+  c->h_klo.assign(geo->k_lo, geo->k_lo + geo->n_k);
+  c->h_khi.assign(geo->k_hi, geo->k_hi + geo->n_k);
+  double kmax = *std::max_element(c->h_khi.begin(), c->h_khi.end());
+  // Hermitian (R2C) evaluation requires every binned mode to lie strictly below Nyquist on every axis
+  for (int d = 0; d < 3; ++d) {
+    double kny = M_PI * geo->grid[d] / geo->box[d];
+    if (!(kmax < kny)) {
+      sww_set_error("k_max=%.6g is not below the Nyquist frequency %.6g of axis %d", kmax, kny, d);
+      delete c;
+      return -1;
+    }
+  }
+  g.bx = max_abs_index_below(geo->kax[0], g.nx, kmax);
+  g.by = max_abs_index_below(geo->kax[1], g.ny, kmax);
+  g.bz = max_abs_index_below(geo->kax[2], g.nz, kmax);
+  g.Kx = std::min(2 * g.bx + 1, g.nx);
+  g.Ky = std::min(2 * g.by + 1, g.ny);
+  g.Kz = std::min(g.bz + 1, g.nzh);
+  // tables: rax(3) kax(3) mas(3) klo khi
+  size_t nt = 3 * (size_t)(g.nx + g.ny + g.nz) + 2 * (size_t)g.n_k;
+  std::vector<double> h(nt);
+  size_t o = 0;
+  double* dptr[11];
+  const double* src[9] = {geo->rax[0], geo->rax[1], geo->rax[2], geo->kax[0], geo->kax[1],
+                          geo->kax[2], geo->mas[0], geo->mas[1], geo->mas[2]};
+  int len[9] = {g.nx, g.ny, g.nz, g.nx, g.ny, g.nz, g.nx, g.ny, g.nz};
+  SWW_CUDA(cudaMalloc(&c->d_tables, nt * sizeof(double)));
+  for (int i = 0; i < 9; ++i) {
+    memcpy(&h[o], src[i], len[i] * sizeof(double));
+    dptr[i] = c->d_tables + o;
+    o += len[i];
+  }
+  memcpy(&h[o], geo->k_lo, g.n_k * sizeof(double));
+  c->d_klo = c->d_tables + o;
+  o += g.n_k;
+  memcpy(&h[o], geo->k_hi, g.n_k * sizeof(double));
+  c->d_khi = c->d_tables + o;
+  o += g.n_k;
+  SWW_CUDA(cudaMemcpy(c->d_tables, h.data(), nt * sizeof(double), cudaMemcpyHostToDevice));
+  for (int d = 0; d < 3; ++d) {
+    g.rax[d] = dptr[d];
+    g.kax[d] = dptr[3 + d];
+    g.mas[d] = dptr[6 + d];
+  }
+  SWW_CUDA(cudaMalloc(&c->d_binmap, (size_t)g.Nc));
+  g.binmap = c->d_binmap;
+  c->partial_elems = (size_t)148 * 4 * SWW_MAX_L * SWW_MAX_BINS;
+  SWW_CUDA(cudaMalloc(&c->d_partial, c->partial_elems * sizeof(double)));
+  SWW_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+  SWW_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int)));
+  SWW_TRY(k_build_binmap(c));
+  SWW_TRY(sww_fft_init(c));
+  SWW_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+extern "C" int sww_ctx_destroy(sww_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  sww_fft_destroy(c);
+  cudaFree(c->d_tables);
+  cudaFree(c->d_binmap);
+  cudaFree(c->d_partial);
+  cudaFree(c->d_counter);
+  if (c->d_tris) cudaFree(c->d_tris);
+  delete c;
+  return 0;
+}
+
+extern "C" int sww_ctx_set_stream(sww_ctx* c, sww_stream s) {
+  SWW_REQUIRE(c, "null context");
+  c->stream = (cudaStream_t)s;
+  if (c->fft_work || c->fft_work_bytes == 0) SWW_TRY(sww_fft_bind_work(c));
+  return 0;
+}
+
+extern "C" int sww_launch_counts(sww_ctx* c, uint64_t* own, uint64_t* fft) {
+  SWW_REQUIRE(c, "null context");
+  if (own) *own = c->n_own;
+  if (fft) *fft = c->n_fft;
+  return 0;
+}
+
+extern "C" int sww_set_fft_backend(sww_ctx* c, int backend) {
+  SWW_REQUIRE(c, "null context");
+  SWW_REQUIRE(backend == 0 || backend == 1, "unknown FFT backend %d", backend);
+  if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes");
+  c->fft_backend = backend;
+  return 0;
+}
+
+static size_t persist_layout(sww_ctx* c) {
+  size_t nW = ((size_t)c->g.N * sizeof(double) + 255) & ~size_t(255);
+  size_t fw = (c->fft_work_bytes + 255) & ~size_t(255);
+  return nW + fw;
+}
+
+size_t sww_pipeline_bytes(sww_ctx* c, int what);  // pipelines.cu
+
+extern "C" int sww_workspace_bytes(sww_ctx* c, int what, uint64_t* bytes) {
+  SWW_REQUIRE(c && bytes, "null argument");
+  *bytes = persist_layout(c) + sww_pipeline_bytes(c, what) + 4096;
+  return 0;
+}
+
+extern "C" int sww_bind_workspace(sww_ctx* c, sww_devptr ws, uint64_t bytes) {
+  SWW_REQUIRE(c, "null context");
+  SWW_REQUIRE(ws % 256 == 0, "workspace must be 256-byte aligned");
+  size_t p = persist_layout(c);
+  SWW_REQUIRE(bytes >= p, "workspace too small: %llu < %zu", (unsigned long long)bytes, p);
+  c->ar.base = (char*)ws;
+  c->ar.cap = bytes;
+  c->persist_bytes = p;
+  c->d_nW = (double*)ws;
+  c->fft_work = (char*)ws + (((size_t)c->g.N * sizeof(double) + 255) & ~size_t(255));
+  c->fields_dirty = true;
+  SWW_TRY(sww_fft_bind_work(c));
+  return 0;
+}
+
+extern "C" int sww_set_fields(sww_ctx* c, sww_devptr nbar, sww_devptr nbar_weight, sww_devptr nbar_A, double shot_fac,
+                              double P_fkp) {
+  SWW_REQUIRE(c, "null context");
+  SWW_REQUIRE(c->ar.base, "bind a workspace before setting the fields");
+  c->nbar = (const double*)nbar;
+  c->nbar_w = (const double*)nbar_weight;
+  c->nbar_A = (const double*)nbar_A;
+  c->shot = shot_fac;
+  c->P_fkp = P_fkp;
+  SWW_TRY(k_prep_static(c));
+  c->fields_dirty = false;
+  return 0;
+}
+
+extern "C" int sww_get_binmap(sww_ctx* c, sww_devptr out) {
+  SWW_REQUIRE(c && out, "null argument");
+  SWW_CUDA(cudaMemcpyAsync((void*)out, c->d_binmap, (size_t)c->g.Nc, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+extern "C" int sww_bk_set_triangles(sww_ctx* c, const int32_t* tris, int32_t n_tri) {
+  SWW_REQUIRE(c && tris && n_tri > 0, "bad triangle list");
+  for (int i = 0; i < 3 * n_tri; ++i) SWW_REQUIRE(tris[i] >= 0 && tris[i] < c->g.n_k, "triangle bin out of range");
+  c->tris.assign(tris, tris + 3 * (size_t)n_tri);
+  c->n_tri = n_tri;
+  if (c->d_tris) cudaFree(c->d_tris);
+  SWW_CUDA(cudaMalloc(&c->d_tris, sizeof(int) * 3 * (size_t)n_tri));
+  SWW_CUDA(cudaMemcpy(c->d_tris, tris, sizeof(int) * 3 * (size_t)n_tri, cudaMemcpyHostToDevice));
+  return 0;
+}

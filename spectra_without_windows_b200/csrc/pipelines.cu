@@ -1,0 +1,236 @@
+// P_l(k) pipelines and the drop-in operator entry points of libsww.
+//
+// Formulation (checked against the reference scripts to 1e-12 in tests):
+//   F^C_l(k) = 4pi/(2l+1) sum_m Y_lm(k^) FT[n C^-1 a Y_lm(r^)](k),   G_l(k) likewise from A^-1 a
+//   u_alpha  = IFT[Theta_a F^C_l],   U_alpha = W u_alpha,  W = n / (n_w (n_w P + s)) on n_w > 0
+//   F_ab     = 1/(2 N v_cell) sum_{k in shell b} conj(FT[n U_alpha](k)) G_l'(k)          (Parseval)
+//   qbar_a   = 1/(2 N)        sum_{k in shell a} F^C_l(k) conj(FT[W N A^-1 a](k))
+// so one realisation costs 2M + 1 + 2 n_b transforms and no derivative map is ever stored
+// (the reference materialises 2 n_b maps or spills them to disk: pk/compute_pk_randoms.py:220-274).
+#include <cmath>
+
+#include "sww_internal.cuh"
+
+static inline double lcoef(int l_i) { return 4.0 * M_PI / (4.0 * l_i + 1.0); }
+
+// sum_m Y_lm(k^) FT[f Y_lm(r^)] for every multipole; tmp: real scratch [N]; spec: complex scratch [Nc]
+static int ylm_project(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
+                       double2* spec, double2* const* out) {
+  int lm = 0;
+  for (int l_i = 0; l_i < c->n_l; ++l_i) {
+    int nm = 4 * l_i + 1;
+    for (int m = 0; m < nm; ++m, ++lm) {
+      SWW_TRY(k_mul_ylm_r(c, f, lm, tmp));
+      SWW_TRY(sww_r2c(c, tmp, spec));
+      double coef = (m == nm - 1) ? (with_coef ? lcoef(l_i) : 1.0) : 0.0;
+      SWW_TRY(k_acc_ylm_k(c, spec, lm, coef, mas_power, m == 0, pruned ? 1 : 0, out[l_i]));
+    }
+  }
+  return 0;
+}
+
+struct PkFisherBufs {
+  double *nCa, *nAa, *WS, *tmp, *row;
+  double2 *FC[SWW_MAX_L], *G[SWW_MAX_L], *X;
+};
+
+static void pk_fisher_layout(sww_ctx* c, Arena& ar, PkFisherBufs& b) {
+  size_t N = c->g.N, Nc = c->g.Nc;
+  ar.reset(c->persist_bytes);
+  for (int l = 0; l < c->n_l; ++l) b.FC[l] = ar.alloc<double2>(Nc);
+  for (int l = 0; l < c->n_l; ++l) b.G[l] = ar.alloc<double2>(Nc);
+  b.X = ar.alloc<double2>(Nc);
+  b.tmp = ar.alloc<double>(N);
+  b.nCa = ar.alloc<double>(N);
+  b.nAa = ar.alloc<double>(N);
+  b.WS = ar.alloc<double>(N);
+  b.row = ar.alloc<double>((size_t)c->n_l * c->g.n_k);
+}
+
+struct PkDataBufs {
+  double *f, *tmp;
+  double2 *FD[SWW_MAX_L], *R, *spec;
+};
+
+static void pk_data_layout(sww_ctx* c, Arena& ar, PkDataBufs& b) {
+  size_t N = c->g.N, Nc = c->g.Nc;
+  ar.reset(c->persist_bytes);
+  for (int l = 0; l < c->n_l; ++l) b.FD[l] = ar.alloc<double2>(Nc);
+  b.R = ar.alloc<double2>(Nc);
+  b.spec = ar.alloc<double2>(Nc);
+  b.f = ar.alloc<double>(N);
+  b.tmp = ar.alloc<double>(N);
+}
+
+struct OpsBufs {
+  double *f, *tmp;
+  double2 *spec, *F[SWW_MAX_L];
+};
+
+static void ops_layout(sww_ctx* c, Arena& ar, OpsBufs& b) {
+  size_t N = c->g.N, Nc = c->g.Nc;
+  ar.reset(c->persist_bytes);
+  b.f = ar.alloc<double>(N);
+  b.tmp = ar.alloc<double>(N);
+  b.spec = ar.alloc<double2>(Nc);
+  for (int l = 0; l < c->n_l; ++l) b.F[l] = ar.alloc<double2>(Nc);
+}
+
+size_t sww_bk_pipeline_bytes(sww_ctx* c, int what);  // bk.cu
+
+size_t sww_pipeline_bytes(sww_ctx* c, int what) {
+  Arena dry;
+  dry.dry = true;
+  size_t save = c->persist_bytes;
+  c->persist_bytes = 0;
+  size_t r = 0;
+  if (what == SWW_WS_PK_FISHER) {
+    PkFisherBufs b;
+    pk_fisher_layout(c, dry, b);
+    r = dry.peak;
+  } else if (what == SWW_WS_PK_DATA) {
+    PkDataBufs b;
+    pk_data_layout(c, dry, b);
+    r = dry.peak;
+  } else if (what == SWW_WS_OPS) {
+    OpsBufs b;
+    ops_layout(c, dry, b);
+    r = dry.peak;
+  } else {
+    r = sww_bk_pipeline_bytes(c, what);
+  }
+  c->persist_bytes = save;
+  return r;
+}
+
+#define CHECK_READY(c)                                                       \
+  SWW_REQUIRE(c, "null context");                                            \
+  SWW_REQUIRE((c)->ar.base, "no workspace bound (sww_bind_workspace)");
+
+#define CHECK_FIELDS(c) SWW_REQUIRE(!(c)->fields_dirty && (c)->nbar, "fields not set (sww_set_fields)")
+
+#define CHECK_ARENA(c) \
+  SWW_REQUIRE((c)->ar.ok(), "workspace too small: pipeline needs %zu bytes, %zu bound", (c)->ar.off, (c)->ar.cap)
+
+// ------------------------------------------------------------------------------------------
+extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr fish_out, sww_devptr qbar_out) {
+  CHECK_READY(c);
+  CHECK_FIELDS(c);
+  SWW_REQUIRE(a_ && fish_out && qbar_out, "null device pointer");
+  PkFisherBufs b;
+  pk_fisher_layout(c, c->ar, b);
+  CHECK_ARENA(c);
+  const double* a = (const double*)a_;
+  double* F = (double*)fish_out;
+  double* qbar = (double*)qbar_out;
+  const int n_k = c->g.n_k, n_l = c->n_l, n_b = n_k * n_l;
+  const double N = (double)c->g.N;
+
+  SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS));
+  SWW_TRY(ylm_project(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
+  SWW_TRY(ylm_project(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
+  // q-bar: one transform of W N A^-1 a, then one binning pass against F^C_l
+  SWW_TRY(sww_r2c(c, b.WS, b.X));
+  SWW_TRY(k_shell_bin(c, b.X, (const double2* const*)b.FC, n_l, 0.5 / N, qbar));
+  // Fisher rows
+  for (int alpha = 0; alpha < n_b; ++alpha) {
+    int l_i = alpha / n_k, ka = alpha % n_k;
+    SWW_TRY(k_shell_fill(c, b.FC[l_i], ka, 1.0, b.X));
+    SWW_TRY(sww_c2r(c, b.X, b.tmp));
+    SWW_TRY(k_weight(c, b.tmp, c->d_nW, 1.0 / N));
+    SWW_TRY(sww_r2c(c, b.tmp, b.X));
+    SWW_TRY(k_shell_bin(c, b.X, (const double2* const*)b.G, n_l, 0.5 / (N * c->v_cell), F + (size_t)alpha * n_b));
+  }
+  SWW_TRY(k_symmetrise(c, F, n_b));
+  return 0;
+}
+
+extern "C" int sww_pk_data_q(sww_ctx* c, sww_devptr diff_, sww_devptr q_out) {
+  CHECK_READY(c);
+  CHECK_FIELDS(c);
+  SWW_REQUIRE(diff_ && q_out, "null device pointer");
+  PkDataBufs b;
+  pk_data_layout(c, c->ar, b);
+  CHECK_ARENA(c);
+  const double N = (double)c->g.N;
+  // f = n C^-1 d
+  SWW_TRY(k_cinv_fkp(c, (const double*)diff_, c->nbar_w, c->v_cell, c->shot, c->P_fkp, b.f, c->nbar));
+  SWW_TRY(ylm_project(c, b.f, 2, true, true, b.tmp, b.spec, b.FD));
+  SWW_TRY(sww_r2c(c, b.f, b.R));
+  SWW_TRY(k_shell_bin(c, b.R, (const double2* const*)b.FD, c->n_l, 0.5 / (N * c->v_cell), (double*)q_out));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// drop-in operators
+// ------------------------------------------------------------------------------------------
+extern "C" int sww_fft_c2c(sww_ctx* c, sww_devptr in, sww_devptr out, int inverse) {
+  SWW_REQUIRE(c && in && out, "null argument");
+  return sww_c2c(c, (const double2*)in, (double2*)out, inverse);
+}
+
+extern "C" int sww_fft_r2c(sww_ctx* c, sww_devptr in, sww_devptr out) {
+  CHECK_READY(c);
+  return sww_r2c(c, (const double*)in, (double2*)out);
+}
+
+extern "C" int sww_fft_c2r(sww_ctx* c, sww_devptr in, sww_devptr out) {
+  CHECK_READY(c);
+  SWW_TRY(sww_c2r(c, (double2*)in, (double*)out));
+  return k_mul(c, (const double*)out, nullptr, 1.0 / (double)c->g.N, (double*)out);
+}
+
+extern "C" int sww_apply_cinv_fkp(sww_ctx* c, sww_devptr x, sww_devptr nbar_w, double v_cell, double shot_fac,
+                                  double P_fkp, sww_devptr out) {
+  SWW_REQUIRE(c && x && nbar_w && out, "null argument");
+  return k_cinv_fkp(c, (const double*)x, (const double*)nbar_w, v_cell, shot_fac, P_fkp, (double*)out, nullptr);
+}
+
+extern "C" int sww_apply_n(sww_ctx* c, sww_devptr x, sww_devptr nbar, double v_cell, double shot_fac, sww_devptr out) {
+  SWW_REQUIRE(c && x && nbar && out, "null argument");
+  return k_apply_n(c, (const double*)x, (const double*)nbar, v_cell, shot_fac, (double*)out);
+}
+
+extern "C" int sww_ylm_project(sww_ctx* c, sww_devptr x, int mas_power, sww_devptr out) {
+  CHECK_READY(c);
+  SWW_REQUIRE(x && out, "null argument");
+  SWW_REQUIRE(mas_power >= 0 && mas_power <= 2, "mas_power must be 0, 1 or 2");
+  OpsBufs b;
+  ops_layout(c, c->ar, b);
+  CHECK_ARENA(c);
+  double2* outs[SWW_MAX_L];
+  for (int l = 0; l < c->n_l; ++l) outs[l] = (double2*)out + (size_t)l * c->g.Nc;
+  return ylm_project(c, (const double*)x, mas_power, false, false, b.tmp, b.spec, outs);
+}
+
+extern "C" int sww_apply_c_alpha_single(sww_ctx* c, sww_devptr x, sww_devptr nbar, double v_cell, int l_i, int a,
+                                        int data, sww_devptr out) {
+  CHECK_READY(c);
+  SWW_REQUIRE(x && nbar && out, "null argument");
+  SWW_REQUIRE(l_i >= 0 && l_i < c->n_l && a >= 0 && a < c->g.n_k, "multipole / bin index out of range");
+  OpsBufs b;
+  ops_layout(c, c->ar, b);
+  CHECK_ARENA(c);
+  SWW_TRY(k_mul(c, (const double*)x, (const double*)nbar, 1.0, b.f));
+  // only the requested multipole
+  int lm0 = 0;
+  for (int l = 0; l < l_i; ++l) lm0 += 4 * l + 1;
+  int nm = 4 * l_i + 1;
+  for (int m = 0; m < nm; ++m) {
+    SWW_TRY(k_mul_ylm_r(c, b.f, lm0 + m, b.tmp));
+    SWW_TRY(sww_r2c(c, b.tmp, b.spec));
+    double coef = (m == nm - 1) ? lcoef(l_i) : 0.0;
+    SWW_TRY(k_acc_ylm_k(c, b.spec, lm0 + m, coef, data ? 2 : 0, m == 0, 1, b.F[0]));
+  }
+  SWW_TRY(k_shell_fill(c, b.F[0], a, 1.0, b.spec));
+  SWW_TRY(sww_c2r(c, b.spec, b.tmp));
+  return k_mul(c, b.tmp, (const double*)nbar, 1.0 / ((double)c->g.N * v_cell), (double*)out);
+}
+
+extern "C" int sww_paint(sww_ctx* c, sww_devptr pos, sww_devptr w, uint64_t n, const double box_center[3], int scheme,
+                         double scale, sww_devptr out) {
+  SWW_REQUIRE(c && out && box_center, "null argument");
+  SWW_REQUIRE(scheme == 2 || scheme == 3, "scheme must be 2 (CIC) or 3 (TSC)");
+  SWW_REQUIRE(n == 0 || (pos && w), "null catalogue pointer");
+  return k_paint(c, (const double*)pos, (const double*)w, n, box_center, scheme, scale, (double*)out);
+}

@@ -1,0 +1,156 @@
+// Internal declarations shared by the libsww translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sww.h"
+
+#define SWW_NO_BIN 255
+#define SWW_MAX_L 3     // multipole slots (l = 0,2,4)
+#define SWW_MAX_BINS 254
+
+void sww_set_error(const char* fmt, ...);
+
+#define SWW_CUDA(x)                                                                             \
+  do {                                                                                          \
+    cudaError_t e__ = (x);                                                                      \
+    if (e__ != cudaSuccess) {                                                                   \
+      sww_set_error("%s:%d CUDA error %s in %s", __FILE__, __LINE__, cudaGetErrorString(e__), #x); \
+      return -2;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+#define SWW_CUFFT(x)                                                                   \
+  do {                                                                                 \
+    cufftResult r__ = (x);                                                             \
+    if (r__ != CUFFT_SUCCESS) {                                                        \
+      sww_set_error("%s:%d cuFFT error %d in %s", __FILE__, __LINE__, (int)r__, #x);  \
+      return -3;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+#define SWW_TRY(x)          \
+  do {                      \
+    int r__ = (x);          \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+#define SWW_REQUIRE(cond, ...)    \
+  do {                            \
+    if (!(cond)) {                \
+      sww_set_error(__VA_ARGS__); \
+      return -1;                  \
+    }                             \
+  } while (0)
+
+// Geometry block passed by value to kernels.
+struct Geo {
+  int nx, ny, nz, nzh;
+  long long N, Nc;
+  const double* rax[3];
+  const double* kax[3];
+  const double* mas[3];
+  const uint8_t* binmap;
+  int n_k;
+  // pruning box: signed indices |ix|<=bx, |iy|<=by, 0<=iz<=bz carry every binned mode
+  int bx, by, bz, Kx, Ky, Kz;
+};
+
+// Bump allocator over the caller-provided workspace.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  void reset(size_t start = 0) { off = start; }
+  template <typename T>
+  T* alloc(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    size_t o = off;
+    off += bytes;
+    if (off > peak) peak = off;
+    if (dry) return nullptr;
+    return (T*)(base + o);
+  }
+  bool ok() const { return dry || off <= cap; }
+};
+
+struct sww_ctx {
+  int device = 0;
+  cudaStream_t stream = 0;
+  Geo g;
+  double box[3];
+  double v_cell;
+  int lmax, n_l, n_lm;
+  std::vector<double> h_klo, h_khi;
+  // ctx-owned small tables
+  double* d_tables = nullptr;
+  double *d_klo = nullptr, *d_khi = nullptr;
+  uint8_t* d_binmap = nullptr;
+  // borrowed fields
+  const double *nbar = nullptr, *nbar_w = nullptr, *nbar_A = nullptr;
+  double shot = 0, P_fkp = 1e4;
+  bool fields_dirty = true;
+  // workspace
+  Arena ar;
+  size_t persist_bytes = 0;   // [nW map][cufft work area] at the front of the workspace
+  double* d_nW = nullptr;     // n * W  with W = n/(n_w (n_w P + s)) [n_w>0]
+  void* fft_work = nullptr;
+  size_t fft_work_bytes = 0;
+  // cuFFT
+  cufftHandle plan_d2z = 0, plan_z2d = 0, plan_z2z = 0;
+  bool have_z2z = false;
+  int fft_backend = 0;
+  // bk
+  std::vector<int> tris;
+  int* d_tris = nullptr;
+  int n_tri = 0;
+  // accounting
+  unsigned long long n_own = 0, n_fft = 0;
+  // scratch for block-level partial sums
+  double* d_partial = nullptr;
+  size_t partial_elems = 0;
+  unsigned int* d_counter = nullptr;
+};
+
+static inline int sww_grid_for(long long n, int block, int max_blocks = 148 * 16) {
+  long long b = (n + block - 1) / block;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---- fft.cu
+int sww_fft_init(sww_ctx* c);
+void sww_fft_destroy(sww_ctx* c);
+int sww_fft_bind_work(sww_ctx* c);
+int sww_r2c(sww_ctx* c, const double* in, double2* out);
+int sww_c2r(sww_ctx* c, double2* in, double* out);  // unnormalised, destroys in
+int sww_c2c(sww_ctx* c, const double2* in, double2* out, int inverse);
+int sww_fft_sm100_supported(const sww_ctx* c);
+int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out);
+int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out);
+
+// ---- kernels.cu (launch wrappers)
+int k_build_binmap(sww_ctx* c);
+int k_prep_static(sww_ctx* c);  // nW map
+int k_prep_pk(sww_ctx* c, const double* a, double* nCa, double* nAa, double* WS);
+int k_cinv_fkp(sww_ctx* c, const double* x, const double* nw, double v_cell, double shot, double P, double* out,
+               const double* post_mul);
+int k_apply_n(sww_ctx* c, const double* x, const double* nbar, double v_cell, double shot, double* out);
+int k_mul(sww_ctx* c, const double* a, const double* b, double s, double* out);
+int k_mul_ylm_r(sww_ctx* c, const double* f, int lm, double* out);
+int k_acc_ylm_k(sww_ctx* c, const double2* spec, int lm, double coef, int mas_power, int first, int pruned,
+                double2* out);
+int k_shell_fill(sww_ctx* c, const double2* F, int a, double coef, double2* X);
+int k_weight(sww_ctx* c, double* u, const double* w, double s);
+int k_shell_bin(sww_ctx* c, const double2* T, const double2* const* G, int n_g, double scale, double* out_row);
+int k_symmetrise(sww_ctx* c, double* F, int n);
+int k_scale_c(sww_ctx* c, double2* x, double s, long long n);
+int k_paint(sww_ctx* c, const double* pos, const double* w, unsigned long long n, const double bc[3], int scheme,
+            double scale, double* out);

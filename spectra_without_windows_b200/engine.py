@@ -1,0 +1,306 @@
+"""Host-side engine: mesh geometry built with the reference's own expressions, and a thin
+object wrapper over the C ABI (libsww.so).  PyTorch is used only to own device buffers,
+pinned host buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_TORCH = None
+
+
+def torch():
+    global _TORCH
+    if _TORCH is None:
+        import torch as t
+        _TORCH = t
+    return _TORCH
+
+
+def signed_index(n):
+    """src/opt_utilities.py:422 -- `kkk-grid if kkk>=grid/2 else kkk`."""
+    i = np.arange(n)
+    return np.where(i >= n / 2, i - n, i)
+
+
+class Mesh:
+    """Geometry + binning of one (box, grid, BoxCenter, k-binning, lmax) configuration.
+
+    Everything that decides bin membership or enters at >1e-9 is evaluated here on the host
+    with the reference's expressions and uploaded as small 1-D tables:
+      kax  : src/opt_utilities.py:420-422         rax : src/opt_utilities.py:428-430
+      mas  : src/opt_utilities.py:448-463 (float32 pi/N prefactor)
+      edges: src/opt_utilities.py:485-487, n_k = int((k_max-k_min)/dk) (pk/compute_pk_randoms.py:197)
+    """
+
+    def __init__(self, box, grid, box_center, k_min, k_max, dk, lmax):
+        self.box = np.asarray(box, dtype=float)
+        self.grid = np.asarray(grid, dtype=int)
+        self.box_center = np.asarray(box_center, dtype=float)
+        self.k_min, self.k_max, self.dk, self.lmax = float(k_min), float(k_max), float(dk), int(lmax)
+        assert self.k_max > self.k_min and self.dk > 0 and self.k_min >= 0
+        assert (self.lmax // 2) * 2 == self.lmax, "l-max must be even!"
+        self.n_l = self.lmax // 2 + 1
+        self.n_k = int((self.k_max - self.k_min) / self.dk)
+        k_all = np.arange(self.k_min, self.k_max + self.dk, self.dk)
+        if len(k_all) - 1 < self.n_k:
+            raise Exception("k-binning yields fewer filters than n_k")
+        self.k_lo = np.ascontiguousarray(k_all[:-1][:self.n_k])
+        self.k_hi = np.ascontiguousarray(k_all[1:][:self.n_k])
+        kF = 2.0 * np.pi / (1.0 * self.box)
+        self.kF = kF
+        self.kax = [np.ascontiguousarray(signed_index(self.grid[i]) * kF[i], dtype=np.float64) for i in range(3)]
+        offset = self.box_center + 0.5 * self.box / self.grid
+        H = self.box / self.grid
+        self.rax = [np.ascontiguousarray((signed_index(self.grid[i]) * H[i]).astype("f8") + offset[i]) for i in range(3)]
+        prefact = np.pi / np.asarray(self.grid, dtype=np.float32)
+        self.mas = []
+        for i in range(3):
+            s = np.sin(prefact[i] * (self.kax[i] / kF[i])) ** 2.0
+            self.mas.append(np.ascontiguousarray(1.0 / (1.0 - s + 2.0 / 15 * s ** 2.0) ** 0.5, dtype=np.float64))
+        self.v_cell = 1.0 * self.box.prod() / (1.0 * self.grid.prod())
+        self.N = int(self.grid.prod())
+        self.nzh = int(self.grid[2]) // 2 + 1
+        self.Nc = int(self.grid[0]) * int(self.grid[1]) * self.nzh
+
+    @property
+    def shape(self):
+        return tuple(int(g) for g in self.grid)
+
+    @property
+    def cshape(self):
+        return (int(self.grid[0]), int(self.grid[1]), self.nzh)
+
+    def key(self):
+        return (tuple(self.box), tuple(self.grid), tuple(self.box_center), self.k_min, self.k_max, self.dk, self.lmax)
+
+    def triangles(self):
+        """Allowed (a<=b<=c) bin triplets -- test_bin of bk/compute_bk_randoms.py:186-211."""
+        k_lo = np.arange(self.k_min, self.k_max, self.dk)
+        k_hi = k_lo + self.dk
+        tol = 1e-6
+        out = []
+        for a in range(self.n_k):
+            for b in range(a, self.n_k):
+                for c in range(b, self.n_k):
+                    k_up = k_hi[a] + k_hi[b]
+                    k_do = 0.0 if a == b else k_lo[b] - k_hi[a]
+                    if k_lo[c] + tol >= k_up or k_hi[c] - tol <= k_do:
+                        continue
+                    out.append((a, b, c))
+        return out
+
+
+PIPELINES = {"ops": _lib.WS_OPS, "pk_fisher": _lib.WS_PK_FISHER, "pk_data": _lib.WS_PK_DATA,
+             "bk_fisher": _lib.WS_BK_FISHER, "bk_data": _lib.WS_BK_DATA}
+
+
+class Context:
+    """One libsww context on one GPU.  Owns (through torch) the single workspace the library
+    carves its buffers from, and keeps the n(r) maps alive while the library borrows them."""
+
+    def __init__(self, mesh: Mesh, device: int = 0, pipelines=("ops", "pk_fisher", "pk_data")):
+        t = torch()
+        self.lib = _lib.load()
+        if not t.cuda.is_available():
+            raise Exception("no CUDA device: spectra_without_windows_b200 has no CPU path")
+        self.mesh = mesh
+        self.device = t.device("cuda", device)
+        t.cuda.set_device(self.device)
+        g = _lib.Geometry()
+        g.grid[:] = [int(x) for x in mesh.grid]
+        g.box[:] = [float(x) for x in mesh.box]
+        g.lmax, g.n_k, g.device = mesh.lmax, mesh.n_k, device
+        as_p = lambda a: a.ctypes.data_as(_lib.pd)
+        g.k_lo, g.k_hi = as_p(mesh.k_lo), as_p(mesh.k_hi)
+        for i in range(3):
+            g.rax[i], g.kax[i], g.mas[i] = as_p(mesh.rax[i]), as_p(mesh.kax[i]), as_p(mesh.mas[i])
+        self._h = _lib.ctxp()
+        _lib.check(self.lib.sww_ctx_create(C.byref(g), C.byref(self._h)))
+        self.n_b = mesh.n_k * mesh.n_l
+        self._tris = None
+        if any(p.startswith("bk") for p in pipelines):
+            self.set_triangles(mesh.triangles())
+        need = 0
+        for p in pipelines:
+            b = _lib.u64(0)
+            _lib.check(self.lib.sww_workspace_bytes(self._h, PIPELINES[p], C.byref(b)))
+            need = max(need, b.value)
+        self.workspace = t.empty(int(need), dtype=t.uint8, device=self.device)
+        self.use_stream(t.cuda.current_stream(self.device))
+        _lib.check(self.lib.sww_bind_workspace(self._h, self.workspace.data_ptr(), int(need)))
+        self._fields = None
+
+    # -- plumbing
+    def use_stream(self, stream):
+        self.stream = stream
+        _lib.check(self.lib.sww_ctx_set_stream(self._h, stream.cuda_stream))
+
+    def close(self):
+        if self._h:
+            self.lib.sww_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dev(self, x, dtype=None):
+        """numpy / torch -> contiguous device tensor (float64 unless dtype given)."""
+        t = torch()
+        dtype = dtype or t.float64
+        if isinstance(x, t.Tensor):
+            return x.to(device=self.device, dtype=dtype).contiguous()
+        npd = {t.float64: np.float64, t.complex128: np.complex128, t.int32: np.int32}[dtype]
+        return t.from_numpy(np.ascontiguousarray(x, dtype=npd)).to(self.device)
+
+    def empty(self, shape, dtype=None):
+        t = torch()
+        return t.empty(shape, dtype=dtype or t.float64, device=self.device)
+
+    def zeros(self, shape, dtype=None):
+        t = torch()
+        return t.zeros(shape, dtype=dtype or t.float64, device=self.device)
+
+    def launch_counts(self):
+        a, b = _lib.u64(0), _lib.u64(0)
+        _lib.check(self.lib.sww_launch_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_fft_backend(self, backend: int):
+        _lib.check(self.lib.sww_set_fft_backend(self._h, int(backend)))
+
+    # -- fields
+    def set_fields(self, nbar, nbar_weight, nbar_A, shot_fac, P_fkp=1e4):
+        n, nw, nA = self.dev(nbar), self.dev(nbar_weight), self.dev(nbar_A)
+        self._fields = (n, nw, nA)
+        self.shot_fac, self.P_fkp = float(shot_fac), float(P_fkp)
+        _lib.check(self.lib.sww_set_fields(self._h, n.data_ptr(), nw.data_ptr(), nA.data_ptr(), float(shot_fac), float(P_fkp)))
+
+    def set_fields_from_randoms_density(self, nbar_r, alpha, shot_fac, P_fkp=1e4):
+        """The n(r) maps of the four scripts from the randoms-density map (load_nbar(...,1.)):
+        nbar = nbar_weight = alpha * nbar_r; nbar_A = nbar_r with empty cells set to
+        0.01 * min(nbar_r > 0)  (pk/compute_pk_randoms.py:135-136,160,173-179)."""
+        nbar_A = np.array(nbar_r, dtype=np.float64, copy=True)
+        nbar_A[nbar_A == 0] = min(nbar_A[nbar_A != 0]) * 0.01
+        nbar = nbar_r * alpha
+        self.set_fields(nbar, nbar.copy(), nbar_A, shot_fac, P_fkp)
+        return nbar_A
+
+    # -- P_l(k)
+    def pk_fisher(self, a, fish_out=None, qbar_out=None):
+        """One realisation -> (F [n_b,n_b] symmetrised, qbar [n_b]) on the device."""
+        a = self.dev(a)
+        F = fish_out if fish_out is not None else self.empty((self.n_b, self.n_b))
+        q = qbar_out if qbar_out is not None else self.empty((self.n_b,))
+        _lib.check(self.lib.sww_pk_fisher_realisation(self._h, a.data_ptr(), F.data_ptr(), q.data_ptr()))
+        return F, q
+
+    def pk_data_q(self, diff):
+        d = self.dev(diff)
+        q = self.empty((self.n_b,))
+        _lib.check(self.lib.sww_pk_data_q(self._h, d.data_ptr(), q.data_ptr()))
+        return q
+
+    # -- painting
+    def paint(self, pos, w, box_center, scheme="TSC", scale=1.0, out=None):
+        t = torch()
+        pos, w = self.dev(pos), self.dev(w)
+        if out is None:
+            out = self.zeros(self.mesh.shape)
+        bc = (C.c_double * 3)(*[float(x) for x in box_center])
+        _lib.check(self.lib.sww_paint(self._h, pos.data_ptr(), w.data_ptr(), int(w.numel()), bc,
+                                      3 if scheme.upper() == "TSC" else 2, float(scale), out.data_ptr()))
+        return out
+
+    def grid_data(self, dpos, dw, rpos, rw, box_center, return_randoms=False):
+        """(n_g - alpha n_r)/V_cell [and alpha n_r/V_cell]  (src/opt_utilities.py:228,257-267)."""
+        dw_h = np.asarray(dw, dtype=np.float64)
+        rw_h = np.asarray(rw, dtype=np.float64)
+        alpha = dw_h.sum() / rw_h.sum()
+        v = self.mesh.v_cell
+        rpos_d, rw_d = self.dev(rpos), self.dev(rw_h)
+        diff = self.paint(dpos, dw_h, box_center, scale=1.0 / v)
+        self.paint(rpos_d, rw_d, box_center, scale=-alpha / v, out=diff)
+        if return_randoms:
+            return diff, self.paint(rpos_d, rw_d, box_center, scale=alpha / v)
+        return diff
+
+    # -- operators (mirrors)
+    def fft_c2c(self, x, inverse=False):
+        t = torch()
+        x = self.dev(x, t.complex128)
+        out = t.empty_like(x)
+        _lib.check(self.lib.sww_fft_c2c(self._h, x.data_ptr(), out.data_ptr(), int(bool(inverse))))
+        return out
+
+    def fft_r2c(self, x):
+        t = torch()
+        x = self.dev(x)
+        out = t.empty(self.mesh.cshape, dtype=t.complex128, device=self.device)
+        _lib.check(self.lib.sww_fft_r2c(self._h, x.data_ptr(), out.data_ptr()))
+        return out
+
+    def fft_c2r(self, x):
+        t = torch()
+        x = self.dev(x, t.complex128).clone()
+        out = self.empty(self.mesh.shape)
+        _lib.check(self.lib.sww_fft_c2r(self._h, x.data_ptr(), out.data_ptr()))
+        return out
+
+    def apply_cinv_fkp(self, x, nbar_w, v_cell, shot_fac, P_fkp=1e4):
+        x, nw = self.dev(x), self.dev(nbar_w)
+        out = self.empty(self.mesh.shape)
+        _lib.check(self.lib.sww_apply_cinv_fkp(self._h, x.data_ptr(), nw.data_ptr(), v_cell, shot_fac, P_fkp, out.data_ptr()))
+        return out
+
+    def apply_n(self, x, nbar, v_cell, shot_fac):
+        x, n = self.dev(x), self.dev(nbar)
+        out = self.empty(self.mesh.shape)
+        _lib.check(self.lib.sww_apply_n(self._h, x.data_ptr(), n.data_ptr(), v_cell, shot_fac, out.data_ptr()))
+        return out
+
+    def ylm_project(self, x, mas_power=0):
+        t = torch()
+        x = self.dev(x)
+        out = t.empty((self.mesh.n_l,) + self.mesh.cshape, dtype=t.complex128, device=self.device)
+        _lib.check(self.lib.sww_ylm_project(self._h, x.data_ptr(), int(mas_power), out.data_ptr()))
+        return out
+
+    def apply_c_alpha_single(self, x, nbar, v_cell, l_i, a, data=False):
+        x, n = self.dev(x), self.dev(nbar)
+        out = self.empty(self.mesh.shape)
+        _lib.check(self.lib.sww_apply_c_alpha_single(self._h, x.data_ptr(), n.data_ptr(), float(v_cell), int(l_i),
+                                                     int(a), int(bool(data)), out.data_ptr()))
+        return out
+
+    def binmap(self):
+        t = torch()
+        out = t.empty(self.mesh.cshape, dtype=t.uint8, device=self.device)
+        _lib.check(self.lib.sww_get_binmap(self._h, out.data_ptr()))
+        return out
+
+    # -- B_l
+    def set_triangles(self, tris):
+        arr = np.ascontiguousarray(np.asarray(tris, dtype=np.int32).reshape(-1, 3))
+        self._tris = arr
+        self.n_tri = arr.shape[0]
+        self.n_b_bk = self.n_tri * self.mesh.n_l
+        _lib.check(self.lib.sww_bk_set_triangles(self._h, arr.ctypes.data_as(C.POINTER(_lib.i32)), arr.shape[0]))
+
+
+_CTX_CACHE = {}
+
+
+def get_context(mesh: Mesh, device=0, pipelines=("ops", "pk_fisher", "pk_data")) -> Context:
+    """Cached context per (geometry, device, pipelines)."""
+    k = (mesh.key(), device, tuple(pipelines))
+    if k not in _CTX_CACHE:
+        _CTX_CACHE[k] = Context(mesh, device, pipelines)
+    return _CTX_CACHE[k]
