@@ -1,0 +1,325 @@
+"""Benchmark of the P_l(k) Fisher Monte-Carlo hot path (BASELINE.json metric:
+"pk/bk Fisher MC realisations/s"), configuration C2 of SURVEY.md section 8d:
+compute_pk_randoms.py Fisher matrix, BOSS-like synthetic n(r), 512^3 mesh, l<=4, dk=0.005.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W    (CPU: the oracle port on host cores)
+
+A "step" is one Monte-Carlo realisation (one Gaussian field -> q-bar_alpha and F_ab).  Prints ONE
+JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: grid, box, box_center, (k_min, k_max, dk, lmax)
+    "C2": dict(grid=(512, 512, 512), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
+               bins=(0.0, 0.41, 0.005, 4)),
+    "C5": dict(grid=(1024, 1024, 1024), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
+               bins=(0.0, 0.40, 0.005, 4)),
+    "C1F": dict(grid=(128, 128, 128), box=(1000.0, 1000.0, 1000.0), box_center=(0.0, 0.0, 2000.0),
+                bins=(0.0, 0.25, 0.01, 4)),
+    "S256": dict(grid=(256, 256, 256), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
+                 bins=(0.0, 0.20, 0.005, 4)),
+}
+ALPHA, SHOT = 0.02, 1.02
+
+
+def survey_nbar_r(rax, xp):
+    """Randoms-density map of SURVEY.md section 8d (C2): n(r) W_ang(r^) / alpha.  `xp` is numpy or torch."""
+    X, Y, Z = xp.meshgrid(*rax, indexing="ij")
+    r = xp.sqrt(X * X + Y * Y + Z * Z)
+    lon = xp.arctan2(Y, X)
+    lat = xp.arcsin(Z / (r + 1e-300))
+    d70, d30 = np.deg2rad(70.0), np.deg2rad(30.0)
+    W = (abs(lon) < d70) * (abs(lat) < d30) * (0.9 + 0.1 * xp.cos(3.0 * lon))
+    n = 4e-4 * xp.exp(-0.5 * ((r - 1400.0) / 250.0) ** 2) * (r > 1150.0) * (r < 1750.0) * W
+    return n / ALPHA
+
+
+def uniform_nbar_r(rax, xp):
+    X, _, _ = xp.meshgrid(*rax, indexing="ij")
+    return X * 0.0 + 3e-4 / ALPHA
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def n_fft_min(M, n_b):
+    return 2 * M + 1 + 2 * n_b
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference algorithm on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import PkFisherSample
+    from spectra_without_windows_b200 import engine
+    wl = WORKLOADS[args.workload]
+    mesh = engine.Mesh(wl["box"], wl["grid"], wl["box_center"], *wl["bins"])
+    nb_fn = uniform_nbar_r if args.workload == "C1F" else survey_nbar_r
+    nbar = nb_fn(mesh.rax, np) * ALPHA
+    smp = PkFisherSample(wl["box"], wl["grid"], wl["box_center"], nbar, *wl["bins"])
+    for _ in range(args.warmup):
+        smp.sample()
+    ts = []
+    for _ in range(args.steps):
+        T, parts = smp.sample()
+        ts.append(T)
+    T = float(np.mean(ts))
+    val = 1.0 / T
+    line = {"impl": "reference", "metric": "pk Fisher MC realisations/s", "value": val, "unit": "realisations/s",
+            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": T * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, mesh),
+            "cpu_baseline": {"value": val, "unit": "realisations/s", "cores": smp.workers, "kind": "port",
+                             "sample": smp.describe(), "parts_s": parts},
+            "e2e": {"value": val, "unit": "realisations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(name, mesh):
+    return {"workload": "%s: compute_pk_randoms Fisher realisation, mesh %s, box %s, k in [%.3f,%.3f] dk=%.4f lmax=%d, n_b=%d, FKP weights"
+            % (name, "x".join(str(int(g)) for g in mesh.grid), "x".join("%g" % b for b in mesh.box), mesh.k_min, mesh.k_max,
+               mesh.dk, mesh.lmax, mesh.n_k * mesh.n_l),
+            "n_b": mesh.n_k * mesh.n_l, "n_fft_min_per_realisation": n_fft_min(sum(2 * l + 1 for l in range(0, mesh.lmax + 1, 2)), mesh.n_k * mesh.n_l),
+            "l2": "inputs>L2 (every map is >= 1 GB, L2 is 126 MB)" if mesh.N * 8 > 2 * 126e6 else "maps fit L2 partially; 512 MB scratch written between steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--fft", type=int, default=int(os.environ.get("SWW_FFT", "-1")), help="FFT backend: 0 cuFFT, 1 sm_100a passes")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from spectra_without_windows_b200 import engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise Exception("bench.py needs a CUDA device (no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    wl = WORKLOADS[args.workload]
+    mesh = engine.Mesh(wl["box"], wl["grid"], wl["box_center"], *wl["bins"])
+    ctx = engine.Context(mesh, local, ("pk_fisher",))
+    if args.fft >= 0:
+        ctx.set_fft_backend(args.fft)
+    rax_d = [torch.from_numpy(a).to(dev) for a in mesh.rax]
+    nb_fn = uniform_nbar_r if args.workload == "C1F" else survey_nbar_r
+    nbar_r = nb_fn(rax_d, torch).contiguous()
+    nbar = (nbar_r * ALPHA).contiguous()
+    nbar_A = nbar_r.clone()
+    nbar_A[nbar_A == 0] = float(nbar_r[nbar_r != 0].min()) * 0.01
+    ctx.set_fields(nbar, nbar, nbar_A, SHOT)
+    del rax_d
+    n_b = ctx.n_b
+    sig = torch.sqrt(nbar_A)
+
+    # synthetic Gaussian fields a ~ N(0, nbar_A) (pk/compute_pk_randoms.py:139-140), one per realisation;
+    # each rank draws its own independent realisations (seed offset by rank)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    nbuf = 2
+    a_dev = [torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig for _ in range(nbuf)]
+    F_acc = torch.zeros((n_b, n_b), dtype=torch.float64, device=dev)
+    q_acc = torch.zeros((n_b,), dtype=torch.float64, device=dev)
+    F_i = torch.empty_like(F_acc)
+    q_i = torch.empty_like(q_acc)
+    flush = None
+    if mesh.N * 8 <= 2 * 126e6:
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        ctx.pk_fisher(a_dev[i % nbuf], F_i, q_i)
+        F_acc.add_(F_i)
+        q_acc.add_(q_i)
+        if flush is not None:
+            flush.fill_(i & 255)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    own0, fft0 = ctx.launch_counts()
+    sampler = ClockSampler(local) if rank == 0 else None
+    F_acc.zero_()
+    q_acc.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    if world > 1:   # the only exchange of the path: partial Fisher / bias sums (pk/compute_pk_data.py:227-233)
+        dist.all_reduce(F_acc)
+        dist.all_reduce(q_acc)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    own1, fft1 = ctx.launch_counts()
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned): H2D of the field, D2H of F and q-bar
+    e2e = None
+    if not args.no_e2e:
+        a_host = [torch.empty(mesh.shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+        for h, d in zip(a_host, a_dev):
+            h.copy_(d)
+        F_host = torch.empty((n_b, n_b), dtype=torch.float64).pin_memory()
+        q_host = torch.empty((n_b,), dtype=torch.float64).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        main_stream = torch.cuda.current_stream(dev)
+
+        def e2e_run(n):
+            for j in range(2):
+                freed[j].record(main_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[0])
+                a_dev[0].copy_(a_host[0], non_blocking=True)
+                ready[0].record(copy_stream)
+            for i in range(n):
+                j = i % 2
+                if i + 1 < n:
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(freed[1 - j])
+                        a_dev[1 - j].copy_(a_host[1 - j], non_blocking=True)
+                        ready[1 - j].record(copy_stream)
+                main_stream.wait_event(ready[j])
+                ctx.pk_fisher(a_dev[j], F_i, q_i)
+                freed[j].record(main_stream)
+                F_host.copy_(F_i, non_blocking=True)
+                q_host.copy_(q_i, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_run(1)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(args.steps)
+        dt = time.perf_counter() - t0
+        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        dt = float(tdt.item())
+        e2e = {"value": world * args.steps / dt, "unit": "realisations/s", "h2d_bytes_per_step": int(mesh.N * 8),
+               "d2h_bytes_per_step": int((n_b * n_b + n_b) * 8), "note": "field H2D from pinned memory (double-buffered on a copy stream), F and q-bar D2H; host RNG not included"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        M = sum(2 * l + 1 for l in range(0, mesh.lmax + 1, 2))
+        nfft = n_fft_min(M, n_b)
+        b_alg = 16.0 * mesh.N * nfft            # bytes per realisation (SURVEY.md section 8d convention)
+        achieved = b_alg * (args.steps / (ms * 1e-3)) / 1e9   # per GPU
+        line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args.workload, mesh),
+                "fft_backend": "sm100a-passes" if args.fft == 1 else "cufft",
+                "gpu_launches": int((own1 - own0) + (fft1 - fft0)),
+                "own_kernel_launches": int(own1 - own0), "fft_calls": int(fft1 - fft0),
+                "clocks": clocks, "e2e": e2e,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                             "kernel": "whole realisation step: algorithmic bytes = 16 N x (2M+1+2n_b) = %.4g B per realisation" % b_alg}}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle.cpu_baseline import PkFisherSample
+                nbar_h = nbar.cpu().numpy()
+                smp = PkFisherSample(wl["box"], wl["grid"], wl["box_center"], nbar_h, *wl["bins"])
+                T, parts = smp.sample()
+                line["cpu_baseline"] = {"value": 1.0 / T, "unit": "realisations/s", "cores": smp.workers, "kind": "port",
+                                        "sample": smp.describe(), "parts_s": parts}
+            except Exception as ex:   # the baseline is a reported number, never a reason to lose the bench line
+                line["cpu_baseline"] = {"value": None, "error": repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,8 +14,8 @@
 static inline double lcoef(int l_i) { return 4.0 * M_PI / (4.0 * l_i + 1.0); }
 
 // sum_m Y_lm(k^) FT[f Y_lm(r^)] for every multipole; tmp: real scratch [N]; spec: complex scratch [Nc]
-static int ylm_project(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
-                       double2* spec, double2* const* out) {
+int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
+                             double2* spec, double2* const* out) {
   int lm = 0;
   for (int l_i = 0; l_i < c->n_l; ++l_i) {
     int nm = 4 * l_i + 1;
@@ -127,8 +127,8 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
   const double N = (double)c->g.N;
 
   SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS));
-  SWW_TRY(ylm_project(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
-  SWW_TRY(ylm_project(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
+  SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
+  SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
   // q-bar: one transform of W N A^-1 a, then one binning pass against F^C_l
   SWW_TRY(sww_r2c(c, b.WS, b.X));
   SWW_TRY(k_shell_bin(c, b.X, (const double2* const*)b.FC, n_l, 0.5 / N, qbar));
@@ -155,7 +155,7 @@ extern "C" int sww_pk_data_q(sww_ctx* c, sww_devptr diff_, sww_devptr q_out) {
   const double N = (double)c->g.N;
   // f = n C^-1 d
   SWW_TRY(k_cinv_fkp(c, (const double*)diff_, c->nbar_w, c->v_cell, c->shot, c->P_fkp, b.f, c->nbar));
-  SWW_TRY(ylm_project(c, b.f, 2, true, true, b.tmp, b.spec, b.FD));
+  SWW_TRY(sww_ylm_project_internal(c, b.f, 2, true, true, b.tmp, b.spec, b.FD));
   SWW_TRY(sww_r2c(c, b.f, b.R));
   SWW_TRY(k_shell_bin(c, b.R, (const double2* const*)b.FD, c->n_l, 0.5 / (N * c->v_cell), (double*)q_out));
   return 0;
@@ -200,7 +200,7 @@ extern "C" int sww_ylm_project(sww_ctx* c, sww_devptr x, int mas_power, sww_devp
   CHECK_ARENA(c);
   double2* outs[SWW_MAX_L];
   for (int l = 0; l < c->n_l; ++l) outs[l] = (double2*)out + (size_t)l * c->g.Nc;
-  return ylm_project(c, (const double*)x, mas_power, false, false, b.tmp, b.spec, outs);
+  return sww_ylm_project_internal(c, (const double*)x, mas_power, false, false, b.tmp, b.spec, outs);
 }
 
 extern "C" int sww_apply_c_alpha_single(sww_ctx* c, sww_devptr x, sww_devptr nbar, double v_cell, int l_i, int a,

@@ -304,3 +304,66 @@ def get_context(mesh: Mesh, device=0, pipelines=("ops", "pk_fisher", "pk_data"))
     if k not in _CTX_CACHE:
         _CTX_CACHE[k] = Context(mesh, device, pipelines)
     return _CTX_CACHE[k]
+
+
+def _bk_methods():
+    """B_l(k1,k2,k3) methods of Context (kept together; attached below)."""
+    t = torch
+
+    def bk_delta(self):
+        """Delta_abc [n_tri*n_l] (bk/compute_bk_randoms.py:427-473); cached per context."""
+        if getattr(self, "_delta", None) is None:
+            d = self.empty((self.n_b_bk,))
+            _lib.check(self.lib.sww_bk_delta(self._h, d.data_ptr()))
+            self._delta = d
+        return self._delta
+
+    def bk_gmaps(self, a, data=False):
+        """g_i^l (and tilde-g_i^l unless data) maps [n_l, n_k, nx, ny, nz] of one field."""
+        a = self.dev(a)
+        shp = (self.mesh.n_l, self.mesh.n_k) + self.mesh.shape
+        g = self.empty(shp)
+        tg = None if data else self.empty(shp)
+        _lib.check(self.lib.sww_bk_gmaps(self._h, a.data_ptr(), int(bool(data)), g.data_ptr(),
+                                         0 if data else tg.data_ptr()))
+        return g if data else (g, tg)
+
+    def bk_fisher_pair(self, aA, aB, maps=None):
+        """Fisher contribution of one pair of realisations -> (F [n_b,n_b], (gA,tgA,gB,tgB))."""
+        aA, aB = self.dev(aA), self.dev(aB)
+        shp = (self.mesh.n_l, self.mesh.n_k) + self.mesh.shape
+        if maps is None:
+            maps = tuple(self.empty(shp) for _ in range(4))
+        F = self.empty((self.n_b_bk, self.n_b_bk))
+        d = self.bk_delta()
+        _lib.check(self.lib.sww_bk_fisher_pair(self._h, aA.data_ptr(), aB.data_ptr(), d.data_ptr(), maps[0].data_ptr(),
+                                               maps[1].data_ptr(), maps[2].data_ptr(), maps[3].data_ptr(), F.data_ptr()))
+        return F, maps
+
+    def bk_q3(self, g):
+        q = self.empty((self.n_tri, self.mesh.n_l))
+        _lib.check(self.lib.sww_bk_q3(self._h, g.data_ptr(), q.data_ptr()))
+        return q
+
+    def bk_q1_accumulate(self, g, g_mc, tg_mc, N_mc, q):
+        g_mc, tg_mc = self.dev(g_mc), self.dev(tg_mc)
+        _lib.check(self.lib.sww_bk_q1_accumulate(self._h, g.data_ptr(), g_mc.data_ptr(), tg_mc.data_ptr(),
+                                                 0.5 / float(N_mc), q.data_ptr()))
+        return q
+
+    def gram(self, A, B, out=None, accumulate=False):
+        """C[i][j] = sum_x A[i][x] B[j][x] on the FP64 tensor cores."""
+        A, B = self.dev(A), self.dev(B)
+        m, n = A.shape[0], B.shape[0]
+        K = A[0].numel()
+        assert B[0].numel() == K
+        if out is None:
+            out = self.zeros((m, n))
+        _lib.check(self.lib.sww_gram_f64(self._h, A.data_ptr(), B.data_ptr(), m, n, K, int(bool(accumulate)), out.data_ptr()))
+        return out
+
+    for f in (bk_delta, bk_gmaps, bk_fisher_pair, bk_q3, bk_q1_accumulate, gram):
+        setattr(Context, f.__name__, f)
+
+
+_bk_methods()
