@@ -1,0 +1,14 @@
+"""Drop-in for the reference's bk/compute_bk_randoms.py: B_l Fisher matrix contribution of a pair of Gaussian realisations.
+
+    python bk/compute_bk_randoms.py <int> <paramfile>
+
+Same arguments, .param format, file names and output layout as the reference script; the body runs
+on the GPU through libsww.so (see spectra_without_windows_b200/drivers.py).
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.realpath(__file__)), ".."))
+from spectra_without_windows_b200.drivers import bk_randoms_main  # noqa: E402
+
+bk_randoms_main(sys.argv)
