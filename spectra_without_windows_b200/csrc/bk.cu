@@ -81,7 +81,6 @@ __global__ void assemble_kernel(Geo g, const double2* __restrict__ p0, int s0, c
     double kx = g.kax[0][ix], ky = g.kax[1][iy];
     for (int iz = threadIdx.x; iz < g.Kz; iz += blockDim.x) {
       int b = g.binmap[base + iz];
-      if (b == SWW_NO_BIN) continue;
       double2 acc = make_double2(0.0, 0.0);
       bool any = false;
       long long ci = row * g.Kz + iz;
@@ -103,7 +102,10 @@ __global__ void assemble_kernel(Geo g, const double2* __restrict__ p0, int s0, c
         acc.y += v.y;
         any = true;
       }
-      if (!any) continue;
+      if (!any) {   // every box cell is written, so the box never holds stale data
+        X[base + iz] = acc;
+        continue;
+      }
       double f = coef;
       if (lm >= 0) {
         double x, y, z;
@@ -324,6 +326,7 @@ static void bk_small_layout(sww_ctx* c, Arena& ar, BkBufs& b) {
   // Delta_abc scratch: n_k bin maps + up to 9 harmonic maps, and a compact unit spectrum
   b.Dt = ar.alloc<double>((size_t)(c->g.n_k + 9) * N);
   b.PS = ar.alloc<double2>(box_elems(c));
+  b.u = ar.alloc<double>(N);
 }
 
 size_t sww_bk_pipeline_bytes(sww_ctx* c, int what) {
@@ -373,6 +376,18 @@ static int gmaps(sww_ctx* c, BkBufs& b, const double* a, int data, double* g_out
     SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
     SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
   }
+  if (c->fft_backend == 1) {
+    for (int l = 0; l < c->n_l; ++l)
+      for (int i = 0; i < n_k; ++i) {
+        SWW_TRY(sww_sm100_inverse_box(c, b.FC[l], i, -1, nullptr, -1, invN, 0, g_out + ((size_t)l * n_k + i) * N));
+        c->n_fft++;
+        if (!data) {
+          SWW_TRY(sww_sm100_inverse_box(c, b.G[l], i, -1, nullptr, -1, invN, 0, tg_out + ((size_t)l * n_k + i) * N));
+          c->n_fft++;
+        }
+      }
+    return 0;
+  }
   for (int l = 0; l < c->n_l; ++l)
     for (int i = 0; i < n_k; ++i) {
       SWW_TRY(k_shell_fill(c, b.FC[l], i, 1.0, b.X));
@@ -399,8 +414,21 @@ extern "C" int sww_bk_gmaps(sww_ctx* c, sww_devptr a, int data, sww_devptr g_out
 
 static int assemble(sww_ctx* c, BkBufs& b, const double2* p0, int s0, const double2* p1, int s1, const double2* p2,
                     int s2, int lm, double coef) {
-  SWW_CUDA(cudaMemsetAsync(b.X, 0, sizeof(double2) * c->g.Nc, c->stream));
+  // the sm_100a inverse chain only reads the pruning box; cuFFT reads (and destroys) the whole array
+  if (c->fft_backend != 1) SWW_CUDA(cudaMemsetAsync(b.X, 0, sizeof(double2) * c->g.Nc, c->stream));
   assemble_kernel<<<SMS * 2, 64, 0, c->stream>>>(c->g, p0, s0, p1, s1, p2, s2, lm, coef, b.X);
+  return launch_ok(c);
+}
+
+// out (+)= invN * wmap * [Y_lm(r^)] * IFT[X]; box_shell bounds the shells present in X
+static int inverse_weighted(sww_ctx* c, BkBufs& b, int box_shell, const double* wmap, int lm, double scale, int first,
+                            double* out) {
+  if (c->fft_backend == 1) {
+    c->n_fft++;
+    return sww_sm100_inverse_box(c, b.X, -1, box_shell, wmap, lm, scale, first ? 0 : 1, out);
+  }
+  SWW_TRY(sww_c2r(c, b.X, b.u));
+  acc_real_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, b.u, wmap, lm, scale, first, out);
   return launch_ok(c);
 }
 
@@ -415,21 +443,15 @@ static int build_phi(sww_ctx* c, BkBufs& b, const PairTable& P, const double2* s
   auto spec = [&](int i, int j, int l) { return spectra + (size_t)P.get(i, j, l) * be; };
   if (l_i == 0) {
     SWW_TRY(assemble(c, b, spec(a, bb, 0), cc, spec(a, cc, 0), bb, spec(bb, cc, 0), a, -1, 1.0));
-    SWW_TRY(sww_c2r(c, b.X, b.u));
-    acc_real_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, b.u, wmap, -1, invN, 1, out);
-    return launch_ok(c);
+    return inverse_weighted(c, b, cc, wmap, -1, invN, 1, out);
   }
   SWW_TRY(assemble(c, b, spec(a, cc, l_i), bb, spec(bb, cc, l_i), a, nullptr, 0, -1, 1.0));
-  SWW_TRY(sww_c2r(c, b.X, b.u));
-  acc_real_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, b.u, wmap, -1, invN, 1, out);
-  SWW_TRY(launch_ok(c));
+  SWW_TRY(inverse_weighted(c, b, bb, wmap, -1, invN, 1, out));
   int lm0 = 0;
   for (int l = 0; l < l_i; ++l) lm0 += 4 * l + 1;
   for (int m = 0; m < 4 * l_i + 1; ++m) {
     SWW_TRY(assemble(c, b, spec(a, bb, 0), cc, nullptr, 0, nullptr, 0, lm0 + m, lcoef(l_i)));
-    SWW_TRY(sww_c2r(c, b.X, b.u));
-    acc_real_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, b.u, wmap, lm0 + m, invN, 0, out);
-    SWW_TRY(launch_ok(c));
+    SWW_TRY(inverse_weighted(c, b, cc, wmap, lm0 + m, invN, 0, out));
   }
   return 0;
 }
@@ -477,7 +499,14 @@ extern "C" int sww_bk_fisher_pair(sww_ctx* c, sww_devptr aA, sww_devptr aB, sww_
       size_t o1 = ((size_t)0 * n_k + P.i[s]) * N, o2 = ((size_t)P.l[s] * n_k + P.j[s]) * N;
       prod_diff_kernel<<<SMS * 8, 256, 0, c->stream>>>(c->g.N, XA + o1, XA + o2, XB + o1, XB + o2, b.tmp);
       SWW_TRY(launch_ok(c));
-      SWW_TRY(sww_r2c(c, b.tmp, b.X));
+      if (c->fft_backend == 1) {
+        F3Args A = {};
+        A.dst = b.X;
+        SWW_TRY(sww_sm100_forward_box(c, b.tmp, nullptr, -1, 0, A));
+        c->n_fft++;
+      } else {
+        SWW_TRY(sww_r2c(c, b.tmp, b.X));
+      }
       extract_box_kernel<<<SMS * 2, 64, 0, c->stream>>>(c->g, b.X, dst + (size_t)s * be);
       SWW_TRY(launch_ok(c));
     }
@@ -523,8 +552,7 @@ extern "C" int sww_bk_delta(sww_ctx* c, sww_devptr delta_out) {
   SWW_TRY(launch_ok(c));
   for (int a = 0; a < n_k; ++a) {
     SWW_TRY(assemble(c, b, b.PS, a, nullptr, 0, nullptr, 0, -1, 1.0));
-    SWW_TRY(sww_c2r(c, b.X, b.tmp));
-    SWW_TRY(k_mul(c, b.tmp, nullptr, invN, bins + (size_t)a * N));
+    SWW_TRY(inverse_weighted(c, b, a, nullptr, -1, invN, 1, bins + (size_t)a * N));
   }
   // sums needed: for every (l>0, triangle with b==c): N0 and N_l
   // results accumulate into a device vector S: [2 * nb]  (N0 at 2j, Nl at 2j+1)
@@ -542,8 +570,7 @@ extern "C" int sww_bk_delta(sww_ctx* c, sww_devptr delta_out) {
       // Dl_c[m] = IFT[Theta_c Y_lm(k^)]
       for (int m = 0; m < nm; ++m) {
         SWW_TRY(assemble(c, b, b.PS, cc, nullptr, 0, nullptr, 0, lm0 + m, 1.0));
-        SWW_TRY(sww_c2r(c, b.X, b.tmp));
-        SWW_TRY(k_mul(c, b.tmp, nullptr, invN, Dl + (size_t)m * N));
+        SWW_TRY(inverse_weighted(c, b, cc, nullptr, -1, invN, 1, Dl + (size_t)m * N));
       }
       TermBatcher tb(c, S);
       for (int t = 0; t < nt; ++t) {

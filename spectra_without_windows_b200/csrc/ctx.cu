@@ -141,7 +141,7 @@ extern "C" int sww_launch_counts(sww_ctx* c, uint64_t* own, uint64_t* fft) {
 extern "C" int sww_set_fft_backend(sww_ctx* c, int backend) {
   SWW_REQUIRE(c, "null context");
   SWW_REQUIRE(backend == 0 || backend == 1, "unknown FFT backend %d", backend);
-  if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes");
+  if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes (nx,ny in [64,1024], nz in [128,2048])");
   c->fft_backend = backend;
   return 0;
 }
@@ -170,6 +170,7 @@ extern "C" int sww_bind_workspace(sww_ctx* c, sww_devptr ws, uint64_t bytes) {
   c->persist_bytes = p;
   c->d_nW = (double*)ws;
   c->fft_work = (char*)ws + (((size_t)c->g.N * sizeof(double) + 255) & ~size_t(255));
+  c->fft_work_cap = c->fft_work_bytes;
   c->fields_dirty = true;
   SWW_TRY(sww_fft_bind_work(c));
   return 0;

@@ -16,6 +16,8 @@ int sww_fft_init(sww_ctx* c) {
   SWW_TRY(make_plan(&c->plan_d2z, c, CUFFT_D2Z, &w1));
   SWW_TRY(make_plan(&c->plan_z2d, c, CUFFT_Z2D, &w2));
   c->fft_work_bytes = w1 > w2 ? w1 : w2;
+  size_t w3 = sww_fft_sm100_work_bytes(c);
+  if (w3 > c->fft_work_bytes) c->fft_work_bytes = w3;
   return 0;
 }
 
@@ -35,6 +37,7 @@ void sww_fft_destroy(sww_ctx* c) {
   if (c->plan_d2z) cufftDestroy(c->plan_d2z);
   if (c->plan_z2d) cufftDestroy(c->plan_z2d);
   if (c->have_z2z) cufftDestroy(c->plan_z2z);
+  sww_fft_sm100_destroy(c);
 }
 
 int sww_fft_bind_work(sww_ctx* c) {

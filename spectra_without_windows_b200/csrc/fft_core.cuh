@@ -118,7 +118,6 @@ FFT_HD void stage_store(double2* tile, int N, int p, int bi, int c, const double
 
 // Radix plan: N = R0*R1*R2[*R3], radix 8 where possible.
 template <int N> struct FftPlan;
-template <> struct FftPlan<32>   { static constexpr int NS = 2; static constexpr int R[4] = {4, 8, 1, 1}; };
 template <> struct FftPlan<64>   { static constexpr int NS = 2; static constexpr int R[4] = {8, 8, 1, 1}; };
 template <> struct FftPlan<128>  { static constexpr int NS = 3; static constexpr int R[4] = {4, 4, 8, 1}; };
 template <> struct FftPlan<256>  { static constexpr int NS = 3; static constexpr int R[4] = {4, 8, 8, 1}; };

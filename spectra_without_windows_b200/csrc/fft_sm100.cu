@@ -1,12 +1,786 @@
-// Hand-written sm_100a 3-D FFT passes (power-of-two meshes).  Filled in after the cuFFT path.
-#include "sww_internal.cuh"
+// Hand-written sm_100a 3-D FFT passes (FP64, power-of-two meshes) with pruning and fused
+// prologue / epilogue work.  Replaces the cuFFT plans + separate element-wise kernels on the hot
+// loops (fft_backend = 1).
+//
+// A 3-D real<->half-spectrum transform is five passes over compact intermediates that only hold the
+// pruning box along the axes already (or still) in Fourier space:
+//
+//   inverse:  I1  x-axis  gather box modes from a spectrum [nx][ny][nzh] (optional shell filter Theta_a)
+//                         -> P [nx][Ky][Kzp]
+//             I2  y-axis  P -> Q [nx][ny][Kzp]
+//             Z   z-axis  complex-to-real of length nz through a half-length complex FFT
+//   forward:  Z   z-axis  real-to-complex, keeping only iz < Kz          -> R [nx][ny][Kzp]
+//             F2  y-axis  R -> P [nx][Ky][Kzp]   (only box rows are stored)
+//             F3  x-axis  P -> epilogue: store into a spectrum, accumulate Y_lm(k^)-weighted, or bin
+//                         conj(T) G_l' straight into the k-shell histogram (no spectrum is written)
+//
+// The fused P_l Fisher row is I1 -> I2 -> Z(c2r * nW * r2c in shared memory) -> F2 -> F3(bin): the
+// real-space map u_alpha and its weighted transform never touch HBM.
+#include <cmath>
+#include <vector>
 
-int sww_fft_sm100_supported(const sww_ctx* c) { return 0; }
-int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out) {
-  sww_set_error("sm_100a FFT backend not available for this mesh");
-  return -1;
+#include "fft_core.cuh"
+#include "sww_internal.cuh"
+#include "ylm_gen.cuh"
+
+#define SMS 148
+
+static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+int sww_fft_sm100_supported(const sww_ctx* c) {
+  const Geo& g = c->g;
+  auto ok = [](int n) { return is_pow2(n) && n >= 64 && n <= 1024; };
+  return ok(g.nx) && ok(g.ny) && ok(g.nz / 2) && is_pow2(g.nz);
 }
+
+// ------------------------------------------------------------------------------------------
+// tile FFT: all Stockham stages with CTA barriers.  Caller syncs after filling the tile.
+// ------------------------------------------------------------------------------------------
+template <int N, int DIR, int S, int P>
+struct TileStages {
+  static __device__ __forceinline__ void run(double2* tile, const double2* tw, int tid) {
+    if constexpr (S < FftPlan<N>::NS) {
+      constexpr int R = FftPlan<N>::R[S];
+      constexpr int NT = N / 2;
+      constexpr int IPT = (N / R) * FFT_TZ / NT;
+      double2 u[IPT][R];
+#pragma unroll
+      for (int s = 0; s < IPT; ++s) {
+        int w = tid + s * NT;
+        stage_load<R, DIR>(tile, N, P, w >> 3, w & 7, tw, u[s]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < IPT; ++s) {
+        int w = tid + s * NT;
+        stage_store<R>(tile, N, P, w >> 3, w & 7, u[s]);
+      }
+      __syncthreads();
+      TileStages<N, DIR, S + 1, P * R>::run(tile, tw, tid);
+    }
+  }
+};
+
+template <int N, int DIR>
+__device__ __forceinline__ void tile_fft(double2* tile, const double2* tw, int tid) {
+  TileStages<N, DIR, 0, 1>::run(tile, tw, tid);
+}
+
+struct BoxAxis {
+  int n, K, b;  // axis length, number of kept indices, last non-negative kept index
+  __host__ __device__ int idx(int j) const { return j <= b ? j : n - K + j; }
+  __host__ __device__ bool has(int i) const { return i <= b || i >= n - (K - b - 1); }
+  __host__ __device__ int pos(int i) const { return i <= b ? i : i - (n - K); }
+};
+
+// ------------------------------------------------------------------------------------------
+// I1: x-axis inverse.  Source: spectrum [nx][ny][nzh] restricted to the box; optional shell filter.
+// item = (jy, z-tile); output P[ix][jy][iz]  (pitch Kzp)
+// ------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(N / 2)
+pass_i1_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __restrict__ src, int shell,
+               const double2* __restrict__ twg, double2* __restrict__ P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);
+  double2* tw = tile + N * FFT_LDT;
+  const int tid = threadIdx.x;
+  constexpr int NT = N / 2;
+  for (int i = tid; i < N; i += NT) tw[i] = twg[i];
+  const int ztiles = Kzp / FFT_TZ;
+  const long long items = (long long)by.K * ztiles;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int jy = (int)(it / ztiles), zt = (int)(it - (long long)jy * ztiles);
+    const int iy = by.idx(jy), iz0 = zt * FFT_TZ;
+    __syncthreads();
+    for (int e = tid; e < N * FFT_TZ; e += NT) {
+      const int ix = e >> 3, cc = e & 7, iz = iz0 + cc;
+      double2 v = make_double2(0.0, 0.0);
+      if (bx.has(ix) && iz < Kz) {
+        long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
+        if (shell < 0 || g.binmap[cell] == shell) v = src[cell];
+      }
+      tile[ix * FFT_LDT + cc] = v;
+    }
+    __syncthreads();
+    tile_fft<N, -1>(tile, tw, tid);
+    for (int e = tid; e < N * FFT_TZ; e += NT) {
+      const int ix = e >> 3, cc = e & 7;
+      P[((long long)ix * by.K + jy) * Kzp + iz0 + cc] = tile[ix * FFT_LDT + cc];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// I2: y-axis inverse.  P[ix][jy][iz] -> Q[ix][iy][iz]; item = (ix, z-tile)
+// ------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(N / 2)
+pass_i2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ P, const double2* __restrict__ twg,
+               double2* __restrict__ Q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);
+  double2* tw = tile + N * FFT_LDT;
+  const int tid = threadIdx.x;
+  constexpr int NT = N / 2;
+  for (int i = tid; i < N; i += NT) tw[i] = twg[i];
+  const int ztiles = Kzp / FFT_TZ;
+  const long long items = (long long)nx * ztiles;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int ix = (int)(it / ztiles), zt = (int)(it - (long long)ix * ztiles);
+    const int iz0 = zt * FFT_TZ;
+    __syncthreads();
+    for (int e = tid; e < N * FFT_TZ; e += NT) {
+      const int iy = e >> 3, cc = e & 7;
+      double2 v = make_double2(0.0, 0.0);
+      if (by.has(iy)) v = P[((long long)ix * by.K + by.pos(iy)) * Kzp + iz0 + cc];
+      tile[iy * FFT_LDT + cc] = v;
+    }
+    __syncthreads();
+    tile_fft<N, -1>(tile, tw, tid);
+    for (int e = tid; e < N * FFT_TZ; e += NT) {
+      const int iy = e >> 3, cc = e & 7;
+      Q[((long long)ix * N + iy) * Kzp + iz0 + cc] = tile[iy * FFT_LDT + cc];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// F2: y-axis forward.  R[ix][iy][iz] -> P[ix][jy][iz] (box rows only); item = (ix, z-tile)
+// ------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(N / 2)
+pass_f2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ R, const double2* __restrict__ twg,
+               double2* __restrict__ P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);
+  double2* tw = tile + N * FFT_LDT;
+  const int tid = threadIdx.x;
+  constexpr int NT = N / 2;
+  for (int i = tid; i < N; i += NT) tw[i] = twg[i];
+  const int ztiles = Kzp / FFT_TZ;
+  const long long items = (long long)nx * ztiles;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int ix = (int)(it / ztiles), zt = (int)(it - (long long)ix * ztiles);
+    const int iz0 = zt * FFT_TZ;
+    __syncthreads();
+    for (int e = tid; e < N * FFT_TZ; e += NT) {
+      const int iy = e >> 3, cc = e & 7;
+      tile[iy * FFT_LDT + cc] = R[((long long)ix * N + iy) * Kzp + iz0 + cc];
+    }
+    __syncthreads();
+    tile_fft<N, 1>(tile, tw, tid);
+    for (int e = tid; e < by.K * FFT_TZ; e += NT) {
+      const int jy = e >> 3, cc = e & 7;
+      P[((long long)ix * by.K + jy) * Kzp + iz0 + cc] = tile[by.idx(jy) * FFT_LDT + cc];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// F3: x-axis forward + epilogue.  P[ix][jy][iz]; item = (jy, z-tile)
+//   MODE 0: dst[cell] = T                         (box cells of a spectrum [nx][ny][nzh])
+//   MODE 1: dst[cell] = (first ? 0 : dst[cell]) + Y_lm(k^) T ; on the last m: *= MAS^p * coef
+//   MODE 2: shell binning  hist[q*n_k + bin] += w_herm Re(conj(T) G_q[cell])   -> out row
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_f(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(N / 2)
+pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __restrict__ P,
+               const double2* __restrict__ twg, F3Args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);
+  double2* tw = tile + N * FFT_LDT;
+  double* hist = reinterpret_cast<double*>(tw + N);  // MODE 2: [nwarps][n_g*n_k]
+  __shared__ bool is_last;
+  const int tid = threadIdx.x;
+  constexpr int NT = N / 2;
+  constexpr int NW = NT / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nb = A.n_g * g.n_k;
+  for (int i = tid; i < N; i += NT) tw[i] = twg[i];
+  if (MODE == 2)
+    for (int i = tid; i < NW * nb; i += NT) hist[i] = 0.0;
+  const int ztiles = Kzp / FFT_TZ;
+  const long long items = (long long)by.K * ztiles;
+  const bool nz_even = (g.nz % 2) == 0;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int jy = (int)(it / ztiles), zt = (int)(it - (long long)jy * ztiles);
+    const int iy = by.idx(jy), iz0 = zt * FFT_TZ;
+    __syncthreads();
+    for (int e = tid; e < N * FFT_TZ; e += NT) {
+      const int ix = e >> 3, cc = e & 7;
+      tile[ix * FFT_LDT + cc] = P[((long long)ix * by.K + jy) * Kzp + iz0 + cc];
+    }
+    __syncthreads();
+    tile_fft<N, 1>(tile, tw, tid);
+    // epilogue over box rows (all threads run the same trip count so warp collectives are safe)
+    const int total = bx.K * FFT_TZ;
+    for (int e0 = 0; e0 < total; e0 += NT) {
+      const int e = e0 + tid;
+      const bool valid = e < total;
+      const int jx = e >> 3, cc = e & 7, iz = iz0 + cc;
+      const int ix = valid ? bx.idx(jx) : 0;
+      const bool inb = valid && iz < Kz;
+      const long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
+      if (MODE == 0) {
+        if (inb) A.dst[cell] = tile[ix * FFT_LDT + cc];
+      } else if (MODE == 1) {
+        if (inb) {
+          double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
+          double r = sqrt(kx * kx + ky * ky + kz * kz);
+          double inv = 1.0 / (1e-12 + r);
+          double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
+          double2 t = tile[ix * FFT_LDT + cc];
+          double2 o = A.first ? make_double2(0.0, 0.0) : A.dst[cell];
+          o.x += t.x * yk;
+          o.y += t.y * yk;
+          if (A.coef != 0.0) {
+            if (A.mas_power) {
+              double m = g.mas[0][ix] * g.mas[1][iy] * g.mas[2][iz];
+              if (A.mas_power == 2) m = m * m;
+              o.x *= m;
+              o.y *= m;
+            }
+            o.x *= A.coef;
+            o.y *= A.coef;
+          }
+          A.dst[cell] = o;
+        }
+      } else {
+        int b = SWW_NO_BIN;
+        double v[3] = {0.0, 0.0, 0.0};
+        if (inb) {
+          b = g.binmap[cell];
+          if (b != SWW_NO_BIN) {
+            double2 t = tile[ix * FFT_LDT + cc];
+            double w = (iz == 0 || (nz_even && iz == g.nz / 2)) ? 1.0 : 2.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (q < A.n_g) {
+                double2 G = A.G[q][cell];
+                v[q] = w * (t.x * G.x + t.y * G.y);
+              }
+          }
+        }
+        unsigned rem = __ballot_sync(0xffffffffu, b != SWW_NO_BIN);
+        while (rem) {
+          int srcl = __ffs(rem) - 1;
+          int cur = __shfl_sync(0xffffffffu, b, srcl);
+          bool mine = (b == cur);
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q < A.n_g) {
+              double s = warp_sum_f(mine ? v[q] : 0.0);
+              if (lane == 0) hist[warp * nb + q * g.n_k + cur] += s;
+            }
+          rem &= ~__ballot_sync(0xffffffffu, mine);
+        }
+      }
+    }
+  }
+  if (MODE == 2) {
+    __syncthreads();
+    for (int j = tid; j < nb; j += NT) {
+      double s = 0.0;
+      for (int w = 0; w < NW; ++w) s += hist[w * nb + j];
+      A.partial[(long long)blockIdx.x * nb + j] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      unsigned t = atomicAdd(A.counter, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      for (int j = tid; j < nb; j += NT) {
+        double s = 0.0;
+        for (unsigned bl = 0; bl < gridDim.x; ++bl) s += A.partial[(long long)bl * nb + j];
+        A.out_row[j] = s * A.scale;
+      }
+      if (tid == 0) *A.counter = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Z pass.  8 rows (ix, iy0..iy0+7) per tile, half-length H = nz/2 complex FFTs.
+//   INV: complex rows Q[row][0..Kz_in) (pitch Kzp_in)  -> real row x[0..nz)
+//   FWD: real row -> complex rows R[row][0..Kz_out) (pitch Kzp_out)
+//   INV && FWD: x * wmap * scale is transformed back without leaving shared memory
+//   INV only : real_out[row][z] = x * scale [* wmap] [* Y_lm(r^)]  (optionally accumulated)
+//   FWD only : x = real_in[row][z] [* wmap] [* Y_lm(r^)]
+// ------------------------------------------------------------------------------------------
+struct ZArgs {
+  const double2* Q;
+  int Kz_in, Kzp_in;
+  double2* R;
+  int Kz_out, Kzp_out;
+  const double* real_in;
+  double* real_out;
+  const double* wmap;
+  double scale;
+  int lm;          // >= 0: multiply the real row by Y_lm(r^)
+  int accumulate;  // INV only: real_out += ...
+};
+
+template <int H, bool INV, bool FWD>
+__global__ void __launch_bounds__(H / 2)
+pass_z_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);   // [H][9]
+  double2* twh = tile + H * FFT_LDT;                      // [H]    exp(-2 pi i j / H)
+  double2* twn = twh + H;                                 // [H+1]  exp(-2 pi i j / nz)
+  double2* stage = twn + (H + 8);                         // [8][H+9]
+  const int tid = threadIdx.x;
+  constexpr int NT = H / 2;
+  constexpr int SP = H + 9;  // staging pitch (odd: conflict-free transposed reads)
+  for (int i = tid; i < H; i += NT) twh[i] = twh_g[i];
+  for (int i = tid; i <= H; i += NT) twn[i] = twn_g[i];
+  const long long groups = (long long)g.nx * g.ny / FFT_TZ;
+  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const long long row0 = grp * FFT_TZ;  // rows row0 .. row0+7 share ix (ny is a multiple of 8)
+    __syncthreads();
+    if (INV) {
+      // stage the complex input rows
+      for (int e = tid; e < FFT_TZ * A.Kz_in; e += NT) {
+        int r = e / A.Kz_in, k = e - r * A.Kz_in;
+        stage[r * SP + k] = A.Q[(row0 + r) * A.Kzp_in + k];
+      }
+      __syncthreads();
+      // Y[k] = (Z[k] + conj Z[H-k]) + i (Z[k] - conj Z[H-k]) e^{+2 pi i k / nz}
+      for (int e = tid; e < H * FFT_TZ; e += NT) {
+        int k = e >> 3, r = e & 7;
+        double2 zk = (k < A.Kz_in) ? stage[r * SP + k] : make_double2(0.0, 0.0);
+        int hk = H - k;
+        double2 zh = (hk < A.Kz_in) ? stage[r * SP + hk] : make_double2(0.0, 0.0);
+        if (k == 0) {  // self-conjugate modes: imaginary parts are ignored (as cuFFT / np.real do)
+          zk.y = 0.0;
+          zh.y = 0.0;
+        }
+        double2 a = make_double2(zk.x + zh.x, zk.y - zh.y);
+        double2 d = make_double2(zk.x - zh.x, zk.y + zh.y);
+        double2 w = twn[k];
+        w.y = -w.y;
+        double2 b = c_mul(d, w);
+        tile[k * FFT_LDT + r] = make_double2(a.x - b.y, a.y + b.x);
+      }
+      __syncthreads();
+      tile_fft<H, -1>(tile, twh, tid);
+    }
+    // real-space stage: thread handles (m, r) with m fastest so that global rows are read contiguously
+    {
+      const int ix = (int)(row0 / g.ny);
+      const int iyb = (int)(row0 - (long long)ix * g.ny);
+      for (int e = tid; e < H * FFT_TZ; e += NT) {
+        int r = e / H, m = e - r * H;
+        long long off = (row0 + r) * g.nz + 2 * m;
+        double f0 = A.scale, f1 = A.scale;
+        if (A.wmap) {
+          double2 w = *reinterpret_cast<const double2*>(A.wmap + off);
+          f0 *= w.x;
+          f1 *= w.y;
+        }
+        if (A.lm >= 0) {
+          double X = g.rax[0][ix], Y = g.rax[1][iyb + r];
+          double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
+          double r0 = sqrt(X * X + Y * Y + Z0 * Z0), r1 = sqrt(X * X + Y * Y + Z1 * Z1);
+          double i0 = 1.0 / (1e-12 + r0), i1 = 1.0 / (1e-12 + r1);
+          f0 *= sww_ylm_dyn(A.lm, X * i0, Y * i0, Z0 * i0);
+          f1 *= sww_ylm_dyn(A.lm, X * i1, Y * i1, Z1 * i1);
+        }
+        if (INV) {
+          double2 y = tile[m * FFT_LDT + r];
+          y.x *= f0;
+          y.y *= f1;
+          if (FWD) {
+            tile[m * FFT_LDT + r] = y;
+          } else {
+            double2* dst = reinterpret_cast<double2*>(A.real_out + off);
+            if (A.accumulate) {
+              double2 o = *dst;
+              y.x += o.x;
+              y.y += o.y;
+            }
+            *dst = y;
+          }
+        } else {
+          double2 x = *reinterpret_cast<const double2*>(A.real_in + off);
+          tile[m * FFT_LDT + r] = make_double2(x.x * f0, x.y * f1);
+        }
+      }
+    }
+    if (FWD) {
+      __syncthreads();
+      tile_fft<H, 1>(tile, twh, tid);
+      // T[k] = 1/2 (V[k] + conj V[H-k]) - i/2 e^{-2 pi i k/nz} (V[k] - conj V[H-k]),  V[H] = V[0]
+      for (int e = tid; e < FFT_TZ * A.Kz_out; e += NT) {
+        int r = e / A.Kz_out, k = e - r * A.Kz_out;
+        int k1 = (k == H) ? 0 : k, k2 = (k == 0 || k == H) ? 0 : H - k;
+        double2 v1 = tile[k1 * FFT_LDT + r], v2 = tile[k2 * FFT_LDT + r];
+        double2 ev = make_double2(0.5 * (v1.x + v2.x), 0.5 * (v1.y - v2.y));
+        double2 dv = make_double2(0.5 * (v1.x - v2.x), 0.5 * (v1.y + v2.y));
+        double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);  // (-i dv) * e^{-2 pi i k/nz}
+        A.R[(row0 + r) * A.Kzp_out + k] = make_double2(ev.x + od.x, ev.y + od.y);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct Sm100State {
+  double2 *tw_x = nullptr, *tw_y = nullptr, *tw_h = nullptr, *tw_n = nullptr;
+  double2 *P = nullptr, *Q = nullptr, *R = nullptr;
+  size_t buf_elems = 0;
+  std::vector<int> shell_bx, shell_by, shell_bz;  // per-bin inverse boxes
+};
+
+static std::vector<double2> make_tw(int n, int count) {
+  std::vector<double2> t(count);
+  for (int j = 0; j < count; ++j) {
+    long double a = -2.0L * M_PIl * (long double)j / (long double)n;
+    t[j] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  return t;
+}
+
+static int up8(int k) { return (k + 7) & ~7; }
+
+size_t sww_fft_sm100_work_bytes(const sww_ctx* c) {
+  if (!sww_fft_sm100_supported(c)) return 0;
+  const Geo& g = c->g;
+  size_t e = (size_t)g.nx * g.ny * up8(g.nzh);
+  return 3 * e * sizeof(double2) + 1024;
+}
+
+static int max_abs_idx(const sww_ctx* c, int axis, double kmax) {
+  int n = axis == 0 ? c->g.nx : (axis == 1 ? c->g.ny : c->g.nz);
+  double kF = 2.0 * M_PI / c->box[axis];
+  int best = 0;
+  for (int i = 0; i <= n / 2; ++i)
+    if (i * kF < kmax) best = i;
+  return best;
+}
+
+int sww_fft_sm100_init(sww_ctx* c) {
+  if (c->sm100) return 0;
+  SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes (nx,ny in [64,1024], nz in [128,2048])");
+  Sm100State* s = new Sm100State();
+  const Geo& g = c->g;
+  const int H = g.nz / 2;
+  auto up = [&](const std::vector<double2>& h, double2** d) -> int {
+    SWW_CUDA(cudaMalloc(d, h.size() * sizeof(double2)));
+    SWW_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  SWW_TRY(up(make_tw(g.nx, g.nx), &s->tw_x));
+  SWW_TRY(up(make_tw(g.ny, g.ny), &s->tw_y));
+  SWW_TRY(up(make_tw(H, H), &s->tw_h));
+  SWW_TRY(up(make_tw(g.nz, H + 1), &s->tw_n));
+  for (int a = 0; a < g.n_k; ++a) {
+    s->shell_bx.push_back(max_abs_idx(c, 0, c->h_khi[a]));
+    s->shell_by.push_back(max_abs_idx(c, 1, c->h_khi[a]));
+    s->shell_bz.push_back(max_abs_idx(c, 2, c->h_khi[a]));
+  }
+  c->sm100 = s;
+  return 0;
+}
+
+void sww_fft_sm100_destroy(sww_ctx* c) {
+  Sm100State* s = (Sm100State*)c->sm100;
+  if (!s) return;
+  cudaFree(s->tw_x);
+  cudaFree(s->tw_y);
+  cudaFree(s->tw_h);
+  cudaFree(s->tw_n);
+  delete s;
+  c->sm100 = nullptr;
+}
+
+static int bind_bufs(sww_ctx* c, Sm100State* s) {
+  SWW_REQUIRE(c->fft_work, "no workspace bound (sww_bind_workspace)");
+  size_t e = (size_t)c->g.nx * c->g.ny * up8(c->g.nzh);
+  SWW_REQUIRE(c->fft_work_cap >= 3 * e * sizeof(double2),
+              "workspace was sized before the sm_100a FFT backend was selected; select it before binding");
+  s->P = (double2*)c->fft_work;
+  s->Q = s->P + e;
+  s->R = s->Q + e;
+  s->buf_elems = e;
+  return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) SWW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+static inline int grid_for_items(long long items, int per_sm) {
+  long long g = (long long)SMS * per_sm;
+  return (int)(items < g ? items : g);
+}
+
+#define DISPATCH_N(n, MACRO)                                         \
+  switch (n) {                                                       \
+    case 64: MACRO(64); break;                                       \
+    case 128: MACRO(128); break;                                     \
+    case 256: MACRO(256); break;                                     \
+    case 512: MACRO(512); break;                                     \
+    case 1024: MACRO(1024); break;                                   \
+    default: SWW_REQUIRE(false, "unsupported FFT length %d", n);     \
+  }
+
+static size_t col_smem(int N, int hist_doubles) {
+  return (size_t)N * FFT_LDT * 16 + (size_t)N * 16 + (size_t)hist_doubles * 8;
+}
+static size_t z_smem(int H) { return (size_t)H * FFT_LDT * 16 + (size_t)H * 16 + (size_t)(H + 8) * 16 + (size_t)8 * (H + 9) * 16; }
+
+static int occ_for(size_t smem) {
+  int o = (int)((220 * 1024) / (smem + 1024));
+  if (o < 1) o = 1;
+  if (o > 4) o = 4;
+  return o;
+}
+
+static int run_i1(sww_ctx* c, Sm100State* s, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* src, int shell) {
+  const int N = c->g.nx;
+  size_t smem = col_smem(N, 0);
+  long long items = (long long)by.K * (Kzp / FFT_TZ);
+  int grid = grid_for_items(items, occ_for(smem));
+#define M(NN)                                                                                             \
+  SWW_TRY(set_smem(pass_i1_kernel<NN>, smem));                                                            \
+  pass_i1_kernel<NN><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, src, shell, s->tw_x, s->P);
+  DISPATCH_N(N, M)
+#undef M
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int run_i2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
+  const int N = c->g.ny;
+  size_t smem = col_smem(N, 0);
+  long long items = (long long)c->g.nx * (Kzp / FFT_TZ);
+  int grid = grid_for_items(items, occ_for(smem));
+#define M(NN)                                                 \
+  SWW_TRY(set_smem(pass_i2_kernel<NN>, smem));                \
+  pass_i2_kernel<NN><<<grid, NN / 2, smem, c->stream>>>(c->g.nx, by, Kzp, s->P, s->tw_y, s->Q);
+  DISPATCH_N(N, M)
+#undef M
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int run_f2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
+  const int N = c->g.ny;
+  size_t smem = col_smem(N, 0);
+  long long items = (long long)c->g.nx * (Kzp / FFT_TZ);
+  int grid = grid_for_items(items, occ_for(smem));
+#define M(NN)                                                 \
+  SWW_TRY(set_smem(pass_f2_kernel<NN>, smem));                \
+  pass_f2_kernel<NN><<<grid, NN / 2, smem, c->stream>>>(c->g.nx, by, Kzp, s->R, s->tw_y, s->P);
+  DISPATCH_N(N, M)
+#undef M
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int run_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bx, BoxAxis by, int Kz, int Kzp, F3Args A) {
+  const int N = c->g.nx;
+  int hist = (mode == 2) ? (N / 2 / 32) * A.n_g * c->g.n_k : 0;
+  size_t smem = col_smem(N, hist);
+  long long items = (long long)by.K * (Kzp / FFT_TZ);
+  int grid = grid_for_items(items, occ_for(smem));
+  if (mode == 2) {
+    SWW_REQUIRE((size_t)grid * A.n_g * c->g.n_k <= c->partial_elems, "F3 bin: partial buffer too small");
+    A.partial = c->d_partial;
+    A.counter = c->d_counter;
+  }
+#define M(NN)                                                                                                    \
+  if (mode == 0) {                                                                                               \
+    SWW_TRY(set_smem(pass_f3_kernel<NN, 0>, smem));                                                              \
+    pass_f3_kernel<NN, 0><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, s->P, s->tw_x, A);           \
+  } else if (mode == 1) {                                                                                        \
+    SWW_TRY(set_smem(pass_f3_kernel<NN, 1>, smem));                                                              \
+    pass_f3_kernel<NN, 1><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, s->P, s->tw_x, A);           \
+  } else {                                                                                                       \
+    SWW_TRY(set_smem(pass_f3_kernel<NN, 2>, smem));                                                              \
+    pass_f3_kernel<NN, 2><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, s->P, s->tw_x, A);           \
+  }
+  DISPATCH_N(N, M)
+#undef M
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
+  const int H = c->g.nz / 2;
+  size_t smem = z_smem(H);
+  long long groups = (long long)c->g.nx * c->g.ny / FFT_TZ;
+  int grid = grid_for_items(groups, occ_for(smem));
+#define M(HH)                                                                                    \
+  if (inv && fwd) {                                                                              \
+    SWW_TRY(set_smem(pass_z_kernel<HH, true, true>, smem));                                      \
+    pass_z_kernel<HH, true, true><<<grid, HH / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n); \
+  } else if (inv) {                                                                              \
+    SWW_TRY(set_smem(pass_z_kernel<HH, true, false>, smem));                                     \
+    pass_z_kernel<HH, true, false><<<grid, HH / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n); \
+  } else {                                                                                       \
+    SWW_TRY(set_smem(pass_z_kernel<HH, false, true>, smem));                                     \
+    pass_z_kernel<HH, false, true><<<grid, HH / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n); \
+  }
+  DISPATCH_N(H, M)
+#undef M
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static BoxAxis full_axis(int n) { return BoxAxis{n, n, n - 1}; }
+static BoxAxis box_axis(int n, int b) {
+  int K = 2 * b + 1;
+  if (K >= n) return full_axis(n);
+  return BoxAxis{n, K, b};
+}
+
+static int get_state(sww_ctx* c, Sm100State** out) {
+  SWW_TRY(sww_fft_sm100_init(c));
+  Sm100State* s = (Sm100State*)c->sm100;
+  SWW_TRY(bind_bufs(c, s));
+  *out = s;
+  return 0;
+}
+
+// ---- generic transforms (full box): used by every pipeline when fft_backend == 1 ----
+int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  const Geo& g = c->g;
+  BoxAxis bx = full_axis(g.nx), by = full_axis(g.ny);
+  int Kz = g.nzh, Kzp = up8(Kz);
+  ZArgs Z = {};
+  Z.R = s->R;
+  Z.Kz_out = Kz;
+  Z.Kzp_out = Kzp;
+  Z.real_in = in;
+  Z.scale = 1.0;
+  Z.lm = -1;
+  SWW_TRY(run_z(c, s, false, true, Z));
+  SWW_TRY(run_f2(c, s, by, Kzp));
+  F3Args A = {};
+  A.dst = out;
+  return run_f3(c, s, 0, bx, by, Kz, Kzp, A);
+}
+
 int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out) {
-  sww_set_error("sm_100a FFT backend not available for this mesh");
-  return -1;
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  const Geo& g = c->g;
+  BoxAxis bx = full_axis(g.nx), by = full_axis(g.ny);
+  int Kz = g.nzh, Kzp = up8(Kz);
+  SWW_TRY(run_i1(c, s, bx, by, Kz, Kzp, in, -1));
+  SWW_TRY(run_i2(c, s, by, Kzp));
+  ZArgs Z = {};
+  Z.Q = s->Q;
+  Z.Kz_in = Kz;
+  Z.Kzp_in = Kzp;
+  Z.real_out = out;
+  Z.scale = 1.0;
+  Z.lm = -1;
+  return run_z(c, s, true, false, Z);
+}
+
+// ---- pruned / fused chains ----
+// forward transform of (real_in * wmap * Y_lm(r^)) restricted to the k_max box, F3 epilogue `mode`
+int sww_sm100_forward_box(sww_ctx* c, const double* real_in, const double* wmap, int lm_r, int mode, F3Args A) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  const Geo& g = c->g;
+  BoxAxis bx = box_axis(g.nx, g.bx), by = box_axis(g.ny, g.by);
+  int Kz = g.Kz, Kzp = up8(Kz);
+  ZArgs Z = {};
+  Z.R = s->R;
+  Z.Kz_out = Kz;
+  Z.Kzp_out = Kzp;
+  Z.real_in = real_in;
+  Z.wmap = wmap;
+  Z.scale = 1.0;
+  Z.lm = lm_r;
+  SWW_TRY(run_z(c, s, false, true, Z));
+  SWW_TRY(run_f2(c, s, by, Kzp));
+  return run_f3(c, s, mode, bx, by, Kz, Kzp, A);
+}
+
+// inverse transform of the box part of `src` (optionally only shell `shell`) into a real map:
+// real_out (+)= scale * wmap * Y_lm(r^) * IFT[...]
+int sww_sm100_inverse_box(sww_ctx* c, const double2* src, int shell, int box_shell, const double* wmap, int lm_r,
+                          double scale, int accumulate, double* real_out) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  const Geo& g = c->g;
+  int b_x = g.bx, b_y = g.by, b_z = g.bz;
+  if (shell >= 0 && box_shell < 0) box_shell = shell;
+  if (box_shell >= 0) {
+    b_x = s->shell_bx[box_shell];
+    b_y = s->shell_by[box_shell];
+    b_z = s->shell_bz[box_shell];
+  }
+  BoxAxis bx = box_axis(g.nx, b_x), by = box_axis(g.ny, b_y);
+  int Kz = b_z + 1 < g.nzh ? b_z + 1 : g.nzh, Kzp = up8(Kz);
+  SWW_TRY(run_i1(c, s, bx, by, Kz, Kzp, src, shell));
+  SWW_TRY(run_i2(c, s, by, Kzp));
+  ZArgs Z = {};
+  Z.Q = s->Q;
+  Z.Kz_in = Kz;
+  Z.Kzp_in = Kzp;
+  Z.real_out = real_out;
+  Z.wmap = wmap;
+  Z.scale = scale;
+  Z.lm = lm_r;
+  Z.accumulate = accumulate;
+  return run_z(c, s, true, false, Z);
+}
+
+// fused P_l Fisher row: out_row[q*n_k + b] = scale * sum_{k in b} w Re[conj(FT[wmap * IFT[Theta_a F]]) G_q]
+int sww_sm100_pk_row(sww_ctx* c, const double2* F, int shell, const double* wmap, double inv_scale,
+                     const double2* const* G, int n_g, double scale, double* out_row) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  const Geo& g = c->g;
+  BoxAxis bxi = box_axis(g.nx, s->shell_bx[shell]), byi = box_axis(g.ny, s->shell_by[shell]);
+  int Kzi = s->shell_bz[shell] + 1, Kzpi = up8(Kzi);
+  BoxAxis bxo = box_axis(g.nx, g.bx), byo = box_axis(g.ny, g.by);
+  int Kzo = g.Kz, Kzpo = up8(Kzo);
+  SWW_TRY(run_i1(c, s, bxi, byi, Kzi, Kzpi, F, shell));
+  SWW_TRY(run_i2(c, s, byi, Kzpi));
+  ZArgs Z = {};
+  Z.Q = s->Q;
+  Z.Kz_in = Kzi;
+  Z.Kzp_in = Kzpi;
+  Z.R = s->R;
+  Z.Kz_out = Kzo;
+  Z.Kzp_out = Kzpo;
+  Z.wmap = wmap;
+  Z.scale = inv_scale;
+  Z.lm = -1;
+  SWW_TRY(run_z(c, s, true, true, Z));
+  SWW_TRY(run_f2(c, s, byo, Kzpo));
+  F3Args A = {};
+  for (int q = 0; q < n_g; ++q) A.G[q] = G[q];
+  A.n_g = n_g;
+  A.scale = scale;
+  A.out_row = out_row;
+  return run_f3(c, s, 2, bxo, byo, Kzo, Kzpo, A);
 }

@@ -17,6 +17,23 @@ static inline double lcoef(int l_i) { return 4.0 * M_PI / (4.0 * l_i + 1.0); }
 int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
                              double2* spec, double2* const* out) {
   int lm = 0;
+  if (c->fft_backend == 1 && pruned) {
+    // fused: Y_lm(r^) on the load of the z pass, Y_lm(k^) accumulation in the x-pass epilogue
+    for (int l_i = 0; l_i < c->n_l; ++l_i) {
+      int nm = 4 * l_i + 1;
+      for (int m = 0; m < nm; ++m, ++lm) {
+        F3Args A = {};
+        A.dst = out[l_i];
+        A.lm = lm;
+        A.first = (m == 0);
+        A.mas_power = mas_power;
+        A.coef = (m == nm - 1) ? (with_coef ? lcoef(l_i) : 1.0) : 0.0;
+        SWW_TRY(sww_sm100_forward_box(c, f, nullptr, lm, 1, A));
+        c->n_fft++;
+      }
+    }
+    return 0;
+  }
   for (int l_i = 0; l_i < c->n_l; ++l_i) {
     int nm = 4 * l_i + 1;
     for (int m = 0; m < nm; ++m, ++lm) {
@@ -130,6 +147,24 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
   SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
   SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
   // q-bar: one transform of W N A^-1 a, then one binning pass against F^C_l
+  if (c->fft_backend == 1) {
+    F3Args A = {};
+    for (int q = 0; q < n_l; ++q) A.G[q] = b.FC[q];
+    A.n_g = n_l;
+    A.scale = 0.5 / N;
+    A.out_row = qbar;
+    SWW_TRY(sww_sm100_forward_box(c, b.WS, nullptr, -1, 2, A));
+    c->n_fft++;
+    // Fisher rows: I1 -> I2 -> Z(c2r * nW * r2c) -> F2 -> F3(bin); nothing but the row leaves the chip
+    for (int alpha = 0; alpha < n_b; ++alpha) {
+      int l_i = alpha / n_k, ka = alpha % n_k;
+      SWW_TRY(sww_sm100_pk_row(c, b.FC[l_i], ka, c->d_nW, 1.0 / N, (const double2* const*)b.G, n_l,
+                               0.5 / (N * c->v_cell), F + (size_t)alpha * n_b));
+      c->n_fft += 2;
+    }
+    SWW_TRY(k_symmetrise(c, F, n_b));
+    return 0;
+  }
   SWW_TRY(sww_r2c(c, b.WS, b.X));
   SWW_TRY(k_shell_bin(c, b.X, (const double2* const*)b.FC, n_l, 0.5 / N, qbar));
   // Fisher rows
@@ -156,6 +191,15 @@ extern "C" int sww_pk_data_q(sww_ctx* c, sww_devptr diff_, sww_devptr q_out) {
   // f = n C^-1 d
   SWW_TRY(k_cinv_fkp(c, (const double*)diff_, c->nbar_w, c->v_cell, c->shot, c->P_fkp, b.f, c->nbar));
   SWW_TRY(sww_ylm_project_internal(c, b.f, 2, true, true, b.tmp, b.spec, b.FD));
+  if (c->fft_backend == 1) {
+    F3Args A = {};
+    for (int q = 0; q < c->n_l; ++q) A.G[q] = b.FD[q];
+    A.n_g = c->n_l;
+    A.scale = 0.5 / (N * c->v_cell);
+    A.out_row = (double*)q_out;
+    c->n_fft++;
+    return sww_sm100_forward_box(c, b.f, nullptr, -1, 2, A);
+  }
   SWW_TRY(sww_r2c(c, b.f, b.R));
   SWW_TRY(k_shell_bin(c, b.R, (const double2* const*)b.FD, c->n_l, 0.5 / (N * c->v_cell), (double*)q_out));
   return 0;
@@ -221,6 +265,10 @@ extern "C" int sww_apply_c_alpha_single(sww_ctx* c, sww_devptr x, sww_devptr nba
     SWW_TRY(sww_r2c(c, b.tmp, b.spec));
     double coef = (m == nm - 1) ? lcoef(l_i) : 0.0;
     SWW_TRY(k_acc_ylm_k(c, b.spec, lm0 + m, coef, data ? 2 : 0, m == 0, 1, b.F[0]));
+  }
+  if (c->fft_backend == 1) {
+    c->n_fft++;
+    return sww_sm100_inverse_box(c, b.F[0], a, -1, (const double*)nbar, -1, 1.0 / ((double)c->g.N * v_cell), 0, (double*)out);
   }
   SWW_TRY(k_shell_fill(c, b.F[0], a, 1.0, b.spec));
   SWW_TRY(sww_c2r(c, b.spec, b.tmp));

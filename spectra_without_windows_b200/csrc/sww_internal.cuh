@@ -101,7 +101,9 @@ struct sww_ctx {
   size_t persist_bytes = 0;   // [nW map][cufft work area] at the front of the workspace
   double* d_nW = nullptr;     // n * W  with W = n/(n_w (n_w P + s)) [n_w>0]
   void* fft_work = nullptr;
-  size_t fft_work_bytes = 0;
+  size_t fft_work_bytes = 0;   // bytes reserved for FFT scratch (cuFFT work area or the sm_100a pass buffers)
+  size_t fft_work_cap = 0;
+  void* sm100 = nullptr;       // Sm100State (fft_sm100.cu)
   // cuFFT
   cufftHandle plan_d2z = 0, plan_z2d = 0, plan_z2z = 0;
   bool have_z2z = false;
@@ -135,6 +137,24 @@ int sww_c2c(sww_ctx* c, const double2* in, double2* out, int inverse);
 int sww_fft_sm100_supported(const sww_ctx* c);
 int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out);
 int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out);
+size_t sww_fft_sm100_work_bytes(const sww_ctx* c);
+void sww_fft_sm100_destroy(sww_ctx* c);
+struct F3Args {
+  double2* dst;
+  int lm, first, mas_power;
+  double coef;
+  const double2* G[3];
+  int n_g;
+  double scale;
+  double* partial;
+  unsigned int* counter;
+  double* out_row;
+};
+int sww_sm100_forward_box(sww_ctx* c, const double* real_in, const double* wmap, int lm_r, int mode, F3Args A);
+int sww_sm100_inverse_box(sww_ctx* c, const double2* src, int filter_shell, int box_shell, const double* wmap, int lm_r,
+                          double scale, int accumulate, double* real_out);
+int sww_sm100_pk_row(sww_ctx* c, const double2* F, int shell, const double* wmap, double inv_scale,
+                     const double2* const* G, int n_g, double scale, double* out_row);
 
 // ---- kernels.cu (launch wrappers)
 int k_build_binmap(sww_ctx* c);

@@ -111,6 +111,7 @@ def make_world(name: str) -> World:
     toyA : 32x24x20 non-cubic mesh, masked n(r) with empty cells, weighted catalogues.
     toyB : 32^3 cubic power-of-two mesh, uniform n(r)   (exercises the custom FFT path)
     toyC : 20x18x15 mesh with an odd last axis (no Nyquist plane on z)
+    toyD : 64x64x128 power-of-two mesh, masked n(r)   (exercises the hand-written FFT passes)
     """
     if name == "toyA":
         grid, box, bc = (32, 24, 20), (640.0, 480.0, 400.0), (900.0, 40.0, -30.0)
@@ -124,6 +125,10 @@ def make_world(name: str) -> World:
         grid, box, bc = (20, 18, 15), (400.0, 360.0, 300.0), (700.0, -20.0, 35.0)
         pk_bins, bk_bins = (0.01, 0.13, 0.03, 2), (0.01, 0.10, 0.03, 2)
         ng, seed = 2500, 31
+    elif name == "toyD":   # smallest mesh the hand-written sm_100a FFT passes accept (64 x 64 x 128)
+        grid, box, bc = (64, 64, 128), (1280.0, 1408.0, 2560.0), (1700.0, 60.0, -45.0)
+        pk_bins, bk_bins = (0.0, 0.12, 0.02, 4), (0.0, 0.08, 0.02, 2)
+        ng, seed = 30000, 41
     else:
         raise Exception("unknown world '%s'" % name)
     rng = np.random.default_rng(seed)

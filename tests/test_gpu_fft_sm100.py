@@ -1,0 +1,106 @@
+"""The hand-written sm_100a FFT passes (fft_backend=1): generic transforms against numpy, and
+every pipeline re-run on the fused / pruned chains against the reference goldens (1e-9)."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from spectra_without_windows_b200 import engine
+    return engine
+
+
+def ctx_for(eng, w, which, pipelines):
+    kmin, kmax, dk, lmax = w.pk_bins if which == "pk" else w.bk_bins
+    mesh = eng.Mesh(w.box, w.grid, w.box_center, kmin, kmax, dk, lmax)
+    ctx = eng.Context(mesh, 0, pipelines)
+    ctx.set_fft_backend(1)
+    ctx.set_fields_from_randoms_density(w.nbar_r, w.alpha, w.shot_fac)
+    return mesh, ctx
+
+
+def oracle_setup(w, which):
+    from oracle import sww_oracle as orc
+    kmin, kmax, dk, lmax = w.pk_bins if which == "pk" else w.bk_bins
+    return orc, orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax)
+
+
+def test_backend_rejects_unsupported_mesh(eng, world):
+    w = world("toyA")
+    mesh = eng.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    ctx = eng.get_context(mesh, 0, ("ops", "pk_fisher", "pk_data"))
+    with pytest.raises(Exception, match="power-of-two"):
+        ctx.set_fft_backend(1)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 128), (128, 64, 256), (64, 256, 128)])
+def test_generic_transforms(eng, shape):
+    box = tuple(20.0 * s for s in shape)
+    mesh = eng.Mesh(box, shape, (0.0, 0.0, 0.0), 0.0, 0.1, 0.05, 0)
+    ctx = eng.Context(mesh, 0, ("ops",))
+    ctx.set_fft_backend(1)
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=shape)
+    X = ctx.fft_r2c(x).cpu().numpy()
+    ref = np.fft.rfftn(x)
+    assert relerr(X, ref) < 1e-13
+    back = ctx.fft_c2r(ref).cpu().numpy()
+    assert relerr(back, x) < 1e-13
+    ctx.close()
+
+
+def test_pk_pipelines_on_fused_chains(eng, world, golden):
+    w, g = world("toyD"), golden("toyD")
+    mesh, ctx = ctx_for(eng, w, "pk", ("ops", "pk_fisher", "pk_data"))
+    orc, S = oracle_setup(w, "pk")
+    for r in (1, 2):
+        a = S.grf(r)
+        F, qbar = ctx.pk_fisher(a)
+        F, qbar = F.cpu().numpy(), qbar.cpu().numpy()
+        assert relerr(F, g["pk_fish_%d" % r]) < TOL
+        assert relerr(qbar, g["pk_qbar_%d" % r]) < TOL
+        F2, q2 = ctx.pk_fisher(a)
+        assert np.array_equal(F, F2.cpu().numpy()) and np.array_equal(qbar, q2.cpu().numpy())   # deterministic
+    # the cuFFT backend agrees with the fused chains to round-off
+    ctx.set_fft_backend(0)
+    F0, q0 = ctx.pk_fisher(S.grf(1))
+    ctx.set_fft_backend(1)
+    F1, q1 = ctx.pk_fisher(S.grf(1))
+    assert relerr(F1.cpu().numpy(), F0.cpu().numpy()) < 1e-12
+    diff = ctx.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box_center)
+    q = ctx.pk_data_q(diff).cpu().numpy()
+    assert relerr(q, g["pk_q"]) < TOL
+    x = np.random.default_rng(3).normal(size=mesh.shape)
+    maps = S.applyC_alpha(x)
+    for l_i in range(S.n_l):
+        got = ctx.apply_c_alpha_single(x, S.nbar, S.v_cell, l_i, 3).cpu().numpy()
+        assert relerr(got, np.real(maps[l_i * S.n_k + 3])) < 1e-12
+    ctx.close()
+
+
+def test_bk_pipelines_on_fused_chains(eng, world, golden):
+    w, g = world("toyD"), golden("toyD")
+    mesh, ctx = ctx_for(eng, w, "bk", ("ops", "bk_fisher", "bk_data"))
+    orc, S = oracle_setup(w, "bk")
+    aA, aB = S.grf(2), S.grf(3)
+    D = ctx.bk_delta().cpu().numpy()
+    assert relerr(D, orc.delta_abc(S, orc.triangle_bins(S.kmin, S.kmax, S.dk, S.n_k))) < 1e-11
+    F, (gA, tgA, gB, tgB) = ctx.bk_fisher_pair(aA, aB)
+    assert relerr(F.cpu().numpy(), g["bk_fish_1"]) < TOL
+    assert relerr(gA.cpu().numpy()[:, :, :, :, 3], g["bk_g_plane"]) < TOL
+    diff = ctx.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box_center)
+    gd = ctx.bk_gmaps(diff, data=True)
+    q = ctx.bk_q3(gd)
+    ctx.bk_q1_accumulate(gd, gA, tgA, 2, q)
+    ctx.bk_q1_accumulate(gd, gB, tgB, 2, q)
+    nt = ctx.n_tri
+    q = q.cpu().numpy()
+    qa = np.concatenate([q[:, l] / D[l * nt:(l + 1) * nt] for l in range(mesh.n_l)])
+    p = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qa)
+    assert relerr(p, g["bk_p"][:, 3:].T.ravel()) < 2e-8
+    ctx.close()

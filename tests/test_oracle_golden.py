@@ -6,7 +6,7 @@ import pytest
 from conftest import relerr
 from oracle import sww_oracle as orc
 
-WORLDS = ["toyA", "toyB", "toyC"]
+WORLDS = ["toyA", "toyB", "toyC", "toyD"]
 TOL = 1e-12      # two FP64 evaluations of the same algorithm
 
 
