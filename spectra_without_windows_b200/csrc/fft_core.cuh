@@ -76,14 +76,73 @@ FFT_HD void dft8(double2* u) {
   u[7] = c_sub(e[3], t3);
 }
 
+// 16-point DFT as 4 x 4 (decimation in time): A[j][q] = DFT4 over s of u[j + 4 s]; twiddle w16^(j q);
+// X[q + 4 t] = DFT4 over j.
+template <int DIR>
+FFT_HD void dft16(double2* u) {
+  const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+  double2 a[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double2 t[4] = {u[j], u[j + 4], u[j + 8], u[j + 12]};
+    dft4<DIR>(t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[j][q] = t[q];
+  }
+  // w16^n = (cos(pi n/8), -DIR sin(pi n/8)), n = j*q in {1,2,3,4,6,9}
+  const double cs[10] = {1.0, c1, h, s1, 0.0, -s1, -h, -c1, -1.0, -c1};
+  const double sn[10] = {0.0, s1, h, c1, 1.0, c1, h, s1, 0.0, -s1};
+#pragma unroll
+  for (int j = 1; j < 4; ++j)
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const int n = j * q;
+      double2 w = double2{cs[n], DIR > 0 ? -sn[n] : sn[n]};
+      a[j][q] = c_mul(a[j][q], w);
+    }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    double2 t[4] = {a[0][q], a[1][q], a[2][q], a[3][q]};
+    dft4<DIR>(t);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) u[q + 4 * s] = t[s];
+  }
+}
+
 template <int R, int DIR>
 FFT_HD void dftR(double2* u) {
-  if (R == 8)
+  if (R == 16)
+    dft16<DIR>(u);
+  else if (R == 8)
     dft8<DIR>(u);
   else if (R == 4)
     dft4<DIR>(u);
   else
     dft2<DIR>(u[0], u[1]);
+}
+
+// Twiddles w^r, r < R, of one butterfly: w^1, w^2, w^4 (, w^8) come from the table, the others are
+// products of two table values (<= 2 roundings), which costs less than the shared-memory loads.
+template <int R, int DIR>
+FFT_HD void stage_twiddle(int N, int p, int k, const double2* tw, double2* u) {
+  if (p > 1) {
+    const int step = k * (N / (p * R));
+    double2 w[R];
+#pragma unroll
+    for (int r = 1; r < R; r <<= 1) {
+      w[r] = tw[step * r];
+      if (DIR < 0) w[r].y = -w[r].y;
+    }
+#pragma unroll
+    for (int r = 3; r < R; ++r) {
+      if ((r & (r - 1)) != 0) {  // not a power of two: highest set bit times the rest
+        int hb = r >= 8 ? 8 : (r >= 4 ? 4 : 2);
+        w[r] = c_mul(w[hb], w[r - hb]);
+      }
+    }
+#pragma unroll
+    for (int r = 1; r < R; ++r) u[r] = c_mul(u[r], w[r]);
+  }
 }
 
 // One Stockham stage, radix R, for work item (butterfly bi, column c) of a tile [N][FFT_LDT].
@@ -95,15 +154,7 @@ FFT_HD void stage_load(const double2* tile, int N, int p, int bi, int c, const d
   const int k = bi & (p - 1);
 #pragma unroll
   for (int r = 0; r < R; ++r) u[r] = tile[(bi + r * T) * FFT_LDT + c];
-  if (p > 1) {
-    const int step = k * (N / (p * R));
-#pragma unroll
-    for (int r = 1; r < R; ++r) {
-      double2 w = tw[step * r];
-      if (DIR < 0) w.y = -w.y;
-      u[r] = c_mul(u[r], w);
-    }
-  }
+  stage_twiddle<R, DIR>(N, p, k, tw, u);
   dftR<R, DIR>(u);
 }
 
@@ -116,10 +167,12 @@ FFT_HD void stage_store(double2* tile, int N, int p, int bi, int c, const double
   for (int r = 0; r < R; ++r) tile[(j + r * p) * FFT_LDT + c] = u[r];
 }
 
-// Radix plan: N = R0*R1*R2[*R3], radix 8 where possible.
+// Radix plan: N = R0*R1[*R2].
+// The plan is palindromic-friendly: the reversed plan is used for the transform that follows a fused
+// real-space step, so that the last stage of one and the first stage of the next share registers.
 template <int N> struct FftPlan;
 template <> struct FftPlan<64>   { static constexpr int NS = 2; static constexpr int R[4] = {8, 8, 1, 1}; };
-template <> struct FftPlan<128>  { static constexpr int NS = 3; static constexpr int R[4] = {4, 4, 8, 1}; };
-template <> struct FftPlan<256>  { static constexpr int NS = 3; static constexpr int R[4] = {4, 8, 8, 1}; };
+template <> struct FftPlan<128>  { static constexpr int NS = 2; static constexpr int R[4] = {8, 16, 1, 1}; };
+template <> struct FftPlan<256>  { static constexpr int NS = 2; static constexpr int R[4] = {16, 16, 1, 1}; };
 template <> struct FftPlan<512>  { static constexpr int NS = 3; static constexpr int R[4] = {8, 8, 8, 1}; };
-template <> struct FftPlan<1024> { static constexpr int NS = 4; static constexpr int R[4] = {4, 4, 8, 8}; };
+template <> struct FftPlan<1024> { static constexpr int NS = 3; static constexpr int R[4] = {4, 16, 16, 1}; };

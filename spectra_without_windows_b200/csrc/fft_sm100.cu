@@ -34,15 +34,28 @@ int sww_fft_sm100_supported(const sww_ctx* c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// tile FFT: all Stockham stages with CTA barriers.  Caller syncs after filling the tile.
+// Tile FFT with register-resident first and last stages.
+//   * stage 0 takes its inputs from a caller-supplied functor (global memory, a staging buffer or
+//     registers left by a previous transform) -- the tile is never filled by a separate pass;
+//   * the last stage hands its outputs to a functor (global stores, epilogues, or the registers of
+//     the next transform) -- the tile is never drained by a separate pass;
+//   * only the exchanges between stages go through shared memory (2 passes per exchange).
+// REV selects the reversed radix order, so that "inverse, then forward" chains share the register
+// layout at the seam: outputs of the last inverse stage sit at positions bi + r*(N/R) -- exactly what
+// stage 0 of a forward transform whose first radix is R consumes.
 // ------------------------------------------------------------------------------------------
-template <int N, int DIR, int S, int P>
-struct TileStages {
+template <int N, bool REV, int S>
+struct PlanRadix {
+  static constexpr int value = REV ? FftPlan<N>::R[FftPlan<N>::NS - 1 - S] : FftPlan<N>::R[S];
+};
+
+template <int N, int DIR, bool REV, int S, int P>
+struct MidStages {   // stages 1 .. NS-2, fully in shared memory
   static __device__ __forceinline__ void run(double2* tile, const double2* tw, int tid) {
-    if constexpr (S < FftPlan<N>::NS) {
-      constexpr int R = FftPlan<N>::R[S];
+    if constexpr (S < FftPlan<N>::NS - 1) {
+      constexpr int R = PlanRadix<N, REV, S>::value;
       constexpr int NT = N / 2;
-      constexpr int IPT = (N / R) * FFT_TZ / NT;
+      constexpr int IPT = 16 / R;
       double2 u[IPT][R];
 #pragma unroll
       for (int s = 0; s < IPT; ++s) {
@@ -56,15 +69,72 @@ struct TileStages {
         stage_store<R>(tile, N, P, w >> 3, w & 7, u[s]);
       }
       __syncthreads();
-      TileStages<N, DIR, S + 1, P * R>::run(tile, tw, tid);
+      MidStages<N, DIR, REV, S + 1, P * R>::run(tile, tw, tid);
     }
   }
 };
 
-template <int N, int DIR>
-__device__ __forceinline__ void tile_fft(double2* tile, const double2* tw, int tid) {
-  TileStages<N, DIR, 0, 1>::run(tile, tw, tid);
+template <int N, bool REV, int S>
+struct PlanProd {   // product of the first S radices
+  static constexpr int value = PlanProd<N, REV, S - 1>::value * PlanRadix<N, REV, S - 1>::value;
+};
+template <int N, bool REV>
+struct PlanProd<N, REV, 0> {
+  static constexpr int value = 1;
+};
+
+// Stage 0: u[s][r] = ld(pos = bi + r*T, c), butterfly, scatter into the tile.  The caller must have
+// synchronised since the tile was last read.
+template <int N, int DIR, bool REV, typename LD>
+__device__ __forceinline__ void fft_first(double2* tile, int tid, LD ld) {
+  constexpr int R = PlanRadix<N, REV, 0>::value;
+  constexpr int NT = N / 2, IPT = 16 / R, T = N / R;
+  double2 u[IPT][R];
+#pragma unroll
+  for (int s = 0; s < IPT; ++s) {
+    int w = tid + s * NT, bi = w >> 3, c = w & 7;
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[s][r] = ld(bi + r * T, c);
+  }
+#pragma unroll
+  for (int s = 0; s < IPT; ++s) {
+    int w = tid + s * NT;
+    dftR<R, DIR>(u[s]);
+    stage_store<R>(tile, N, 1, w >> 3, w & 7, u[s]);
+  }
+  __syncthreads();
 }
+
+// Stage 0 fed from registers laid out as the outputs of a preceding last stage of the same radix.
+template <int N, int DIR, bool REV, int R>
+__device__ __forceinline__ void fft_first_regs(double2* tile, int tid, double2 (*u)[R]) {
+  static_assert(R == PlanRadix<N, REV, 0>::value, "radix mismatch at the seam");
+  constexpr int NT = N / 2, IPT = 16 / R;
+#pragma unroll
+  for (int s = 0; s < IPT; ++s) {
+    int w = tid + s * NT;
+    dftR<R, DIR>(u[s]);
+    stage_store<R>(tile, N, 1, w >> 3, w & 7, u[s]);
+  }
+  __syncthreads();
+}
+
+// Last stage: outputs u[s][r] sit at position bi + r*P of column c (P = N/R).
+template <int N, int DIR, bool REV, int R>
+__device__ __forceinline__ void fft_last(const double2* tile, const double2* tw, int tid, double2 (*u)[R]) {
+  static_assert(R == PlanRadix<N, REV, FftPlan<N>::NS - 1>::value, "radix mismatch");
+  constexpr int NT = N / 2, IPT = 16 / R;
+  constexpr int P = N / R;
+#pragma unroll
+  for (int s = 0; s < IPT; ++s) {
+    int w = tid + s * NT;
+    stage_load<R, DIR>(tile, N, P, w >> 3, w & 7, tw, u[s]);
+  }
+}
+
+#define FFT_LAST_RADIX(N, REV) (PlanRadix<N, REV, FftPlan<N>::NS - 1>::value)
+#define FFT_MID(N, DIR, REV, tile, tw, tid) \
+  MidStages<N, DIR, REV, 1, PlanRadix<N, REV, 0>::value>::run(tile, tw, tid)
 
 struct BoxAxis {
   int n, K, b;  // axis length, number of kept indices, last non-negative kept index
@@ -75,7 +145,7 @@ struct BoxAxis {
 
 // ------------------------------------------------------------------------------------------
 // I1: x-axis inverse.  Source: spectrum [nx][ny][nzh] restricted to the box; optional shell filter.
-// item = (jy, z-tile); output P[ix][jy][iz]  (pitch Kzp)
+// item = (jy, z-tile); output P[ix][jy][iz]  (pitch Kzp).  Rows outside the box are never read.
 // ------------------------------------------------------------------------------------------
 template <int N>
 __global__ void __launch_bounds__(N / 2)
@@ -86,6 +156,7 @@ pass_i1_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
   double2* tw = tile + N * FFT_LDT;
   const int tid = threadIdx.x;
   constexpr int NT = N / 2;
+  constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
   const long long items = (long long)by.K * ztiles;
@@ -93,20 +164,26 @@ pass_i1_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
     const int jy = (int)(it / ztiles), zt = (int)(it - (long long)jy * ztiles);
     const int iy = by.idx(jy), iz0 = zt * FFT_TZ;
     __syncthreads();
-    for (int e = tid; e < N * FFT_TZ; e += NT) {
-      const int ix = e >> 3, cc = e & 7, iz = iz0 + cc;
+    fft_first<N, -1, false>(tile, tid, [&](int ix, int cc) {
       double2 v = make_double2(0.0, 0.0);
+      const int iz = iz0 + cc;
       if (bx.has(ix) && iz < Kz) {
         long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
         if (shell < 0 || g.binmap[cell] == shell) v = src[cell];
       }
-      tile[ix * FFT_LDT + cc] = v;
-    }
-    __syncthreads();
-    tile_fft<N, -1>(tile, tw, tid);
-    for (int e = tid; e < N * FFT_TZ; e += NT) {
-      const int ix = e >> 3, cc = e & 7;
-      P[((long long)ix * by.K + jy) * Kzp + iz0 + cc] = tile[ix * FFT_LDT + cc];
+      return v;
+    });
+    FFT_MID(N, -1, false, tile, tw, tid);
+    double2 u[16 / RL][RL];
+    fft_last<N, -1, false, RL>(tile, tw, tid, u);
+#pragma unroll
+    for (int s = 0; s < 16 / RL; ++s) {
+      int w = tid + s * NT, bi = w >> 3, cc = w & 7;
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        int ix = bi + r * (N / RL);
+        P[((long long)ix * by.K + jy) * Kzp + iz0 + cc] = u[s][r];
+      }
     }
   }
 }
@@ -123,6 +200,7 @@ pass_i2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ P, const
   double2* tw = tile + N * FFT_LDT;
   const int tid = threadIdx.x;
   constexpr int NT = N / 2;
+  constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
   const long long items = (long long)nx * ztiles;
@@ -130,17 +208,22 @@ pass_i2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ P, const
     const int ix = (int)(it / ztiles), zt = (int)(it - (long long)ix * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    for (int e = tid; e < N * FFT_TZ; e += NT) {
-      const int iy = e >> 3, cc = e & 7;
+    fft_first<N, -1, false>(tile, tid, [&](int iy, int cc) {
       double2 v = make_double2(0.0, 0.0);
       if (by.has(iy)) v = P[((long long)ix * by.K + by.pos(iy)) * Kzp + iz0 + cc];
-      tile[iy * FFT_LDT + cc] = v;
-    }
-    __syncthreads();
-    tile_fft<N, -1>(tile, tw, tid);
-    for (int e = tid; e < N * FFT_TZ; e += NT) {
-      const int iy = e >> 3, cc = e & 7;
-      Q[((long long)ix * N + iy) * Kzp + iz0 + cc] = tile[iy * FFT_LDT + cc];
+      return v;
+    });
+    FFT_MID(N, -1, false, tile, tw, tid);
+    double2 u[16 / RL][RL];
+    fft_last<N, -1, false, RL>(tile, tw, tid, u);
+#pragma unroll
+    for (int s = 0; s < 16 / RL; ++s) {
+      int w = tid + s * NT, bi = w >> 3, cc = w & 7;
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        int iy = bi + r * (N / RL);
+        Q[((long long)ix * N + iy) * Kzp + iz0 + cc] = u[s][r];
+      }
     }
   }
 }
@@ -157,6 +240,7 @@ pass_f2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ R, const
   double2* tw = tile + N * FFT_LDT;
   const int tid = threadIdx.x;
   constexpr int NT = N / 2;
+  constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
   const long long items = (long long)nx * ztiles;
@@ -164,21 +248,24 @@ pass_f2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ R, const
     const int ix = (int)(it / ztiles), zt = (int)(it - (long long)ix * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    for (int e = tid; e < N * FFT_TZ; e += NT) {
-      const int iy = e >> 3, cc = e & 7;
-      tile[iy * FFT_LDT + cc] = R[((long long)ix * N + iy) * Kzp + iz0 + cc];
-    }
-    __syncthreads();
-    tile_fft<N, 1>(tile, tw, tid);
-    for (int e = tid; e < by.K * FFT_TZ; e += NT) {
-      const int jy = e >> 3, cc = e & 7;
-      P[((long long)ix * by.K + jy) * Kzp + iz0 + cc] = tile[by.idx(jy) * FFT_LDT + cc];
+    fft_first<N, 1, false>(tile, tid, [&](int iy, int cc) { return R[((long long)ix * N + iy) * Kzp + iz0 + cc]; });
+    FFT_MID(N, 1, false, tile, tw, tid);
+    double2 u[16 / RL][RL];
+    fft_last<N, 1, false, RL>(tile, tw, tid, u);
+#pragma unroll
+    for (int s = 0; s < 16 / RL; ++s) {
+      int w = tid + s * NT, bi = w >> 3, cc = w & 7;
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        int iy = bi + r * (N / RL);
+        if (by.has(iy)) P[((long long)ix * by.K + by.pos(iy)) * Kzp + iz0 + cc] = u[s][r];
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// F3: x-axis forward + epilogue.  P[ix][jy][iz]; item = (jy, z-tile)
+// F3: x-axis forward + epilogue straight from the registers of the last stage.  item = (jy, z-tile)
 //   MODE 0: dst[cell] = T                         (box cells of a spectrum [nx][ny][nzh])
 //   MODE 1: dst[cell] = (first ? 0 : dst[cell]) + Y_lm(k^) T ; on the last m: *= MAS^p * coef
 //   MODE 2: shell binning  hist[q*n_k + bin] += w_herm Re(conj(T) G_q[cell])   -> out row
@@ -190,7 +277,7 @@ __device__ __forceinline__ double warp_sum_f(double v) {
 }
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(N / 2)
+__global__ void __launch_bounds__(N / 2, (N >= 512 ? (N >= 1024 ? 1 : 2) : 3))
 pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __restrict__ P,
                const double2* __restrict__ twg, F3Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -201,6 +288,7 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
   const int tid = threadIdx.x;
   constexpr int NT = N / 2;
   constexpr int NW = NT / 32;
+  constexpr int RL = FFT_LAST_RADIX(N, false);
   const int warp = tid >> 5, lane = tid & 31;
   const int nb = A.n_g * g.n_k;
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
@@ -213,73 +301,94 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
     const int jy = (int)(it / ztiles), zt = (int)(it - (long long)jy * ztiles);
     const int iy = by.idx(jy), iz0 = zt * FFT_TZ;
     __syncthreads();
-    for (int e = tid; e < N * FFT_TZ; e += NT) {
-      const int ix = e >> 3, cc = e & 7;
-      tile[ix * FFT_LDT + cc] = P[((long long)ix * by.K + jy) * Kzp + iz0 + cc];
-    }
-    __syncthreads();
-    tile_fft<N, 1>(tile, tw, tid);
-    // epilogue over box rows (all threads run the same trip count so warp collectives are safe)
-    const int total = bx.K * FFT_TZ;
-    for (int e0 = 0; e0 < total; e0 += NT) {
-      const int e = e0 + tid;
-      const bool valid = e < total;
-      const int jx = e >> 3, cc = e & 7, iz = iz0 + cc;
-      const int ix = valid ? bx.idx(jx) : 0;
-      const bool inb = valid && iz < Kz;
-      const long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
-      if (MODE == 0) {
-        if (inb) A.dst[cell] = tile[ix * FFT_LDT + cc];
-      } else if (MODE == 1) {
-        if (inb) {
-          double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
-          double r = sqrt(kx * kx + ky * ky + kz * kz);
-          double inv = 1.0 / (1e-12 + r);
-          double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
-          double2 t = tile[ix * FFT_LDT + cc];
-          double2 o = A.first ? make_double2(0.0, 0.0) : A.dst[cell];
-          o.x += t.x * yk;
-          o.y += t.y * yk;
-          if (A.coef != 0.0) {
-            if (A.mas_power) {
-              double m = g.mas[0][ix] * g.mas[1][iy] * g.mas[2][iz];
-              if (A.mas_power == 2) m = m * m;
-              o.x *= m;
-              o.y *= m;
+    fft_first<N, 1, false>(tile, tid,
+                           [&](int ix, int cc) { return P[((long long)ix * by.K + jy) * Kzp + iz0 + cc]; });
+    FFT_MID(N, 1, false, tile, tw, tid);
+    double2 u[16 / RL][RL];
+    fft_last<N, 1, false, RL>(tile, tw, tid, u);
+    // epilogue straight from registers (uniform trip count: the warp collectives of MODE 2 are safe)
+    if (MODE != 2) {
+#pragma unroll
+      for (int s = 0; s < 16 / RL; ++s) {
+        const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7, iz = iz0 + cc;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          const int ix = bi + r * (N / RL);
+          const bool inb = bx.has(ix) && iz < Kz;
+          const long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
+          const double2 t = u[s][r];
+          if (MODE == 0) {
+            if (inb) A.dst[cell] = t;
+          } else if (inb) {
+            double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
+            double rr = sqrt(kx * kx + ky * ky + kz * kz);
+            double inv = 1.0 / (1e-12 + rr);
+            double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
+            double2 o = A.first ? make_double2(0.0, 0.0) : A.dst[cell];
+            o.x += t.x * yk;
+            o.y += t.y * yk;
+            if (A.coef != 0.0) {
+              if (A.mas_power) {
+                double m = g.mas[0][ix] * g.mas[1][iy] * g.mas[2][iz];
+                if (A.mas_power == 2) m = m * m;
+                o.x *= m;
+                o.y *= m;
+              }
+              o.x *= A.coef;
+              o.y *= A.coef;
             }
-            o.x *= A.coef;
-            o.y *= A.coef;
+            A.dst[cell] = o;
           }
-          A.dst[cell] = o;
         }
-      } else {
-        int b = SWW_NO_BIN;
-        double v[3] = {0.0, 0.0, 0.0};
-        if (inb) {
-          b = g.binmap[cell];
+      }
+    } else {
+      // shell binning: loads are batched four elements deep (bin indices, then the G_l' values)
+      constexpr int GRP = 2;
+#pragma unroll
+      for (int e0 = 0; e0 < 16; e0 += GRP) {
+        int bq[GRP];
+        long long cellq[GRP];
+        double wq[GRP];
+#pragma unroll
+        for (int j = 0; j < GRP; ++j) {
+          const int e = e0 + j, s = e / RL, r = e % RL;
+          const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7, iz = iz0 + cc;
+          const int ix = bi + r * (N / RL);
+          const bool inb = bx.has(ix) && iz < Kz;
+          cellq[j] = ((long long)ix * g.ny + iy) * g.nzh + iz;
+          bq[j] = inb ? (int)g.binmap[cellq[j]] : SWW_NO_BIN;
+          wq[j] = (iz == 0 || (nz_even && iz == g.nz / 2)) ? 1.0 : 2.0;
+        }
+        double2 Gq[GRP][3];
+#pragma unroll
+        for (int j = 0; j < GRP; ++j)
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q < A.n_g && bq[j] != SWW_NO_BIN) Gq[j][q] = A.G[q][cellq[j]];
+#pragma unroll
+        for (int j = 0; j < GRP; ++j) {
+          const int e = e0 + j, s = e / RL, r = e % RL;
+          const double2 t = u[s][r];
+          const int b = bq[j];
+          double v[3] = {0.0, 0.0, 0.0};
           if (b != SWW_NO_BIN) {
-            double2 t = tile[ix * FFT_LDT + cc];
-            double w = (iz == 0 || (nz_even && iz == g.nz / 2)) ? 1.0 : 2.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (q < A.n_g) v[q] = wq[j] * (t.x * Gq[j][q].x + t.y * Gq[j][q].y);
+          }
+          unsigned rem = __ballot_sync(0xffffffffu, b != SWW_NO_BIN);
+          while (rem) {
+            int srcl = __ffs(rem) - 1;
+            int cur = __shfl_sync(0xffffffffu, b, srcl);
+            bool mine = (b == cur);
 #pragma unroll
             for (int q = 0; q < 3; ++q)
               if (q < A.n_g) {
-                double2 G = A.G[q][cell];
-                v[q] = w * (t.x * G.x + t.y * G.y);
+                double sm = warp_sum_f(mine ? v[q] : 0.0);
+                if (lane == 0) hist[warp * nb + q * g.n_k + cur] += sm;
               }
+            rem &= ~__ballot_sync(0xffffffffu, mine);
           }
-        }
-        unsigned rem = __ballot_sync(0xffffffffu, b != SWW_NO_BIN);
-        while (rem) {
-          int srcl = __ffs(rem) - 1;
-          int cur = __shfl_sync(0xffffffffu, b, srcl);
-          bool mine = (b == cur);
-#pragma unroll
-          for (int q = 0; q < 3; ++q)
-            if (q < A.n_g) {
-              double s = warp_sum_f(mine ? v[q] : 0.0);
-              if (lane == 0) hist[warp * nb + q * g.n_k + cur] += s;
-            }
-          rem &= ~__ballot_sync(0xffffffffu, mine);
         }
       }
     }
@@ -287,9 +396,9 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
   if (MODE == 2) {
     __syncthreads();
     for (int j = tid; j < nb; j += NT) {
-      double s = 0.0;
-      for (int w = 0; w < NW; ++w) s += hist[w * nb + j];
-      A.partial[(long long)blockIdx.x * nb + j] = s;
+      double sm = 0.0;
+      for (int w = 0; w < NW; ++w) sm += hist[w * nb + j];
+      A.partial[(long long)blockIdx.x * nb + j] = sm;
     }
     __threadfence();
     __syncthreads();
@@ -301,9 +410,9 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
     if (is_last) {
       __threadfence();
       for (int j = tid; j < nb; j += NT) {
-        double s = 0.0;
-        for (unsigned bl = 0; bl < gridDim.x; ++bl) s += A.partial[(long long)bl * nb + j];
-        A.out_row[j] = s * A.scale;
+        double sm = 0.0;
+        for (unsigned bl = 0; bl < gridDim.x; ++bl) sm += A.partial[(long long)bl * nb + j];
+        A.out_row[j] = sm * A.scale;
       }
       if (tid == 0) *A.counter = 0;
     }
@@ -314,7 +423,8 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
 // Z pass.  8 rows (ix, iy0..iy0+7) per tile, half-length H = nz/2 complex FFTs.
 //   INV: complex rows Q[row][0..Kz_in) (pitch Kzp_in)  -> real row x[0..nz)
 //   FWD: real row -> complex rows R[row][0..Kz_out) (pitch Kzp_out)
-//   INV && FWD: x * wmap * scale is transformed back without leaving shared memory
+//   INV && FWD: x * wmap * scale goes from the registers of the last inverse stage straight into the
+//               first forward stage (reversed radix plan): the real-space map never leaves registers
 //   INV only : real_out[row][z] = x * scale [* wmap] [* Y_lm(r^)]  (optionally accumulated)
 //   FWD only : x = real_in[row][z] [* wmap] [* Y_lm(r^)]
 // ------------------------------------------------------------------------------------------
@@ -331,9 +441,9 @@ struct ZArgs {
   int accumulate;  // INV only: real_out += ...
 };
 
-template <int H, bool INV, bool FWD>
+template <int H, bool INV, bool FWD, bool YLM>
 __global__ void __launch_bounds__(H / 2)
-pass_z_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
+pass_z_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g, int SP) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);   // [H][9]
   double2* twh = tile + H * FFT_LDT;                      // [H]    exp(-2 pi i j / H)
@@ -341,23 +451,46 @@ pass_z_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* 
   double2* stage = twn + (H + 8);                         // [8][H+9]
   const int tid = threadIdx.x;
   constexpr int NT = H / 2;
-  constexpr int SP = H + 9;  // staging pitch (odd: conflict-free transposed reads)
+  // seam radix: last stage of the inverse plan == first stage of the (reversed) forward plan
+  constexpr int RS = FFT_LAST_RADIX(H, false);
+  constexpr int IPT = 16 / RS;
+  constexpr int PS = H / RS;
   for (int i = tid; i < H; i += NT) twh[i] = twh_g[i];
   for (int i = tid; i <= H; i += NT) twn[i] = twn_g[i];
   const long long groups = (long long)g.nx * g.ny / FFT_TZ;
   for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const long long row0 = grp * FFT_TZ;  // rows row0 .. row0+7 share ix (ny is a multiple of 8)
+    const int ix = (int)(row0 / g.ny);
+    const int iyb = (int)(row0 - (long long)ix * g.ny);
+    double2 u[IPT][RS];
     __syncthreads();
     if (INV) {
-      // stage the complex input rows
-      for (int e = tid; e < FFT_TZ * A.Kz_in; e += NT) {
-        int r = e / A.Kz_in, k = e - r * A.Kz_in;
-        stage[r * SP + k] = A.Q[(row0 + r) * A.Kzp_in + k];
+      // stage the complex input rows (coalesced; loads batched four deep ahead of the stores)
+      {
+        const int tot = FFT_TZ * A.Kz_in;
+        for (int e0 = tid; e0 < tot; e0 += 4 * NT) {
+          double2 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int e = e0 + q * NT;
+            if (e < tot) {
+              int r = e / A.Kz_in, k = e - r * A.Kz_in;
+              v[q] = A.Q[(row0 + r) * A.Kzp_in + k];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int e = e0 + q * NT;
+            if (e < tot) {
+              int r = e / A.Kz_in, k = e - r * A.Kz_in;
+              stage[r * SP + k] = v[q];
+            }
+          }
+        }
       }
       __syncthreads();
-      // Y[k] = (Z[k] + conj Z[H-k]) + i (Z[k] - conj Z[H-k]) e^{+2 pi i k / nz}
-      for (int e = tid; e < H * FFT_TZ; e += NT) {
-        int k = e >> 3, r = e & 7;
+      // Y[k] = (Z[k] + conj Z[H-k]) + i (Z[k] - conj Z[H-k]) e^{+2 pi i k / nz}, built on the fly
+      fft_first<H, -1, false>(tile, tid, [&](int k, int r) {
         double2 zk = (k < A.Kz_in) ? stage[r * SP + k] : make_double2(0.0, 0.0);
         int hk = H - k;
         double2 zh = (hk < A.Kz_in) ? stage[r * SP + hk] : make_double2(0.0, 0.0);
@@ -370,56 +503,97 @@ pass_z_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* 
         double2 w = twn[k];
         w.y = -w.y;
         double2 b = c_mul(d, w);
-        tile[k * FFT_LDT + r] = make_double2(a.x - b.y, a.y + b.x);
-      }
-      __syncthreads();
-      tile_fft<H, -1>(tile, twh, tid);
+        return make_double2(a.x - b.y, a.y + b.x);
+      });
+      FFT_MID(H, -1, false, tile, twh, tid);
+      fft_last<H, -1, false, RS>(tile, twh, tid, u);
     }
-    // real-space stage: thread handles (m, r) with m fastest so that global rows are read contiguously
+    // real-space step on registers: element (s, r) is the pair x[2m], x[2m+1], m = bi + r*PS, row c.
+    // All global loads of the step are issued before any use (one exposed latency, not sixteen).
     {
-      const int ix = (int)(row0 / g.ny);
-      const int iyb = (int)(row0 - (long long)ix * g.ny);
-      for (int e = tid; e < H * FFT_TZ; e += NT) {
-        int r = e / H, m = e - r * H;
-        long long off = (row0 + r) * g.nz + 2 * m;
-        double f0 = A.scale, f1 = A.scale;
-        if (A.wmap) {
-          double2 w = *reinterpret_cast<const double2*>(A.wmap + off);
-          f0 *= w.x;
-          f1 *= w.y;
+      double2 wv[IPT][RS];
+      if (A.wmap) {
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+          const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
+#pragma unroll
+          for (int r = 0; r < RS; ++r)
+            wv[s][r] = *reinterpret_cast<const double2*>(A.wmap + (row0 + c) * g.nz + 2 * (bi + r * PS));
         }
-        if (A.lm >= 0) {
-          double X = g.rax[0][ix], Y = g.rax[1][iyb + r];
-          double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
-          double r0 = sqrt(X * X + Y * Y + Z0 * Z0), r1 = sqrt(X * X + Y * Y + Z1 * Z1);
-          double i0 = 1.0 / (1e-12 + r0), i1 = 1.0 / (1e-12 + r1);
-          f0 *= sww_ylm_dyn(A.lm, X * i0, Y * i0, Z0 * i0);
-          f1 *= sww_ylm_dyn(A.lm, X * i1, Y * i1, Z1 * i1);
+      }
+      if (!INV) {
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+          const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
+#pragma unroll
+          for (int r = 0; r < RS; ++r)
+            u[s][r] = *reinterpret_cast<const double2*>(A.real_in + (row0 + c) * g.nz + 2 * (bi + r * PS));
         }
-        if (INV) {
-          double2 y = tile[m * FFT_LDT + r];
-          y.x *= f0;
-          y.y *= f1;
-          if (FWD) {
-            tile[m * FFT_LDT + r] = y;
-          } else {
-            double2* dst = reinterpret_cast<double2*>(A.real_out + off);
-            if (A.accumulate) {
-              double2 o = *dst;
-              y.x += o.x;
-              y.y += o.y;
-            }
-            *dst = y;
+      }
+#pragma unroll
+      for (int s = 0; s < IPT; ++s) {
+        const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+          const int m = bi + r * PS;
+          double f0 = A.scale, f1 = A.scale;
+          if (A.wmap) {
+            f0 *= wv[s][r].x;
+            f1 *= wv[s][r].y;
           }
-        } else {
-          double2 x = *reinterpret_cast<const double2*>(A.real_in + off);
-          tile[m * FFT_LDT + r] = make_double2(x.x * f0, x.y * f1);
+          if (YLM) {
+            double X = g.rax[0][ix], Y = g.rax[1][iyb + c];
+            double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
+            double r0 = sqrt(X * X + Y * Y + Z0 * Z0), r1 = sqrt(X * X + Y * Y + Z1 * Z1);
+            double i0 = 1.0 / (1e-12 + r0), i1 = 1.0 / (1e-12 + r1);
+            f0 *= sww_ylm_dyn(A.lm, X * i0, Y * i0, Z0 * i0);
+            f1 *= sww_ylm_dyn(A.lm, X * i1, Y * i1, Z1 * i1);
+          }
+          u[s][r].x *= f0;
+          u[s][r].y *= f1;
+        }
+      }
+      if (INV && !FWD) {
+        if (A.accumulate) {
+#pragma unroll
+          for (int s = 0; s < IPT; ++s) {
+            const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
+#pragma unroll
+            for (int r = 0; r < RS; ++r)
+              wv[s][r] = *reinterpret_cast<const double2*>(A.real_out + (row0 + c) * g.nz + 2 * (bi + r * PS));
+          }
+#pragma unroll
+          for (int s = 0; s < IPT; ++s)
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+              u[s][r].x += wv[s][r].x;
+              u[s][r].y += wv[s][r].y;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+          const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
+#pragma unroll
+          for (int r = 0; r < RS; ++r)
+            *reinterpret_cast<double2*>(A.real_out + (row0 + c) * g.nz + 2 * (bi + r * PS)) = u[s][r];
         }
       }
     }
     if (FWD) {
+      if (INV) __syncthreads();   // every thread has finished reading the tile in the last inverse stage
+      fft_first_regs<H, 1, true, RS>(tile, tid, u);
+      MidStages<H, 1, true, 1, RS>::run(tile, twh, tid);
+      constexpr int RL = FFT_LAST_RADIX(H, true);
+      double2 v[16 / RL][RL];
+      fft_last<H, 1, true, RL>(tile, twh, tid, v);
       __syncthreads();
-      tile_fft<H, 1>(tile, twh, tid);
+#pragma unroll
+      for (int s = 0; s < 16 / RL; ++s) {
+        int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) tile[(bi + r * (H / RL)) * FFT_LDT + c] = v[s][r];
+      }
+      __syncthreads();
       // T[k] = 1/2 (V[k] + conj V[H-k]) - i/2 e^{-2 pi i k/nz} (V[k] - conj V[H-k]),  V[H] = V[0]
       for (int e = tid; e < FFT_TZ * A.Kz_out; e += NT) {
         int r = e / A.Kz_out, k = e - r * A.Kz_out;
@@ -542,10 +716,13 @@ static inline int grid_for_items(long long items, int per_sm) {
 static size_t col_smem(int N, int hist_doubles) {
   return (size_t)N * FFT_LDT * 16 + (size_t)N * 16 + (size_t)hist_doubles * 8;
 }
-static size_t z_smem(int H) { return (size_t)H * FFT_LDT * 16 + (size_t)H * 16 + (size_t)(H + 8) * 16 + (size_t)8 * (H + 9) * 16; }
+static int z_stage_pitch(int Kz_in) { return (Kz_in + 8) | 1; }   // odd pitch: conflict-free transposed reads
+static size_t z_smem(int H, int Kz_in) {
+  return (size_t)H * FFT_LDT * 16 + (size_t)H * 16 + (size_t)(H + 8) * 16 + (size_t)8 * z_stage_pitch(Kz_in) * 16;
+}
 
 static int occ_for(size_t smem) {
-  int o = (int)((220 * 1024) / (smem + 1024));
+  int o = (int)((227 * 1024) / (smem + 1024));
   if (o < 1) o = 1;
   if (o > 4) o = 4;
   return o;
@@ -625,21 +802,31 @@ static int run_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bx, BoxAxis by, i
   return 0;
 }
 
+template <int H, bool INV, bool FWD, bool YLM>
+static int launch_z(sww_ctx* c, Sm100State* s, ZArgs A, int grid, size_t smem, int SP) {
+  SWW_TRY(set_smem(pass_z_kernel<H, INV, FWD, YLM>, smem));
+  pass_z_kernel<H, INV, FWD, YLM><<<grid, H / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, SP);
+  return 0;
+}
+
 static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   const int H = c->g.nz / 2;
-  size_t smem = z_smem(H);
+  const int Kz_in = inv ? A.Kz_in : 0;
+  const int SP = z_stage_pitch(Kz_in);
+  size_t smem = z_smem(H, Kz_in);
   long long groups = (long long)c->g.nx * c->g.ny / FFT_TZ;
   int grid = grid_for_items(groups, occ_for(smem));
-#define M(HH)                                                                                    \
-  if (inv && fwd) {                                                                              \
-    SWW_TRY(set_smem(pass_z_kernel<HH, true, true>, smem));                                      \
-    pass_z_kernel<HH, true, true><<<grid, HH / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n); \
-  } else if (inv) {                                                                              \
-    SWW_TRY(set_smem(pass_z_kernel<HH, true, false>, smem));                                     \
-    pass_z_kernel<HH, true, false><<<grid, HH / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n); \
-  } else {                                                                                       \
-    SWW_TRY(set_smem(pass_z_kernel<HH, false, true>, smem));                                     \
-    pass_z_kernel<HH, false, true><<<grid, HH / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n); \
+  const bool ylm = A.lm >= 0;
+#define M(HH)                                                                       \
+  if (inv && fwd) {                                                                 \
+    SWW_REQUIRE(!ylm, "fused z pass has no Y_lm variant");                         \
+    SWW_TRY((launch_z<HH, true, true, false>(c, s, A, grid, smem, SP)));            \
+  } else if (inv) {                                                                 \
+    if (ylm) SWW_TRY((launch_z<HH, true, false, true>(c, s, A, grid, smem, SP)));   \
+    else SWW_TRY((launch_z<HH, true, false, false>(c, s, A, grid, smem, SP)));      \
+  } else {                                                                          \
+    if (ylm) SWW_TRY((launch_z<HH, false, true, true>(c, s, A, grid, smem, SP)));   \
+    else SWW_TRY((launch_z<HH, false, true, false>(c, s, A, grid, smem, SP)));      \
   }
   DISPATCH_N(H, M)
 #undef M

@@ -51,7 +51,8 @@ double test() {
   int p = 1;
   for (int s = 0; s < P::NS; ++s) {
     int R = P::R[s];
-    if (R == 8) run_stage<N, 8, DIR>(tile, p, tw);
+    if (R == 16) run_stage<N, 16, DIR>(tile, p, tw);
+    else if (R == 8) run_stage<N, 8, DIR>(tile, p, tw);
     else if (R == 4) run_stage<N, 4, DIR>(tile, p, tw);
     else run_stage<N, 2, DIR>(tile, p, tw);
     p *= R;
