@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--fft", type=int, default=int(os.environ.get("SWW_FFT", "-1")), help="FFT backend: 0 cuFFT, 1 sm_100a passes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="after the timed region, one extra realisation with CUDA-event profiling per kernel family")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -283,6 +284,13 @@ def main():
         e2e = {"value": world * args.steps / dt, "unit": "realisations/s", "h2d_bytes_per_step": int(mesh.N * 8),
                "d2h_bytes_per_step": int((n_b * n_b + n_b) * 8), "note": "field H2D from pinned memory (double-buffered on a copy stream), F and q-bar D2H; host RNG not included"}
 
+    prof = None
+    if args.profile and rank == 0:
+        ctx.profile(True)
+        ctx.pk_fisher(a_dev[0], F_i, q_i)
+        prof = {k: {"launches": n, "ms": round(ms_, 3)} for k, (n, ms_) in ctx.profile_report().items()}
+        ctx.profile(False)
+
     if rank == 0:
         peaks = {}
         try:
@@ -306,6 +314,8 @@ def main():
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                              "kernel": "whole realisation step: algorithmic bytes = 16 N x (2M+1+2n_b) = %.4g B per realisation" % b_alg}}
+        if prof is not None:
+            line["profile_one_realisation"] = prof
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle.cpu_baseline import PkFisherSample

@@ -64,6 +64,10 @@ int sww_workspace_bytes(sww_ctx* c, int what, uint64_t* bytes);
 int sww_bind_workspace(sww_ctx* c, sww_devptr ws, uint64_t bytes);
 /* number of kernel launches (own kernels, cuFFT calls) issued by this context so far */
 int sww_launch_counts(sww_ctx* c, uint64_t* own_kernels, uint64_t* fft_calls);
+/* CUDA-event profiling of the library's own launches, aggregated per kernel family.
+ * enable != 0 starts a fresh recording; the report is a text table (name, launches, ms). */
+int sww_profile_enable(sww_ctx* c, int enable);
+int sww_profile_report(sww_ctx* c, char* buf, uint64_t buf_bytes);
 /* choose the FFT backend: 0 = cuFFT, 1 = hand-written sm_100a passes (power-of-two meshes) */
 int sww_set_fft_backend(sww_ctx* c, int backend);
 

@@ -120,6 +120,7 @@ extern "C" int sww_ctx_destroy(sww_ctx* c) {
   cudaFree(c->d_partial);
   cudaFree(c->d_counter);
   if (c->d_tris) cudaFree(c->d_tris);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return 0;
 }
@@ -204,5 +205,66 @@ extern "C" int sww_bk_set_triangles(sww_ctx* c, const int32_t* tris, int32_t n_t
   if (c->d_tris) cudaFree(c->d_tris);
   SWW_CUDA(cudaMalloc(&c->d_tris, sizeof(int) * 3 * (size_t)n_tri));
   SWW_CUDA(cudaMemcpy(c->d_tris, tris, sizeof(int) * 3 * (size_t)n_tri, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// profiling
+// ------------------------------------------------------------------------------------------
+ProfScope::ProfScope(sww_ctx* c_, const char* name) : c(c_), slot(-1) {
+  if (!c->prof_on) return;
+  int cat = -1;
+  for (size_t i = 0; i < c->prof_names.size(); ++i)
+    if (c->prof_names[i] == name) cat = (int)i;
+  if (cat < 0) {
+    cat = (int)c->prof_names.size();
+    c->prof_names.push_back(name);
+  }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  slot = (int)c->prof_cat.size();
+  c->prof_cat.push_back(cat);
+  c->prof_ev.push_back(a);
+  c->prof_ev.push_back(b);
+  cudaEventRecord(a, c->stream);
+}
+
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(c->prof_ev[2 * slot + 1], c->stream);
+}
+
+static void prof_clear(sww_ctx* c) {
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  c->prof_ev.clear();
+  c->prof_cat.clear();
+  c->prof_names.clear();
+}
+
+extern "C" int sww_profile_enable(sww_ctx* c, int enable) {
+  SWW_REQUIRE(c, "null context");
+  prof_clear(c);
+  c->prof_on = enable != 0;
+  return 0;
+}
+
+extern "C" int sww_profile_report(sww_ctx* c, char* buf, uint64_t n) {
+  SWW_REQUIRE(c && buf && n > 0, "null argument");
+  SWW_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<double> ms(c->prof_names.size(), 0.0);
+  std::vector<long long> cnt(c->prof_names.size(), 0);
+  for (size_t i = 0; i < c->prof_cat.size(); ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]);
+    ms[c->prof_cat[i]] += t;
+    cnt[c->prof_cat[i]]++;
+  }
+  std::string out;
+  char line[256];
+  for (size_t i = 0; i < ms.size(); ++i) {
+    snprintf(line, sizeof(line), "%-28s %8lld %12.3f\n", c->prof_names[i].c_str(), cnt[i], ms[i]);
+    out += line;
+  }
+  snprintf(buf, n, "%s", out.c_str());
   return 0;
 }

@@ -30,7 +30,7 @@ static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 int sww_fft_sm100_supported(const sww_ctx* c) {
   const Geo& g = c->g;
   auto ok = [](int n) { return is_pow2(n) && n >= 64 && n <= 1024; };
-  return ok(g.nx) && ok(g.ny) && ok(g.nz / 2) && is_pow2(g.nz);
+  return ok(g.nx) && ok(g.ny) && is_pow2(g.nz) && g.nz >= 128 && g.nz <= 1024;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -609,6 +609,291 @@ pass_z_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* 
 }
 
 // ------------------------------------------------------------------------------------------
+// Z pass, warp-per-row variant.  Each warp owns RW = max(1, 256/H) rows and a private padded
+// shared-memory buffer; stages are separated by __syncwarp only, so the warps of an SM are fully
+// independent and hide each other's global-memory latency (the CTA-cooperative variant above stalls
+// all its warps at every barrier).  Radix plans end (inverse) / start (forward) with radix 8, so the
+// seam between the inverse and the forward transform is register-resident:
+//   H = 64: 8,8   H = 128: 4,4,8   H = 256: 4,8,8   H = 512: 8,8,8      (forward: reversed)
+// Element index i of a row lives at i + (i >> 3) (one pad slot per 8): conflict-free 128-bit accesses
+// for every stage pattern.
+// ------------------------------------------------------------------------------------------
+template <int H> struct WPlan;
+template <> struct WPlan<64>  { static constexpr int NS = 2; static constexpr int R[3] = {8, 8, 1}; };
+template <> struct WPlan<128> { static constexpr int NS = 3; static constexpr int R[3] = {4, 4, 8}; };
+template <> struct WPlan<256> { static constexpr int NS = 3; static constexpr int R[3] = {4, 8, 8}; };
+template <> struct WPlan<512> { static constexpr int NS = 3; static constexpr int R[3] = {8, 8, 8}; };
+
+__device__ __forceinline__ int zpad(int i) { return i + (i >> 3); }
+
+template <int H, bool REV, int S>
+struct WRadix {
+  static constexpr int value = REV ? WPlan<H>::R[WPlan<H>::NS - 1 - S] : WPlan<H>::R[S];
+};
+template <int H, bool REV, int S>
+struct WProd {
+  static constexpr int value = WProd<H, REV, S - 1>::value * WRadix<H, REV, S - 1>::value;
+};
+template <int H, bool REV>
+struct WProd<H, REV, 0> {
+  static constexpr int value = 1;
+};
+
+// geometry of the warp's work: RW rows, butterfly index vb -> (row rho, bi)
+template <int H>
+struct WGeo {
+  static constexpr int RW = (H >= 256) ? 1 : 256 / H;
+  static constexpr int ROWLEN = H + H / 8 + 2;      // padded row (+ room for the Nyquist element at index H)
+  static constexpr int ELEMS = RW * H / 32;         // complex values per lane (8, or 16 for H = 512)
+};
+
+// middle stage S (load, twiddle, butterfly, store) entirely inside the warp
+template <int H, int DIR, bool REV, int S>
+__device__ __forceinline__ void w_mid_stage(double2* buf, const double2* tw, int lane) {
+  constexpr int R = WRadix<H, REV, S>::value;
+  constexpr int P = WProd<H, REV, S>::value;
+  constexpr int BPR = H / R;                         // butterflies per row
+  constexpr int IPT = WGeo<H>::RW * BPR / 32;
+  double2 u[IPT][R];
+#pragma unroll
+  for (int s = 0; s < IPT; ++s) {
+    const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+    const double2* row = buf + rho * WGeo<H>::ROWLEN;
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[s][r] = row[zpad(bi + r * BPR)];
+    stage_twiddle<R, DIR>(H, P, bi & (P - 1), tw, u[s]);
+    dftR<R, DIR>(u[s]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < IPT; ++s) {
+    const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+    double2* row = buf + rho * WGeo<H>::ROWLEN;
+    const int k = bi & (P - 1), j = (bi - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) row[zpad(j + r * P)] = u[s][r];
+  }
+  __syncwarp();
+}
+
+template <int H, int DIR, bool REV>
+__device__ __forceinline__ void w_mid_stages(double2* buf, const double2* tw, int lane) {
+  if constexpr (WPlan<H>::NS == 3) w_mid_stage<H, DIR, REV, 1>(buf, tw, lane);
+}
+
+template <int H, bool INV, bool FWD, bool YLM>
+__global__ void __launch_bounds__(256, 2)
+pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int WARPS = 8;
+  constexpr int RW = WGeo<H>::RW, ROWLEN = WGeo<H>::ROWLEN;
+  constexpr int SE = 8;                       // seam radix
+  constexpr int BPS = H / SE;                 // butterflies per row at the seam; outputs at bi + r*BPS
+  constexpr int IPS = RW * BPS / 32;          // seam butterflies per lane
+  double2* twh = reinterpret_cast<double2*>(smem_raw);   // [H]
+  double2* twn = twh + H;                                // [H+1]
+  double2* bufs = twn + (H + 8);                         // [WARPS][RW*ROWLEN (+8)]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double2* buf = bufs + warp * (RW * ROWLEN + 8);
+  for (int i = tid; i < H; i += 256) twh[i] = twh_g[i];
+  for (int i = tid; i <= H; i += 256) twn[i] = twn_g[i];
+  __syncthreads();
+  const long long ngroups = (long long)g.nx * g.ny / RW;
+  for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * WARPS) {
+    const long long row0 = grp * RW;
+    double2 u[IPS][SE];
+    double2 wv[IPS][SE];
+    // weights of the real-space step: issued first, consumed after the inverse transform
+    if (A.wmap) {
+#pragma unroll
+      for (int s = 0; s < IPS; ++s) {
+        const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+#pragma unroll
+        for (int r = 0; r < SE; ++r)
+          wv[s][r] = *reinterpret_cast<const double2*>(A.wmap + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
+      }
+    }
+    if (INV) {
+      // 1. complex input rows -> buffer (natural positions, padded)
+      __syncwarp();
+      for (int rho = 0; rho < RW; ++rho) {
+        const double2* src = A.Q + (row0 + rho) * A.Kzp_in;
+        double2* row = buf + rho * ROWLEN;
+        for (int k0 = lane; k0 < A.Kz_in; k0 += 128) {
+          double2 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (k0 + 32 * q < A.Kz_in) v[q] = src[k0 + 32 * q];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (k0 + 32 * q < A.Kz_in) row[zpad(k0 + 32 * q)] = v[q];
+        }
+      }
+      __syncwarp();
+      // 2. stage 0 of the inverse transform, inputs Y[k] built on the fly
+      {
+        constexpr int R = WRadix<H, false, 0>::value;
+        constexpr int BPR = H / R;
+        constexpr int IPT = RW * BPR / 32;
+        double2 y[IPT][R];
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+          const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+          const double2* row = buf + rho * ROWLEN;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int k = bi + r * BPR, hk = H - k;
+            double2 zk = (k < A.Kz_in) ? row[zpad(k)] : make_double2(0.0, 0.0);
+            double2 zh = (hk < A.Kz_in) ? row[zpad(hk)] : make_double2(0.0, 0.0);
+            if (k == 0) {
+              zk.y = 0.0;
+              zh.y = 0.0;
+            }
+            double2 a = make_double2(zk.x + zh.x, zk.y - zh.y);
+            double2 d = make_double2(zk.x - zh.x, zk.y + zh.y);
+            double2 w = twn[k];
+            w.y = -w.y;
+            double2 b = c_mul(d, w);
+            y[s][r] = make_double2(a.x - b.y, a.y + b.x);
+          }
+          dftR<R, -1>(y[s]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+          const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+          double2* row = buf + rho * ROWLEN;
+#pragma unroll
+          for (int r = 0; r < R; ++r) row[zpad(bi * R + r)] = y[s][r];
+        }
+        __syncwarp();
+      }
+      w_mid_stages<H, -1, false>(buf, twh, lane);
+      // last inverse stage (radix 8) -> registers, outputs at m = bi + r*BPS
+#pragma unroll
+      for (int s = 0; s < IPS; ++s) {
+        const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+        const double2* row = buf + rho * ROWLEN;
+#pragma unroll
+        for (int r = 0; r < SE; ++r) u[s][r] = row[zpad(bi + r * BPS)];
+        stage_twiddle<SE, -1>(H, BPS, bi, twh, u[s]);
+        dftR<SE, -1>(u[s]);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < IPS; ++s) {
+        const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+#pragma unroll
+        for (int r = 0; r < SE; ++r)
+          u[s][r] = *reinterpret_cast<const double2*>(A.real_in + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
+      }
+    }
+    // real-space step on registers
+#pragma unroll
+    for (int s = 0; s < IPS; ++s) {
+      const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+#pragma unroll
+      for (int r = 0; r < SE; ++r) {
+        double f0 = A.scale, f1 = A.scale;
+        if (A.wmap) {
+          f0 *= wv[s][r].x;
+          f1 *= wv[s][r].y;
+        }
+        if (YLM) {
+          const long long row = row0 + rho;
+          const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny), m = bi + r * BPS;
+          double X = g.rax[0][ix], Y = g.rax[1][iy];
+          double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
+          double r0 = sqrt(X * X + Y * Y + Z0 * Z0), r1 = sqrt(X * X + Y * Y + Z1 * Z1);
+          double i0 = 1.0 / (1e-12 + r0), i1 = 1.0 / (1e-12 + r1);
+          f0 *= sww_ylm_dyn(A.lm, X * i0, Y * i0, Z0 * i0);
+          f1 *= sww_ylm_dyn(A.lm, X * i1, Y * i1, Z1 * i1);
+        }
+        u[s][r].x *= f0;
+        u[s][r].y *= f1;
+      }
+    }
+    if (INV && !FWD) {
+      if (A.accumulate) {
+#pragma unroll
+        for (int s = 0; s < IPS; ++s) {
+          const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+#pragma unroll
+          for (int r = 0; r < SE; ++r)
+            wv[s][r] = *reinterpret_cast<const double2*>(A.real_out + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
+        }
+#pragma unroll
+        for (int s = 0; s < IPS; ++s)
+#pragma unroll
+          for (int r = 0; r < SE; ++r) {
+            u[s][r].x += wv[s][r].x;
+            u[s][r].y += wv[s][r].y;
+          }
+      }
+#pragma unroll
+      for (int s = 0; s < IPS; ++s) {
+        const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+#pragma unroll
+        for (int r = 0; r < SE; ++r)
+          *reinterpret_cast<double2*>(A.real_out + (row0 + rho) * g.nz + 2 * (bi + r * BPS)) = u[s][r];
+      }
+    }
+    if (FWD) {
+      // forward stage 0 (radix 8, reversed plan) straight from the registers
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < IPS; ++s) {
+        const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+        double2* row = buf + rho * ROWLEN;
+        dftR<SE, 1>(u[s]);
+#pragma unroll
+        for (int r = 0; r < SE; ++r) row[zpad(bi * SE + r)] = u[s][r];
+      }
+      __syncwarp();
+      w_mid_stages<H, 1, true>(buf, twh, lane);
+      // last forward stage -> natural order in the buffer
+      {
+        constexpr int R = WRadix<H, true, WPlan<H>::NS - 1>::value;
+        constexpr int BPR = H / R;
+        constexpr int IPT = RW * BPR / 32;
+        double2 v[IPT][R];
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+          const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+          const double2* row = buf + rho * ROWLEN;
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[s][r] = row[zpad(bi + r * BPR)];
+          stage_twiddle<R, 1>(H, BPR, bi, twh, v[s]);
+          dftR<R, 1>(v[s]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+          const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+          double2* row = buf + rho * ROWLEN;
+#pragma unroll
+          for (int r = 0; r < R; ++r) row[zpad(bi + r * BPR)] = v[s][r];
+        }
+        __syncwarp();
+      }
+      // T[k] = 1/2 (V[k] + conj V[H-k]) - i/2 e^{-2 pi i k/nz} (V[k] - conj V[H-k]),  V[H] = V[0]
+      for (int rho = 0; rho < RW; ++rho) {
+        const double2* row = buf + rho * ROWLEN;
+        double2* dst = A.R + (row0 + rho) * A.Kzp_out;
+        for (int k = lane; k < A.Kz_out; k += 32) {
+          int k1 = (k == H) ? 0 : k, k2 = (k == 0 || k == H) ? 0 : H - k;
+          double2 v1 = row[zpad(k1)], v2 = row[zpad(k2)];
+          double2 ev = make_double2(0.5 * (v1.x + v2.x), 0.5 * (v1.y - v2.y));
+          double2 dv = make_double2(0.5 * (v1.x - v2.x), 0.5 * (v1.y + v2.y));
+          double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);
+          dst[k] = make_double2(ev.x + od.x, ev.y + od.y);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct Sm100State {
@@ -729,6 +1014,7 @@ static int occ_for(size_t smem) {
 }
 
 static int run_i1(sww_ctx* c, Sm100State* s, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* src, int shell) {
+  SWW_PROF(c, "fft.I1 x-inverse");
   const int N = c->g.nx;
   size_t smem = col_smem(N, 0);
   long long items = (long long)by.K * (Kzp / FFT_TZ);
@@ -744,6 +1030,7 @@ static int run_i1(sww_ctx* c, Sm100State* s, BoxAxis bx, BoxAxis by, int Kz, int
 }
 
 static int run_i2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
+  SWW_PROF(c, "fft.I2 y-inverse");
   const int N = c->g.ny;
   size_t smem = col_smem(N, 0);
   long long items = (long long)c->g.nx * (Kzp / FFT_TZ);
@@ -759,6 +1046,7 @@ static int run_i2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
 }
 
 static int run_f2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
+  SWW_PROF(c, "fft.F2 y-forward");
   const int N = c->g.ny;
   size_t smem = col_smem(N, 0);
   long long items = (long long)c->g.nx * (Kzp / FFT_TZ);
@@ -774,6 +1062,7 @@ static int run_f2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
 }
 
 static int run_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bx, BoxAxis by, int Kz, int Kzp, F3Args A) {
+  SWW_PROF(c, mode == 2 ? "fft.F3 x-forward+bin" : (mode == 1 ? "fft.F3 x-forward+ylm" : "fft.F3 x-forward+store"));
   const int N = c->g.nx;
   int hist = (mode == 2) ? (N / 2 / 32) * A.n_g * c->g.n_k : 0;
   size_t smem = col_smem(N, hist);
@@ -803,32 +1092,39 @@ static int run_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bx, BoxAxis by, i
 }
 
 template <int H, bool INV, bool FWD, bool YLM>
-static int launch_z(sww_ctx* c, Sm100State* s, ZArgs A, int grid, size_t smem, int SP) {
-  SWW_TRY(set_smem(pass_z_kernel<H, INV, FWD, YLM>, smem));
-  pass_z_kernel<H, INV, FWD, YLM><<<grid, H / 2, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, SP);
+static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 8;
+  size_t smem = (size_t)(H + H + 8) * 16 + (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16;
+  long long ngroups = (long long)c->g.nx * c->g.ny / WGeo<H>::RW;
+  long long ctas = (ngroups + WARPS - 1) / WARPS;
+  int grid = (int)(ctas < SMS * 2 ? ctas : SMS * 2);
+  SWW_TRY(set_smem(pass_zw_kernel<H, INV, FWD, YLM>, smem));
+  pass_zw_kernel<H, INV, FWD, YLM><<<grid, 256, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n);
   return 0;
 }
 
 static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
+  SWW_PROF(c, inv && fwd ? "fft.Z c2r*w*r2c fused" : (inv ? "fft.Z c2r" : "fft.Z r2c"));
   const int H = c->g.nz / 2;
-  const int Kz_in = inv ? A.Kz_in : 0;
-  const int SP = z_stage_pitch(Kz_in);
-  size_t smem = z_smem(H, Kz_in);
-  long long groups = (long long)c->g.nx * c->g.ny / FFT_TZ;
-  int grid = grid_for_items(groups, occ_for(smem));
   const bool ylm = A.lm >= 0;
-#define M(HH)                                                                       \
-  if (inv && fwd) {                                                                 \
-    SWW_REQUIRE(!ylm, "fused z pass has no Y_lm variant");                         \
-    SWW_TRY((launch_z<HH, true, true, false>(c, s, A, grid, smem, SP)));            \
-  } else if (inv) {                                                                 \
-    if (ylm) SWW_TRY((launch_z<HH, true, false, true>(c, s, A, grid, smem, SP)));   \
-    else SWW_TRY((launch_z<HH, true, false, false>(c, s, A, grid, smem, SP)));      \
-  } else {                                                                          \
-    if (ylm) SWW_TRY((launch_z<HH, false, true, true>(c, s, A, grid, smem, SP)));   \
-    else SWW_TRY((launch_z<HH, false, true, false>(c, s, A, grid, smem, SP)));      \
+#define M(HH)                                                      \
+  if (inv && fwd) {                                                \
+    SWW_REQUIRE(!ylm, "fused z pass has no Y_lm variant");        \
+    SWW_TRY((launch_zw<HH, true, true, false>(c, s, A)));          \
+  } else if (inv) {                                                \
+    if (ylm) SWW_TRY((launch_zw<HH, true, false, true>(c, s, A))); \
+    else SWW_TRY((launch_zw<HH, true, false, false>(c, s, A)));    \
+  } else {                                                         \
+    if (ylm) SWW_TRY((launch_zw<HH, false, true, true>(c, s, A))); \
+    else SWW_TRY((launch_zw<HH, false, true, false>(c, s, A)));    \
   }
-  DISPATCH_N(H, M)
+  switch (H) {
+    case 64: M(64); break;
+    case 128: M(128); break;
+    case 256: M(256); break;
+    case 512: M(512); break;
+    default: SWW_REQUIRE(false, "unsupported z length %d", 2 * H);
+  }
 #undef M
   c->n_own++;
   SWW_CUDA(cudaGetLastError());

@@ -118,7 +118,21 @@ struct sww_ctx {
   double* d_partial = nullptr;
   size_t partial_elems = 0;
   unsigned int* d_counter = nullptr;
+  // profiling
+  bool prof_on = false;
+  std::vector<std::string> prof_names;
+  std::vector<int> prof_cat;
+  std::vector<cudaEvent_t> prof_ev;   // pairs
 };
+
+// ---- profiling (ctx.cu): events around the library's own launches
+struct ProfScope {
+  sww_ctx* c;
+  int slot;
+  ProfScope(sww_ctx* c, const char* name);
+  ~ProfScope();
+};
+#define SWW_PROF(c, name) ProfScope prof_scope__(c, name)
 
 static inline int sww_grid_for(long long n, int block, int max_blocks = 148 * 16) {
   long long b = (n + block - 1) / block;

@@ -173,6 +173,20 @@ class Context:
         _lib.check(self.lib.sww_launch_counts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def profile(self, enable=True):
+        """Start (or stop) CUDA-event profiling of the library's own launches."""
+        _lib.check(self.lib.sww_profile_enable(self._h, int(bool(enable))))
+
+    def profile_report(self):
+        """{kernel family: (launches, total ms)} since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(self.lib.sww_profile_report(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line[:28].strip(), line[28:].split()[0], line[28:].split()[1]
+            out[name] = (int(n), float(ms))
+        return out
+
     def set_fft_backend(self, backend: int):
         _lib.check(self.lib.sww_set_fft_backend(self._h, int(backend)))
 

@@ -38,7 +38,8 @@ def test_backend_rejects_unsupported_mesh(eng, world):
         ctx.set_fft_backend(1)
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 128), (128, 64, 256), (64, 256, 128)])
+@pytest.mark.parametrize("shape", [(64, 64, 128), (128, 64, 256), (64, 256, 128), (64, 64, 512), (512, 64, 1024),
+                                   (64, 1024, 128)])
 def test_generic_transforms(eng, shape):
     box = tuple(20.0 * s for s in shape)
     mesh = eng.Mesh(box, shape, (0.0, 0.0, 0.0), 0.0, 0.1, 0.05, 0)
@@ -103,4 +104,26 @@ def test_bk_pipelines_on_fused_chains(eng, world, golden):
     qa = np.concatenate([q[:, l] / D[l * nt:(l + 1) * nt] for l in range(mesh.n_l)])
     p = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qa)
     assert relerr(p, g["bk_p"][:, 3:].T.ravel()) < 2e-8
+    ctx.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 128, 512), (128, 64, 1024)])
+def test_fused_chains_agree_with_cufft_backend(eng, shape):
+    """Every radix plan of the fused z pass (H = 256, 512) against the cuFFT backend (itself pinned to
+    the oracle at small sizes): P_l Fisher matrix and q-bar of one realisation on a masked n(r)."""
+    from spectra_without_windows_b200 import synthetic as syn
+    box = tuple(18.0 * s for s in shape)
+    bc = (2.0 * box[0], 30.0, -20.0)
+    mesh = eng.Mesh(box, shape, bc, 0.0, 0.12, 0.02, 4)
+    ctx = eng.Context(mesh, 0, ("pk_fisher",))
+    n_gal = syn.survey_nbar(box, shape, bc, n0=3e-4)
+    nbar_r = n_gal / 0.05
+    nbar_A = ctx.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)
+    a = np.random.default_rng(2).normal(size=shape) * np.sqrt(nbar_A)
+    F0, q0 = ctx.pk_fisher(a)
+    F0, q0 = F0.cpu().numpy(), q0.cpu().numpy()
+    ctx.set_fft_backend(1)
+    F1, q1 = ctx.pk_fisher(a)
+    assert relerr(F1.cpu().numpy(), F0) < 1e-11
+    assert relerr(q1.cpu().numpy(), q0) < 1e-11
     ctx.close()
