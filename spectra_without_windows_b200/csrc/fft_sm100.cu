@@ -342,22 +342,30 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
         }
       }
     } else {
-      // shell binning: loads are batched four elements deep (bin indices, then the G_l' values)
-      constexpr int GRP = 2;
+      // shell binning.  The spectrum goes back to the tile (natural order) so that only box rows are
+      // visited and the global loads (bin index, then G_l') can be batched four elements deep.
+      __syncthreads();   // all threads are done reading the tile in the last stage
 #pragma unroll
-      for (int e0 = 0; e0 < 16; e0 += GRP) {
+      for (int s = 0; s < 16 / RL; ++s) {
+        const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) tile[(bi + r * (N / RL)) * FFT_LDT + cc] = u[s][r];
+      }
+      __syncthreads();
+      constexpr int GRP = 4;
+      const int total = bx.K * FFT_TZ;
+      for (int e0 = 0; e0 < total; e0 += GRP * NT) {   // uniform trip count (warp collectives below)
         int bq[GRP];
         long long cellq[GRP];
-        double wq[GRP];
+        int ixq[GRP];
 #pragma unroll
         for (int j = 0; j < GRP; ++j) {
-          const int e = e0 + j, s = e / RL, r = e % RL;
-          const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7, iz = iz0 + cc;
-          const int ix = bi + r * (N / RL);
-          const bool inb = bx.has(ix) && iz < Kz;
-          cellq[j] = ((long long)ix * g.ny + iy) * g.nzh + iz;
+          const int e = e0 + j * NT + tid;
+          const int jx = e >> 3, cc = e & 7, iz = iz0 + cc;
+          const bool inb = (e < total) && iz < Kz;
+          ixq[j] = inb ? bx.idx(jx) : 0;
+          cellq[j] = ((long long)ixq[j] * g.ny + iy) * g.nzh + iz;
           bq[j] = inb ? (int)g.binmap[cellq[j]] : SWW_NO_BIN;
-          wq[j] = (iz == 0 || (nz_even && iz == g.nz / 2)) ? 1.0 : 2.0;
         }
         double2 Gq[GRP][3];
 #pragma unroll
@@ -367,27 +375,42 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
             if (q < A.n_g && bq[j] != SWW_NO_BIN) Gq[j][q] = A.G[q][cellq[j]];
 #pragma unroll
         for (int j = 0; j < GRP; ++j) {
-          const int e = e0 + j, s = e / RL, r = e % RL;
-          const double2 t = u[s][r];
+          const int cc = tid & 7, iz = iz0 + cc;
           const int b = bq[j];
           double v[3] = {0.0, 0.0, 0.0};
           if (b != SWW_NO_BIN) {
+            const double2 t = tile[ixq[j] * FFT_LDT + cc];
+            const double wq = (iz == 0 || (nz_even && iz == g.nz / 2)) ? 1.0 : 2.0;
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-              if (q < A.n_g) v[q] = wq[j] * (t.x * Gq[j][q].x + t.y * Gq[j][q].y);
+              if (q < A.n_g) v[q] = wq * (t.x * Gq[j][q].x + t.y * Gq[j][q].y);
           }
-          unsigned rem = __ballot_sync(0xffffffffu, b != SWW_NO_BIN);
-          while (rem) {
-            int srcl = __ffs(rem) - 1;
-            int cur = __shfl_sync(0xffffffffu, b, srcl);
-            bool mine = (b == cur);
+          // The 8 lanes of a quarter-warp hold 8 consecutive iz of one (ix, iy): |k| grows with iz, so
+          // equal bins form contiguous runs.  Segmented shuffle reduction over the runs (3 steps), then
+          // the run heads add into the warp-private histogram, one 8-lane row at a time (rows may
+          // share a bin; within a row the heads' bins are distinct).  Fixed order -> deterministic.
+          const int l8 = lane & 7;
+#pragma unroll
+          for (int d = 1; d < 8; d <<= 1) {
+            const int nbk = __shfl_down_sync(0xffffffffu, b, d);
+            const bool take = (l8 + d < 8) && (nbk == b);
 #pragma unroll
             for (int q = 0; q < 3; ++q)
               if (q < A.n_g) {
-                double sm = warp_sum_f(mine ? v[q] : 0.0);
-                if (lane == 0) hist[warp * nb + q * g.n_k + cur] += sm;
+                const double nv = __shfl_down_sync(0xffffffffu, v[q], d);
+                if (take) v[q] += nv;
               }
-            rem &= ~__ballot_sync(0xffffffffu, mine);
+          }
+          const int pbk = __shfl_up_sync(0xffffffffu, b, 1);
+          const bool head = (b != SWW_NO_BIN) && (l8 == 0 || pbk != b);
+#pragma unroll
+          for (int rowq = 0; rowq < 4; ++rowq) {
+            if (head && (lane >> 3) == rowq) {
+#pragma unroll
+              for (int q = 0; q < 3; ++q)
+                if (q < A.n_g) hist[warp * nb + q * g.n_k + b] += v[q];
+            }
+            __syncwarp();
           }
         }
       }
