@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="C2")
-    ap.add_argument("--fft", type=int, default=int(os.environ.get("SWW_FFT", "-1")), help="FFT backend: 0 cuFFT, 1 sm_100a passes")
+    ap.add_argument("--fft", type=int, default=-1, help="FFT backend: 0 cuFFT, 1 hand-written sm_100a passes (default: auto = 1 on power-of-two meshes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="after the timed region, one extra realisation with CUDA-event profiling per kernel family")
@@ -306,7 +306,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args.workload, mesh),
-                "fft_backend": "sm100a-passes" if args.fft == 1 else "cufft",
+                "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
                 "gpu_launches": int((own1 - own0) + (fft1 - fft0)),
                 "own_kernel_launches": int(own1 - own0), "fft_calls": int(fft1 - fft0),
                 "clocks": clocks, "e2e": e2e,

@@ -5,6 +5,7 @@ pinned host buffers and streams.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -134,6 +135,15 @@ class Context:
         self.use_stream(t.cuda.current_stream(self.device))
         _lib.check(self.lib.sww_bind_workspace(self._h, self.workspace.data_ptr(), int(need)))
         self._fields = None
+        # FFT backend: the hand-written sm_100a passes wherever the mesh allows (power-of-two sizes),
+        # cuFFT plans otherwise.  SWW_FFT=0/1 forces one.
+        want = os.environ.get("SWW_FFT", "auto")
+        self.fft_backend = 0
+        if want != "0":
+            if self.lib.sww_set_fft_backend(self._h, 1) == 0:
+                self.fft_backend = 1
+            elif want == "1":
+                _lib.check(-1)
 
     # -- plumbing
     def use_stream(self, stream):
@@ -189,6 +199,7 @@ class Context:
 
     def set_fft_backend(self, backend: int):
         _lib.check(self.lib.sww_set_fft_backend(self._h, int(backend)))
+        self.fft_backend = int(backend)
 
     # -- fields
     def set_fields(self, nbar, nbar_weight, nbar_A, shot_fac, P_fkp=1e4):

@@ -1,0 +1,142 @@
+"""Monte-Carlo Fisher driver: all N_mc realisations of a .param file on 1..8 GPUs.
+
+The reference runs one OS process per seed under SLURM and reduces through files
+(slurm/pk_randoms_boss_nC.slurm:24-35, pk/compute_pk_data.py:227-233).  Here the seeds are dealt
+round-robin to the ranks of one torch.distributed job (one process per GPU), every rank accumulates
+its partial sums on the device, and ONE all-reduce of n_b^2 + n_b doubles ends the run; rank 0 writes
+the combined `fisher-pk_*` / `bias-pk_*` (or `fisher-bk_*`) files the data scripts read.  There is no
+data-path collective: realisations are independent.
+
+    torchrun --nproc-per-node 8 -m spectra_without_windows_b200.mc_driver pk <paramfile> [--per-seed]
+
+`--per-seed` also writes the reference's per-seed checkpoint files, and seeds whose files already
+exist are skipped (the reference's idempotent re-entry, pk/compute_pk_randoms.py:121-127).
+The Gaussian fields come from numpy's legacy stream with the reference's seeds
+(pk/compute_pk_randoms.py:139-140), drawn by a small pool of host workers that runs ahead of the GPU.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+
+def shard(items, rank, world):
+    """Round-robin deal of work items to ranks."""
+    return list(items)[rank::world]
+
+
+def reduce_sums(parts, world_ok, dist=None):
+    """All-reduce (sum) a list of tensors in place when running distributed."""
+    if world_ok and dist is not None:
+        for p in parts:
+            dist.all_reduce(p)
+    return parts
+
+
+def run_mc(seeds, realisation_fn, zeros_fn, rank=0, world=1, dist=None, prefetch_fn=None, workers=2):
+    """Generic sharded Monte-Carlo accumulation.
+
+    seeds           : all work items (e.g. rand_it = 1..N_mc, or pair indices for the bispectrum)
+    realisation_fn  : (seed, prefetched) -> tuple of tensors to accumulate
+    zeros_fn        : () -> tuple of zero tensors with the shapes of the sums
+    prefetch_fn     : seed -> host object (e.g. the numpy Gaussian field), run ahead on host threads
+    Returns (sums after all-reduce, number of items this rank processed).
+    """
+    mine = shard(seeds, rank, world)
+    sums = zeros_fn()
+    pool = ThreadPoolExecutor(max_workers=max(1, workers)) if prefetch_fn else None
+    futs = {}
+    if pool:
+        for s in mine[:workers + 1]:
+            futs[s] = pool.submit(prefetch_fn, s)
+    for i, s in enumerate(mine):
+        pre = None
+        if pool:
+            pre = futs.pop(s).result()
+            nxt = i + workers + 1
+            if nxt < len(mine):
+                futs[mine[nxt]] = pool.submit(prefetch_fn, mine[nxt])
+        out = realisation_fn(s, pre)
+        for acc, o in zip(sums, out):
+            acc += o
+    if pool:
+        pool.shutdown()
+    reduce_sums(sums, world > 1, dist)
+    return sums, len(mine)
+
+
+def main(argv):
+    import torch
+    import torch.distributed as dist
+    from . import drivers
+
+    if len(argv) < 3 or argv[1] not in ("pk", "bk"):
+        raise Exception("usage: mc_driver.py <pk|bk> <paramfile> [--per-seed]")
+    spec, paramfile = argv[1], argv[2]
+    per_seed = "--per-seed" in argv
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = drivers.Params(paramfile, spec)
+    P.unsupported()
+    for d in (P.outdir, P.mcdir):
+        os.makedirs(d, exist_ok=True)
+    tag = P.ktag()
+    ctx, mesh, nbar_A, alpha_ran, shot_fac, _ = drivers._setup(P, 1, ("pk_fisher",) if spec == "pk" else ("bk_fisher",), paint_data=False)
+    sig = np.sqrt(nbar_A)
+
+    def grf(seed):
+        # numpy's legacy global stream is not thread-safe: a private RandomState gives the same values
+        # as np.random.seed(seed); np.random.normal(...)  (pk/compute_pk_randoms.py:139-140)
+        return np.random.RandomState(seed).normal(loc=0.0, scale=sig, size=sig.shape)
+
+    if spec == "pk":
+        n_b = ctx.n_b
+        fish_name = lambda r: P.mcdir + "%s%d_%s_pk_fish_a_%s.npy" % (P.string, r, P.weight_type, tag)
+        bias_name = lambda r: P.mcdir + "%s%d_%s_pk_q-bar_a_%s.npy" % (P.string, r, P.weight_type, tag)
+
+        def one(seed, a):
+            if per_seed and os.path.exists(fish_name(seed)) and os.path.exists(bias_name(seed)):
+                return ctx.dev(np.load(fish_name(seed))), ctx.dev(np.load(bias_name(seed)))
+            F, q = ctx.pk_fisher(a)
+            if per_seed:
+                np.save(fish_name(seed), F.cpu().numpy())
+                np.save(bias_name(seed), q.cpu().numpy())
+            return F, q
+
+        (F, q), n = run_mc(range(1, P.N_mc + 1), one, lambda: (ctx.zeros((n_b, n_b)), ctx.zeros((n_b,))), rank, world,
+                           dist if world > 1 else None, prefetch_fn=grf)
+        if rank == 0:
+            np.save(P.outdir + "fisher-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (F / P.N_mc).cpu().numpy())
+            np.save(P.outdir + "bias-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (q / P.N_mc).cpu().numpy())
+    else:
+        n_b = ctx.n_b_bk
+        fish_name = lambda r: P.mcdir + "%s%d_%s_bk_fish_alpha_beta_%s.npy" % (P.string, r, P.weight_type, tag)
+        bias_name = lambda ii: P.mcdir + "%s%d_%s_bk_bias_alpha_%s.npz" % (P.string, ii, P.weight_type, tag)
+        maps = None
+
+        def one(pair, ab):
+            nonlocal maps
+            F, maps = ctx.bk_fisher_pair(ab[0], ab[1], maps)
+            # the g-maps of every seed feed the 1-field term of compute_bk_data.py (bk/compute_bk_randoms.py:273-274)
+            drivers.save_gmaps(bias_name(2 * pair), maps[0], maps[1])
+            drivers.save_gmaps(bias_name(2 * pair + 1), maps[2], maps[3])
+            if per_seed:
+                np.save(fish_name(pair), F.cpu().numpy())
+            return (F,)
+
+        (F,), n = run_mc(range(1, P.N_mc // 2 + 1), one, lambda: (ctx.zeros((n_b, n_b)),), rank, world,
+                         dist if world > 1 else None, prefetch_fn=lambda p: (grf(2 * p), grf(2 * p + 1)), workers=1)
+        if rank == 0:
+            np.save(P.outdir + "fisher-bk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (F / (P.N_mc // 2)).cpu().numpy())
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv)

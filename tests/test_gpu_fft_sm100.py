@@ -34,6 +34,7 @@ def test_backend_rejects_unsupported_mesh(eng, world):
     w = world("toyA")
     mesh = eng.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
     ctx = eng.get_context(mesh, 0, ("ops", "pk_fisher", "pk_data"))
+    assert ctx.fft_backend == 0          # auto-selection fell back to cuFFT on a 32x24x20 mesh
     with pytest.raises(Exception, match="power-of-two"):
         ctx.set_fft_backend(1)
 
@@ -116,6 +117,8 @@ def test_fused_chains_agree_with_cufft_backend(eng, shape):
     bc = (2.0 * box[0], 30.0, -20.0)
     mesh = eng.Mesh(box, shape, bc, 0.0, 0.12, 0.02, 4)
     ctx = eng.Context(mesh, 0, ("pk_fisher",))
+    assert ctx.fft_backend == 1
+    ctx.set_fft_backend(0)
     n_gal = syn.survey_nbar(box, shape, bc, n0=3e-4)
     nbar_r = n_gal / 0.05
     nbar_A = ctx.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)

@@ -59,3 +59,24 @@ def test_error_behaviour(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "pk/compute_pk_data.py"), "1", str(tmp_path) + "/nope.param"],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "Parameter file does not exist!" in r.stderr
+
+
+def test_mc_driver_writes_combined_files(world, golden, tmp_path):
+    """The sharded MC driver (here 1 rank) reproduces the combined Fisher / bias files that
+    compute_pk_data.py would fold from the per-seed files, and the bk combined Fisher."""
+    from spectra_without_windows_b200 import synthetic as syn
+    w, g = world("toyD"), golden("toyD")
+    p = syn.write_world_files(w, str(tmp_path))
+    od = str(tmp_path) + "/out/"
+    for spec in ("pk", "bk"):
+        r = subprocess.run([sys.executable, "-m", "spectra_without_windows_b200.mc_driver", spec, p], capture_output=True,
+                           text=True, cwd=ROOT)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert relerr(np.load(glob.glob(od + "fisher-pk_*.npy")[0]), g["pk_fish_comb"]) < 1e-9
+    assert relerr(np.load(glob.glob(od + "bias-pk_*.npy")[0]), g["pk_bias_comb"]) < 1e-9
+    assert relerr(np.load(glob.glob(od + "fisher-bk_*.npy")[0]), g["bk_fish_comb"]) < 1e-9
+    # and the data scripts pick the combined files up
+    run("pk/compute_pk_data.py", 1, p)
+    run("bk/compute_bk_data.py", 1, p)
+    assert relerr(np.loadtxt(glob.glob(od + "pk_*.txt")[0]), g["pk_p"]) < 2e-8
+    assert relerr(np.loadtxt(glob.glob(od + "bk_*.txt")[0]), g["bk_p"]) < 2e-8
