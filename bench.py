@@ -285,7 +285,7 @@ def main():
                "d2h_bytes_per_step": int((n_b * n_b + n_b) * 8), "note": "field H2D from pinned memory (double-buffered on a copy stream), F and q-bar D2H; host RNG not included"}
 
     prof = None
-    if args.profile and rank == 0:
+    if rank == 0 and (args.profile or ctx.fft_backend == 1):
         ctx.profile(True)
         ctx.pk_fisher(a_dev[0], F_i, q_i)
         prof = {k: {"launches": n, "ms": round(ms_, 3)} for k, (n, ms_) in ctx.profile_report().items()}
@@ -302,18 +302,40 @@ def main():
         nfft = n_fft_min(M, n_b)
         b_alg = 16.0 * mesh.N * nfft            # bytes per realisation (SURVEY.md section 8d convention)
         achieved = b_alg * (args.steps / (ms * 1e-3)) / 1e9   # per GPU
+        step_roof = {"achieved": achieved, "frac": achieved / peak, "unit": "GB/s",
+                     "algorithmic_bytes_per_realisation": b_alg,
+                     "definition": "16 N bytes per 3-D transform x (2M+1+2n_b) transforms per realisation (SURVEY.md 8d) / measured step time"}
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                "kernel": "whole realisation step", "step": step_roof}
+        zkey = "fft.Z c2r*w*r2c fused"
+        if prof is not None and zkey in prof:
+            # dominant kernel: the fused z pass (c2r * nW * r2c in shared memory).  Algorithmic bytes per launch =
+            # the weight map (8 N) + the complex input rows of the shell's box + the complex output rows of the k_max box.
+            nx, ny, nz = (int(v) for v in mesh.grid)
+            kFz = 2.0 * np.pi / mesh.box[2]
+            kz_of = lambda kmax: min(int(np.floor(np.nextafter(kmax / kFz, 0))) + 1, nz // 2 + 1)
+            kz_out = kz_of(mesh.k_hi[-1])
+            kz_in_mean = float(np.mean([kz_of(k) for k in mesh.k_hi]))
+            bytes_launch = 8.0 * mesh.N + 16.0 * nx * ny * (kz_in_mean + kz_out)
+            dur = prof[zkey]["ms"] / prof[zkey]["launches"] * 1e-3
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            roof.update({"kernel": "pass_zw_kernel<256,INV,FWD> (fused z pass of one Fisher row), avg over %d launches of one realisation, CUDA events on the launching stream" % prof[zkey]["launches"],
+                         "achieved": bytes_launch / dur / 1e9, "frac": bytes_launch / dur / 1e9 / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": dur * 1e3,
+                         "share_of_step": prof[zkey]["ms"] / (ms / args.steps)})
         line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args.workload, mesh),
                 "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
-                "gpu_launches": int((own1 - own0) + (fft1 - fft0)),
-                "own_kernel_launches": int(own1 - own0), "fft_calls": int(fft1 - fft0),
-                "clocks": clocks, "e2e": e2e,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
-                             "kernel": "whole realisation step: algorithmic bytes = 16 N x (2M+1+2n_b) = %.4g B per realisation" % b_alg}}
+                "gpu_launches": int((own1 - own0) + (fft1 - fft0)) if ctx.fft_backend == 0 else int(own1 - own0),
+                "own_kernel_launches": int(own1 - own0), "library_fft_calls": int(fft1 - fft0) if ctx.fft_backend == 0 else 0,
+                "clocks": clocks, "e2e": e2e, "roofline": roof}
         if prof is not None:
             line["profile_one_realisation"] = prof
         if world == 1 and not args.no_cpu_baseline:
