@@ -32,6 +32,11 @@ WORKLOADS = {
                bins=(0.0, 0.40, 0.005, 4)),
     "C1F": dict(grid=(128, 128, 128), box=(1000.0, 1000.0, 1000.0), box_center=(0.0, 0.0, 2000.0),
                 bins=(0.0, 0.25, 0.01, 4)),
+    # bispectrum Fisher (a step = one PAIR of realisations): 256^3, k in [0,0.11] dk=0.01, l<=4 -> 191 triangles, n_b=573
+    "C4": dict(grid=(256, 256, 256), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
+               bins=(0.0, 0.11, 0.01, 4), bk=True),
+    "C4S": dict(grid=(128, 128, 128), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
+                bins=(0.0, 0.11, 0.01, 2), bk=True),
     "S256": dict(grid=(256, 256, 256), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
                  bins=(0.0, 0.20, 0.005, 4)),
 }
@@ -141,6 +146,78 @@ def workload_config(name, mesh):
             "l2": "inputs>L2 (every map is >= 1 GB, L2 is 126 MB)" if mesh.N * 8 > 2 * 126e6 else "maps fit L2 partially; 512 MB scratch written between steps"}
 
 
+def run_bk(args, wl, mesh, rank, world, local, dev):
+    """Bispectrum Fisher: one step = one pair of realisations (bk/compute_bk_randoms.py)."""
+    import torch
+    import torch.distributed as dist
+    from spectra_without_windows_b200 import engine
+    ctx = engine.Context(mesh, local, ("bk_fisher",))
+    if args.fft >= 0:
+        ctx.set_fft_backend(args.fft)
+    rax_d = [torch.from_numpy(a).to(dev) for a in mesh.rax]
+    nbar_r = survey_nbar_r(rax_d, torch).contiguous()
+    nbar = (nbar_r * ALPHA).contiguous()
+    nbar_A = nbar_r.clone()
+    nbar_A[nbar_A == 0] = float(nbar_r[nbar_r != 0].min()) * 0.01
+    ctx.set_fields(nbar, nbar, nbar_A, SHOT)
+    sig = torch.sqrt(nbar_A)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + rank)
+    aA = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig
+    aB = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig
+    n_b = ctx.n_b_bk
+    ctx.bk_delta()
+    F_acc = torch.zeros((n_b, n_b), dtype=torch.float64, device=dev)
+    maps = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        F, maps = ctx.bk_fisher_pair(aA, aB, maps)
+    barrier()
+    own0, fft0 = ctx.launch_counts()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        F, maps = ctx.bk_fisher_pair(aA, aB, maps)
+        F_acc.add_(F)
+    if world > 1:
+        dist.all_reduce(F_acc)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    own1, fft1 = ctx.launch_counts()
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    prof = None
+    if rank == 0:
+        ctx.profile(True)
+        ctx.bk_fisher_pair(aA, aB, maps)
+        prof = {k: {"launches": n, "ms": round(m_, 3)} for k, (n, m_) in ctx.profile_report().items()}
+        ctx.profile(False)
+        value = 2.0 * world * args.steps / (ms * 1e-3)
+        line = {"metric": "bk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: compute_bk_randoms Fisher pair (2 realisations per step), mesh %s, k in [%.3f,%.3f] dk=%.3f lmax=%d, %d triangles, n_b=%d"
+                           % (args.workload, "x".join(str(int(g)) for g in mesh.grid), mesh.k_min, mesh.k_max, mesh.dk, mesh.lmax, ctx.n_tri, n_b),
+                           "l2": "inputs>L2"},
+                "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
+                "gpu_launches": int(own1 - own0), "clocks": clocks, "profile_one_pair": prof,
+                "gram_flop_per_pair": 2.0 * n_b * n_b * mesh.N}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +249,8 @@ def main():
 
     wl = WORKLOADS[args.workload]
     mesh = engine.Mesh(wl["box"], wl["grid"], wl["box_center"], *wl["bins"])
+    if wl.get("bk"):
+        return run_bk(args, wl, mesh, rank, world, local, dev)
     ctx = engine.Context(mesh, local, ("pk_fisher",))
     if args.fft >= 0:
         ctx.set_fft_backend(args.fft)

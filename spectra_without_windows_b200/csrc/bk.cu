@@ -210,6 +210,7 @@ triple_sum_kernel(long long N, TripleTerms T, double* __restrict__ partial, unsi
 }
 
 static int run_triple_terms(sww_ctx* c, const TripleTerms& T, double* out) {
+  SWW_PROF(c, "bk.triple_sum");
   int grid = SMS * 4;
   SWW_REQUIRE((size_t)grid * TS_MAX_TERMS <= c->partial_elems, "triple_sum: partial buffer too small");
   triple_sum_kernel<<<grid, 256, 0, c->stream>>>(c->g.N, T, c->d_partial, c->d_counter, out);
@@ -414,6 +415,7 @@ extern "C" int sww_bk_gmaps(sww_ctx* c, sww_devptr a, int data, sww_devptr g_out
 
 static int assemble(sww_ctx* c, BkBufs& b, const double2* p0, int s0, const double2* p1, int s1, const double2* p2,
                     int s2, int lm, double coef) {
+  SWW_PROF(c, "bk.assemble");
   // the sm_100a inverse chain only reads the pruning box; cuFFT reads (and destroys) the whole array
   if (c->fft_backend != 1) SWW_CUDA(cudaMemsetAsync(b.X, 0, sizeof(double2) * c->g.Nc, c->stream));
   assemble_kernel<<<SMS * 2, 64, 0, c->stream>>>(c->g, p0, s0, p1, s1, p2, s2, lm, coef, b.X);
@@ -497,8 +499,11 @@ extern "C" int sww_bk_fisher_pair(sww_ctx* c, sww_devptr aA, sww_devptr aB, sww_
     double2* dst = kind ? b.PST : b.PS;
     for (int s = 0; s < n_slots; ++s) {
       size_t o1 = ((size_t)0 * n_k + P.i[s]) * N, o2 = ((size_t)P.l[s] * n_k + P.j[s]) * N;
-      prod_diff_kernel<<<SMS * 8, 256, 0, c->stream>>>(c->g.N, XA + o1, XA + o2, XB + o1, XB + o2, b.tmp);
-      SWW_TRY(launch_ok(c));
+      {
+        SWW_PROF(c, "bk.prod_diff");
+        prod_diff_kernel<<<SMS * 8, 256, 0, c->stream>>>(c->g.N, XA + o1, XA + o2, XB + o1, XB + o2, b.tmp);
+        SWW_TRY(launch_ok(c));
+      }
       if (c->fft_backend == 1) {
         F3Args A = {};
         A.dst = b.X;

@@ -164,6 +164,7 @@ static size_t g_partial_bytes = 0;
 static int gram_run(sww_ctx* c, const double* A, const double* B, int m, int n, long long K, int accumulate, double* C,
                     int ldc, int col0) {
   SWW_REQUIRE(m > 0 && n > 0 && K > 0, "gram: empty operand");
+  SWW_PROF(c, "gram.dmma f64");
   int mtiles = (m + TM - 1) / TM, ntiles = (n + TN - 1) / TN;
   int Mpad = mtiles * TM, Npad = ntiles * TN;
   long long total_chunks = (K + KC - 1) / KC;
