@@ -1,5 +1,6 @@
 // Context life-cycle, workspace layout and the small C-ABI entry points of libsww.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cmath>
@@ -40,6 +41,10 @@ extern "C" int sww_ctx_create(const sww_geometry* geo, sww_ctx** out) {
   SWW_CUDA(cudaSetDevice(geo->device));
   sww_ctx* c = new sww_ctx();
   c->device = geo->device;
+  {
+    const char* e = getenv("SWW_TIGHT_WS");
+    c->tight_ws = e && e[0] == '1';
+  }
   Geo& g = c->g;
   g.nx = geo->grid[0];
   g.ny = geo->grid[1];
@@ -142,6 +147,7 @@ extern "C" int sww_launch_counts(sww_ctx* c, uint64_t* own, uint64_t* fft) {
 extern "C" int sww_set_fft_backend(sww_ctx* c, int backend) {
   SWW_REQUIRE(c, "null context");
   SWW_REQUIRE(backend == 0 || backend == 1, "unknown FFT backend %d", backend);
+  SWW_REQUIRE(!(c->tight_ws && c->ar.base && backend != c->fft_backend), "SWW_TIGHT_WS=1: the FFT backend is fixed once the workspace is bound");
   if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes (nx,ny in [64,1024], nz in [128,2048])");
   c->fft_backend = backend;
   return 0;

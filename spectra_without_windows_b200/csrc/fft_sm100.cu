@@ -705,7 +705,7 @@ __device__ __forceinline__ void w_mid_stages(double2* buf, const double2* tw, in
 }
 
 template <int H, bool INV, bool FWD, bool YLM>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (H >= 512 ? 1 : 2))
 pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = 8;
@@ -725,9 +725,10 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
   for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * WARPS) {
     const long long row0 = grp * RW;
     double2 u[IPS][SE];
-    double2 wv[IPS][SE];
+    constexpr bool EARLY_W = (IPS == 1);   // 16 values per lane (H = 512) leave no registers for an early prefetch
+    double2 wv[EARLY_W ? IPS : 1][SE];
     // weights of the real-space step: issued first, consumed after the inverse transform
-    if (A.wmap) {
+    if (EARLY_W && A.wmap) {
 #pragma unroll
       for (int s = 0; s < IPS; ++s) {
         const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
@@ -815,12 +816,18 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 #pragma unroll
     for (int s = 0; s < IPS; ++s) {
       const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+      const int ws = EARLY_W ? s : 0;
+      if (!EARLY_W && A.wmap) {
+#pragma unroll
+        for (int r = 0; r < SE; ++r)
+          wv[0][r] = *reinterpret_cast<const double2*>(A.wmap + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
+      }
 #pragma unroll
       for (int r = 0; r < SE; ++r) {
         double f0 = A.scale, f1 = A.scale;
         if (A.wmap) {
-          f0 *= wv[s][r].x;
-          f1 *= wv[s][r].y;
+          f0 *= wv[ws][r].x;
+          f1 *= wv[ws][r].y;
         }
         if (YLM) {
           const long long row = row0 + rho;
@@ -843,15 +850,13 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
           const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
 #pragma unroll
           for (int r = 0; r < SE; ++r)
-            wv[s][r] = *reinterpret_cast<const double2*>(A.real_out + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
-        }
-#pragma unroll
-        for (int s = 0; s < IPS; ++s)
+            wv[0][r] = *reinterpret_cast<const double2*>(A.real_out + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
 #pragma unroll
           for (int r = 0; r < SE; ++r) {
-            u[s][r].x += wv[s][r].x;
-            u[s][r].y += wv[s][r].y;
+            u[s][r].x += wv[0][r].x;
+            u[s][r].y += wv[0][r].y;
           }
+        }
       }
 #pragma unroll
       for (int s = 0; s < IPS; ++s) {

@@ -56,8 +56,10 @@ static void pk_fisher_layout(sww_ctx* c, Arena& ar, PkFisherBufs& b) {
   ar.reset(c->persist_bytes);
   for (int l = 0; l < c->n_l; ++l) b.FC[l] = ar.alloc<double2>(Nc);
   for (int l = 0; l < c->n_l; ++l) b.G[l] = ar.alloc<double2>(Nc);
-  b.X = ar.alloc<double2>(Nc);
-  b.tmp = ar.alloc<double>(N);
+  // the fused sm_100a chains never materialise the shell-filtered spectrum or the real-space map
+  const bool fused_only = c->fft_backend == 1 && c->tight_ws;
+  b.X = fused_only ? nullptr : ar.alloc<double2>(Nc);
+  b.tmp = fused_only ? nullptr : ar.alloc<double>(N);
   b.nCa = ar.alloc<double>(N);
   b.nAa = ar.alloc<double>(N);
   b.WS = ar.alloc<double>(N);

@@ -108,6 +108,7 @@ struct sww_ctx {
   cufftHandle plan_d2z = 0, plan_z2d = 0, plan_z2z = 0;
   bool have_z2z = false;
   int fft_backend = 0;
+  bool tight_ws = false;   // SWW_TIGHT_WS=1: size the workspace for the selected FFT backend only
   // bk
   std::vector<int> tris;
   int* d_tris = nullptr;

@@ -126,6 +126,15 @@ class Context:
         self._tris = None
         if any(p.startswith("bk") for p in pipelines):
             self.set_triangles(mesh.triangles())
+        # FFT backend: the hand-written sm_100a passes wherever the mesh allows (power-of-two sizes),
+        # cuFFT plans otherwise.  SWW_FFT=0/1 forces one.  Chosen before the workspace is sized.
+        want = os.environ.get("SWW_FFT", "auto")
+        self.fft_backend = 0
+        if want != "0":
+            if self.lib.sww_set_fft_backend(self._h, 1) == 0:
+                self.fft_backend = 1
+            elif want == "1":
+                _lib.check(-1)
         need = 0
         for p in pipelines:
             b = _lib.u64(0)
@@ -135,15 +144,6 @@ class Context:
         self.use_stream(t.cuda.current_stream(self.device))
         _lib.check(self.lib.sww_bind_workspace(self._h, self.workspace.data_ptr(), int(need)))
         self._fields = None
-        # FFT backend: the hand-written sm_100a passes wherever the mesh allows (power-of-two sizes),
-        # cuFFT plans otherwise.  SWW_FFT=0/1 forces one.
-        want = os.environ.get("SWW_FFT", "auto")
-        self.fft_backend = 0
-        if want != "0":
-            if self.lib.sww_set_fft_backend(self._h, 1) == 0:
-                self.fft_backend = 1
-            elif want == "1":
-                _lib.check(-1)
 
     # -- plumbing
     def use_stream(self, stream):
