@@ -670,6 +670,57 @@ struct WGeo {
   static constexpr int ELEMS = RW * H / 32;         // complex values per lane (8, or 16 for H = 512)
 };
 
+// Per-stage twiddle tables: tab[rl*P + k] = W_H^(k * 2^rl * H/(P R)), rl = 0,1,2 (w^1, w^2, w^4), k < P.
+// Consecutive lanes read consecutive k: conflict-free (the single W_H table would be read with
+// strides 1, 2, 4 ... times H/(P R): up to 4-way conflicts, 24 % of all shared wavefronts under ncu).
+template <int H, bool REV, int S>
+struct WTabOff {   // offset of stage S's table (stage 0 has none)
+  static constexpr int value = WTabOff<H, REV, S - 1>::value + (S - 1 >= 1 ? 3 * WProd<H, REV, S - 1>::value : 0);
+};
+template <int H, bool REV>
+struct WTabOff<H, REV, 0> {
+  static constexpr int value = 0;
+};
+template <int H, bool REV>
+struct WTabSize {
+  static constexpr int value = WTabOff<H, REV, WPlan<H>::NS>::value;
+};
+
+template <int H, bool REV, int S>
+__device__ __forceinline__ void w_fill_tab(double2* tabs, const double2* __restrict__ twh_g, int tid, int nthreads) {
+  if constexpr (S < WPlan<H>::NS) {
+    if constexpr (S >= 1) {
+      constexpr int R = WRadix<H, REV, S>::value;
+      constexpr int P = WProd<H, REV, S>::value;
+      double2* tab = tabs + WTabOff<H, REV, S>::value;
+      for (int e = tid; e < 3 * P; e += nthreads) {
+        const int rl = e / P, k = e - rl * P, r = 1 << rl;
+        tab[e] = (r < R) ? twh_g[k * r * (H / (P * R))] : make_double2(1.0, 0.0);
+      }
+    }
+    w_fill_tab<H, REV, S + 1>(tabs, twh_g, tid, nthreads);
+  }
+}
+
+template <int R, int DIR>
+__device__ __forceinline__ void w_twiddle(const double2* tab, int P, int k, double2* u) {
+  double2 w[R];
+#pragma unroll
+  for (int r = 1, rl = 0; r < R; r <<= 1, ++rl) {
+    w[r] = tab[rl * P + k];
+    if (DIR < 0) w[r].y = -w[r].y;
+  }
+#pragma unroll
+  for (int r = 3; r < R; ++r) {
+    if ((r & (r - 1)) != 0) {
+      int hb = r >= 4 ? 4 : 2;
+      w[r] = c_mul(w[hb], w[r - hb]);
+    }
+  }
+#pragma unroll
+  for (int r = 1; r < R; ++r) u[r] = c_mul(u[r], w[r]);
+}
+
 // middle stage S (load, twiddle, butterfly, store) entirely inside the warp
 template <int H, int DIR, bool REV, int S>
 __device__ __forceinline__ void w_mid_stage(double2* buf, const double2* tw, int lane) {
@@ -684,7 +735,7 @@ __device__ __forceinline__ void w_mid_stage(double2* buf, const double2* tw, int
     const double2* row = buf + rho * WGeo<H>::ROWLEN;
 #pragma unroll
     for (int r = 0; r < R; ++r) u[s][r] = row[zpad(bi + r * BPR)];
-    stage_twiddle<R, DIR>(H, P, bi & (P - 1), tw, u[s]);
+    w_twiddle<R, DIR>(tw + WTabOff<H, REV, S>::value, P, bi & (P - 1), u[s]);
     dftR<R, DIR>(u[s]);
   }
   __syncwarp();
@@ -713,13 +764,16 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
   constexpr int SE = 8;                       // seam radix
   constexpr int BPS = H / SE;                 // butterflies per row at the seam; outputs at bi + r*BPS
   constexpr int IPS = RW * BPS / 32;          // seam butterflies per lane
-  double2* twh = reinterpret_cast<double2*>(smem_raw);   // [H]
-  double2* twn = twh + H;                                // [H+1]
-  double2* bufs = twn + (H + 8);                         // [WARPS][RW*ROWLEN (+8)]
+  constexpr int TI = WTabSize<H, false>::value, TF = WTabSize<H, true>::value;
+  double2* twn = reinterpret_cast<double2*>(smem_raw);   // [H+1]  exp(-2 pi i j / nz)
+  double2* tabi = twn + (H + 8);                         // per-stage twiddles of the inverse plan
+  double2* tabf = tabi + TI;                             // ... of the (reversed) forward plan
+  double2* bufs = tabf + TF;                             // [WARPS][RW*ROWLEN (+8)]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double2* buf = bufs + warp * (RW * ROWLEN + 8);
-  for (int i = tid; i < H; i += 256) twh[i] = twh_g[i];
   for (int i = tid; i <= H; i += 256) twn[i] = twn_g[i];
+  w_fill_tab<H, false, 0>(tabi, twh_g, tid, 256);
+  w_fill_tab<H, true, 0>(tabf, twh_g, tid, 256);
   __syncthreads();
   const long long ngroups = (long long)g.nx * g.ny / RW;
   for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * WARPS) {
@@ -792,7 +846,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         }
         __syncwarp();
       }
-      w_mid_stages<H, -1, false>(buf, twh, lane);
+      w_mid_stages<H, -1, false>(buf, tabi, lane);
       // last inverse stage (radix 8) -> registers, outputs at m = bi + r*BPS
 #pragma unroll
       for (int s = 0; s < IPS; ++s) {
@@ -800,7 +854,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         const double2* row = buf + rho * ROWLEN;
 #pragma unroll
         for (int r = 0; r < SE; ++r) u[s][r] = row[zpad(bi + r * BPS)];
-        stage_twiddle<SE, -1>(H, BPS, bi, twh, u[s]);
+        w_twiddle<SE, -1>(tabi + WTabOff<H, false, WPlan<H>::NS - 1>::value, BPS, bi, u[s]);
         dftR<SE, -1>(u[s]);
       }
     } else {
@@ -878,7 +932,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         for (int r = 0; r < SE; ++r) row[zpad(bi * SE + r)] = u[s][r];
       }
       __syncwarp();
-      w_mid_stages<H, 1, true>(buf, twh, lane);
+      w_mid_stages<H, 1, true>(buf, tabf, lane);
       // last forward stage -> natural order in the buffer
       {
         constexpr int R = WRadix<H, true, WPlan<H>::NS - 1>::value;
@@ -891,7 +945,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
           const double2* row = buf + rho * ROWLEN;
 #pragma unroll
           for (int r = 0; r < R; ++r) v[s][r] = row[zpad(bi + r * BPR)];
-          stage_twiddle<R, 1>(H, BPR, bi, twh, v[s]);
+          w_twiddle<R, 1>(tabf + WTabOff<H, true, WPlan<H>::NS - 1>::value, BPR, bi, v[s]);
           dftR<R, 1>(v[s]);
         }
         __syncwarp();
@@ -1122,7 +1176,8 @@ static int run_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bx, BoxAxis by, i
 template <int H, bool INV, bool FWD, bool YLM>
 static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
   constexpr int WARPS = 8;
-  size_t smem = (size_t)(H + H + 8) * 16 + (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16;
+  size_t smem = (size_t)(H + 8 + WTabSize<H, false>::value + WTabSize<H, true>::value) * 16 +
+                (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16;
   long long ngroups = (long long)c->g.nx * c->g.ny / WGeo<H>::RW;
   long long ctas = (ngroups + WARPS - 1) / WARPS;
   int grid = (int)(ctas < SMS * 2 ? ctas : SMS * 2);
