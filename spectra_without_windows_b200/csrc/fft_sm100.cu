@@ -144,12 +144,23 @@ struct BoxAxis {
 };
 
 // ------------------------------------------------------------------------------------------
-// I1: x-axis inverse.  Source: spectrum [nx][ny][nzh] restricted to the box; optional shell filter.
-// item = (jy, z-tile); output P[ix][jy][iz]  (pitch Kzp).  Rows outside the box are never read.
+// Column passes are generic in the axis they transform: AX = 0 (x) or 1 (y).  `a` runs along the
+// transformed axis, `o` along the other one; row(a, o) = ix*ny + iy.  The pass order is chosen on the
+// host so that the more strongly pruned axis is transformed first on the way forward and last on the
+// way back, which minimises the compact intermediates:
+//     inverse:  first pass (gather)  spectrum -> P[Ko][nA][Kzp],   second pass  P -> Q[nx][ny][Kzp]
+//     forward:  first pass           R -> P[K_B][nC][Kzp],          last pass    P -> epilogue
 // ------------------------------------------------------------------------------------------
-template <int N>
+template <int AX>
+__device__ __forceinline__ long long row_of(int a, int o, int ny) {
+  return AX == 0 ? (long long)a * ny + o : (long long)o * ny + a;
+}
+
+// First inverse pass.  Source: spectrum [nx][ny][nzh] restricted to the box; optional shell filter.
+// item = (jo, z-tile).  Rows outside the box are never read.
+template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
-pass_i1_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __restrict__ src, int shell,
+pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ src, int shell,
                const double2* __restrict__ twg, double2* __restrict__ P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
@@ -159,16 +170,16 @@ pass_i1_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
   constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
-  const long long items = (long long)by.K * ztiles;
+  const long long items = (long long)bO.K * ztiles;
   for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int jy = (int)(it / ztiles), zt = (int)(it - (long long)jy * ztiles);
-    const int iy = by.idx(jy), iz0 = zt * FFT_TZ;
+    const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
+    const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
     __syncthreads();
-    fft_first<N, -1, false>(tile, tid, [&](int ix, int cc) {
+    fft_first<N, -1, false>(tile, tid, [&](int ia, int cc) {
       double2 v = make_double2(0.0, 0.0);
       const int iz = iz0 + cc;
-      if (bx.has(ix) && iz < Kz) {
-        long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
+      if (bA.has(ia) && iz < Kz) {
+        long long cell = row_of<AX>(ia, io, g.ny) * g.nzh + iz;
         if (shell < 0 || g.binmap[cell] == shell) v = src[cell];
       }
       return v;
@@ -181,19 +192,17 @@ pass_i1_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
       int w = tid + s * NT, bi = w >> 3, cc = w & 7;
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
-        int ix = bi + r * (N / RL);
-        P[((long long)ix * by.K + jy) * Kzp + iz0 + cc] = u[s][r];
+        int ia = bi + r * (N / RL);
+        P[((long long)jo * N + ia) * Kzp + iz0 + cc] = u[s][r];
       }
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// I2: y-axis inverse.  P[ix][jy][iz] -> Q[ix][iy][iz]; item = (ix, z-tile)
-// ------------------------------------------------------------------------------------------
-template <int N>
+// Second inverse pass (axis AX, box bA): P[ja][f][iz] -> Q[row][iz]; item = (f, z-tile), f < nF
+template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
-pass_i2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ P, const double2* __restrict__ twg,
+pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ P, const double2* __restrict__ twg,
                double2* __restrict__ Q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
@@ -203,14 +212,14 @@ pass_i2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ P, const
   constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
-  const long long items = (long long)nx * ztiles;
+  const long long items = (long long)nF * ztiles;
   for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int ix = (int)(it / ztiles), zt = (int)(it - (long long)ix * ztiles);
+    const int f = (int)(it / ztiles), zt = (int)(it - (long long)f * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    fft_first<N, -1, false>(tile, tid, [&](int iy, int cc) {
+    fft_first<N, -1, false>(tile, tid, [&](int ia, int cc) {
       double2 v = make_double2(0.0, 0.0);
-      if (by.has(iy)) v = P[((long long)ix * by.K + by.pos(iy)) * Kzp + iz0 + cc];
+      if (bA.has(ia)) v = P[((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc];
       return v;
     });
     FFT_MID(N, -1, false, tile, tw, tid);
@@ -221,19 +230,17 @@ pass_i2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ P, const
       int w = tid + s * NT, bi = w >> 3, cc = w & 7;
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
-        int iy = bi + r * (N / RL);
-        Q[((long long)ix * N + iy) * Kzp + iz0 + cc] = u[s][r];
+        int ia = bi + r * (N / RL);
+        Q[row_of<AX>(ia, f, ny) * Kzp + iz0 + cc] = u[s][r];
       }
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// F2: y-axis forward.  R[ix][iy][iz] -> P[ix][jy][iz] (box rows only); item = (ix, z-tile)
-// ------------------------------------------------------------------------------------------
-template <int N>
+// First forward column pass (axis AX, box bA): R[row][iz] -> P[ja][c][iz] (box rows only); item = (c, z-tile), c < nC
+template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
-pass_f2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ R, const double2* __restrict__ twg,
+pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ R, const double2* __restrict__ twg,
                double2* __restrict__ P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
@@ -243,12 +250,12 @@ pass_f2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ R, const
   constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
-  const long long items = (long long)nx * ztiles;
+  const long long items = (long long)nC * ztiles;
   for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int ix = (int)(it / ztiles), zt = (int)(it - (long long)ix * ztiles);
+    const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    fft_first<N, 1, false>(tile, tid, [&](int iy, int cc) { return R[((long long)ix * N + iy) * Kzp + iz0 + cc]; });
+    fft_first<N, 1, false>(tile, tid, [&](int ia, int cc) { return R[row_of<AX>(ia, ic, ny) * Kzp + iz0 + cc]; });
     FFT_MID(N, 1, false, tile, tw, tid);
     double2 u[16 / RL][RL];
     fft_last<N, 1, false, RL>(tile, tw, tid, u);
@@ -257,8 +264,8 @@ pass_f2_kernel(int nx, BoxAxis by, int Kzp, const double2* __restrict__ R, const
       int w = tid + s * NT, bi = w >> 3, cc = w & 7;
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
-        int iy = bi + r * (N / RL);
-        if (by.has(iy)) P[((long long)ix * by.K + by.pos(iy)) * Kzp + iz0 + cc] = u[s][r];
+        int ia = bi + r * (N / RL);
+        if (bA.has(ia)) P[((long long)bA.pos(ia) * nC + ic) * Kzp + iz0 + cc] = u[s][r];
       }
     }
   }
@@ -276,9 +283,9 @@ __device__ __forceinline__ double warp_sum_f(double v) {
   return v;
 }
 
-template <int N, int MODE>
+template <int N, int AX, int MODE>
 __global__ void __launch_bounds__(N / 2, (N >= 512 ? (N >= 1024 ? 1 : 2) : 3))
-pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __restrict__ P,
+pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ P,
                const double2* __restrict__ twg, F3Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
@@ -295,14 +302,14 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
   if (MODE == 2)
     for (int i = tid; i < NW * nb; i += NT) hist[i] = 0.0;
   const int ztiles = Kzp / FFT_TZ;
-  const long long items = (long long)by.K * ztiles;
+  const long long items = (long long)bO.K * ztiles;
   const bool nz_even = (g.nz % 2) == 0;
   for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int jy = (int)(it / ztiles), zt = (int)(it - (long long)jy * ztiles);
-    const int iy = by.idx(jy), iz0 = zt * FFT_TZ;
+    const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
+    const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
     __syncthreads();
     fft_first<N, 1, false>(tile, tid,
-                           [&](int ix, int cc) { return P[((long long)ix * by.K + jy) * Kzp + iz0 + cc]; });
+                           [&](int ia, int cc) { return P[((long long)jo * N + ia) * Kzp + iz0 + cc]; });
     FFT_MID(N, 1, false, tile, tw, tid);
     double2 u[16 / RL][RL];
     fft_last<N, 1, false, RL>(tile, tw, tid, u);
@@ -313,8 +320,9 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
         const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7, iz = iz0 + cc;
 #pragma unroll
         for (int r = 0; r < RL; ++r) {
-          const int ix = bi + r * (N / RL);
-          const bool inb = bx.has(ix) && iz < Kz;
+          const int ia = bi + r * (N / RL);
+          const bool inb = bA.has(ia) && iz < Kz;
+          const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
           const long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
           const double2 t = u[s][r];
           if (MODE == 0) {
@@ -353,7 +361,7 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
       }
       __syncthreads();
       constexpr int GRP = 4;
-      const int total = bx.K * FFT_TZ;
+      const int total = bA.K * FFT_TZ;
       for (int e0 = 0; e0 < total; e0 += GRP * NT) {   // uniform trip count (warp collectives below)
         int bq[GRP];
         long long cellq[GRP];
@@ -361,10 +369,10 @@ pass_f3_kernel(Geo g, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* __
 #pragma unroll
         for (int j = 0; j < GRP; ++j) {
           const int e = e0 + j * NT + tid;
-          const int jx = e >> 3, cc = e & 7, iz = iz0 + cc;
+          const int ja = e >> 3, cc = e & 7, iz = iz0 + cc;
           const bool inb = (e < total) && iz < Kz;
-          ixq[j] = inb ? bx.idx(jx) : 0;
-          cellq[j] = ((long long)ixq[j] * g.ny + iy) * g.nzh + iz;
+          ixq[j] = inb ? bA.idx(ja) : 0;
+          cellq[j] = row_of<AX>(ixq[j], io, g.ny) * g.nzh + iz;
           bq[j] = inb ? (int)g.binmap[cellq[j]] : SWW_NO_BIN;
         }
         double2 Gq[GRP][3];
@@ -1095,81 +1103,132 @@ static int occ_for(size_t smem) {
   return o;
 }
 
-static int run_i1(sww_ctx* c, Sm100State* s, BoxAxis bx, BoxAxis by, int Kz, int Kzp, const double2* src, int shell) {
-  SWW_PROF(c, "fft.I1 x-inverse");
-  const int N = c->g.nx;
-  size_t smem = col_smem(N, 0);
-  long long items = (long long)by.K * (Kzp / FFT_TZ);
-  int grid = grid_for_items(items, occ_for(smem));
-#define M(NN)                                                                                             \
-  SWW_TRY(set_smem(pass_i1_kernel<NN>, smem));                                                            \
-  pass_i1_kernel<NN><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, src, shell, s->tw_x, s->P);
-  DISPATCH_N(N, M)
-#undef M
-  c->n_own++;
-  SWW_CUDA(cudaGetLastError());
-  return 0;
+// ---- column-pass launchers, generic in the transformed axis -------------------------------------
+struct AxisPlan {
+  BoxAxis bx, by;   // kept indices along x and y
+  bool x_first_fwd; // forward: transform x before y (x is the more strongly pruned axis)
+};
+
+static AxisPlan make_plan(const Geo& g, BoxAxis bx, BoxAxis by) {
+  AxisPlan p;
+  p.bx = bx;
+  p.by = by;
+  p.x_first_fwd = (long long)bx.K * g.ny <= (long long)by.K * g.nx;
+  return p;
 }
 
-static int run_i2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
-  SWW_PROF(c, "fft.I2 y-inverse");
-  const int N = c->g.ny;
+static const double2* tw_of(Sm100State* s, int ax) { return ax == 0 ? s->tw_x : s->tw_y; }
+
+template <int N, int AX>
+static int launch_i1(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* src, int shell) {
   size_t smem = col_smem(N, 0);
-  long long items = (long long)c->g.nx * (Kzp / FFT_TZ);
+  long long items = (long long)bO.K * (Kzp / FFT_TZ);
   int grid = grid_for_items(items, occ_for(smem));
-#define M(NN)                                                 \
-  SWW_TRY(set_smem(pass_i2_kernel<NN>, smem));                \
-  pass_i2_kernel<NN><<<grid, NN / 2, smem, c->stream>>>(c->g.nx, by, Kzp, s->P, s->tw_y, s->Q);
-  DISPATCH_N(N, M)
-#undef M
-  c->n_own++;
-  SWW_CUDA(cudaGetLastError());
+  SWW_TRY(set_smem(pass_i1_kernel<N, AX>, smem));
+  pass_i1_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P);
   return 0;
 }
-
-static int run_f2(sww_ctx* c, Sm100State* s, BoxAxis by, int Kzp) {
-  SWW_PROF(c, "fft.F2 y-forward");
-  const int N = c->g.ny;
+template <int N, int AX>
+static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp) {
   size_t smem = col_smem(N, 0);
-  long long items = (long long)c->g.nx * (Kzp / FFT_TZ);
+  long long items = (long long)nF * (Kzp / FFT_TZ);
   int grid = grid_for_items(items, occ_for(smem));
-#define M(NN)                                                 \
-  SWW_TRY(set_smem(pass_f2_kernel<NN>, smem));                \
-  pass_f2_kernel<NN><<<grid, NN / 2, smem, c->stream>>>(c->g.nx, by, Kzp, s->R, s->tw_y, s->P);
-  DISPATCH_N(N, M)
-#undef M
-  c->n_own++;
-  SWW_CUDA(cudaGetLastError());
+  SWW_TRY(set_smem(pass_i2_kernel<N, AX>, smem));
+  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), s->Q);
   return 0;
 }
-
-static int run_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bx, BoxAxis by, int Kz, int Kzp, F3Args A) {
-  SWW_PROF(c, mode == 2 ? "fft.F3 x-forward+bin" : (mode == 1 ? "fft.F3 x-forward+ylm" : "fft.F3 x-forward+store"));
-  const int N = c->g.nx;
+template <int N, int AX>
+static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp) {
+  size_t smem = col_smem(N, 0);
+  long long items = (long long)nC * (Kzp / FFT_TZ);
+  int grid = grid_for_items(items, occ_for(smem));
+  SWW_TRY(set_smem(pass_f2_kernel<N, AX>, smem));
+  pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P);
+  return 0;
+}
+template <int N, int AX>
+static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, F3Args A) {
   int hist = (mode == 2) ? (N / 2 / 32) * A.n_g * c->g.n_k : 0;
   size_t smem = col_smem(N, hist);
-  long long items = (long long)by.K * (Kzp / FFT_TZ);
+  long long items = (long long)bO.K * (Kzp / FFT_TZ);
   int grid = grid_for_items(items, occ_for(smem));
   if (mode == 2) {
     SWW_REQUIRE((size_t)grid * A.n_g * c->g.n_k <= c->partial_elems, "F3 bin: partial buffer too small");
     A.partial = c->d_partial;
     A.counter = c->d_counter;
   }
-#define M(NN)                                                                                                    \
-  if (mode == 0) {                                                                                               \
-    SWW_TRY(set_smem(pass_f3_kernel<NN, 0>, smem));                                                              \
-    pass_f3_kernel<NN, 0><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, s->P, s->tw_x, A);           \
-  } else if (mode == 1) {                                                                                        \
-    SWW_TRY(set_smem(pass_f3_kernel<NN, 1>, smem));                                                              \
-    pass_f3_kernel<NN, 1><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, s->P, s->tw_x, A);           \
-  } else {                                                                                                       \
-    SWW_TRY(set_smem(pass_f3_kernel<NN, 2>, smem));                                                              \
-    pass_f3_kernel<NN, 2><<<grid, NN / 2, smem, c->stream>>>(c->g, bx, by, Kz, Kzp, s->P, s->tw_x, A);           \
+  if (mode == 0) {
+    SWW_TRY(set_smem(pass_f3_kernel<N, AX, 0>, smem));
+    pass_f3_kernel<N, AX, 0><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, s->P, tw_of(s, AX), A);
+  } else if (mode == 1) {
+    SWW_TRY(set_smem(pass_f3_kernel<N, AX, 1>, smem));
+    pass_f3_kernel<N, AX, 1><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, s->P, tw_of(s, AX), A);
+  } else {
+    SWW_TRY(set_smem(pass_f3_kernel<N, AX, 2>, smem));
+    pass_f3_kernel<N, AX, 2><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, s->P, tw_of(s, AX), A);
   }
-  DISPATCH_N(N, M)
-#undef M
-  c->n_own++;
-  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define DISPATCH_AX(n, ax, CALL)                                                   \
+  switch (n) {                                                                     \
+    case 64: if (ax == 0) { SWW_TRY((CALL(64, 0))); } else { SWW_TRY((CALL(64, 1))); } break;       \
+    case 128: if (ax == 0) { SWW_TRY((CALL(128, 0))); } else { SWW_TRY((CALL(128, 1))); } break;    \
+    case 256: if (ax == 0) { SWW_TRY((CALL(256, 0))); } else { SWW_TRY((CALL(256, 1))); } break;    \
+    case 512: if (ax == 0) { SWW_TRY((CALL(512, 0))); } else { SWW_TRY((CALL(512, 1))); } break;    \
+    case 1024: if (ax == 0) { SWW_TRY((CALL(1024, 0))); } else { SWW_TRY((CALL(1024, 1))); } break; \
+    default: SWW_REQUIRE(false, "unsupported FFT length %d", n);                   \
+  }
+
+static int axis_len(const Geo& g, int ax) { return ax == 0 ? g.nx : g.ny; }
+
+// inverse column passes: spectrum (box, optional shell filter) -> Q[nx][ny][Kzp]
+static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, const double2* src, int shell) {
+  const int a1 = pl.x_first_fwd ? 1 : 0;   // first inverse axis = the weakly pruned one
+  const int a2 = 1 - a1;
+  const BoxAxis b1 = a1 == 0 ? pl.bx : pl.by, b2 = a2 == 0 ? pl.bx : pl.by;
+  const int n1 = axis_len(c->g, a1), n2 = axis_len(c->g, a2);
+  {
+    SWW_PROF(c, a1 == 0 ? "fft.I1 x-inverse (gather)" : "fft.I1 y-inverse (gather)");
+#define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell)
+    DISPATCH_AX(n1, a1, CALL)
+#undef CALL
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+  }
+  {
+    SWW_PROF(c, a2 == 0 ? "fft.I2 x-inverse" : "fft.I2 y-inverse");
+#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp)
+    DISPATCH_AX(n2, a2, CALL)
+#undef CALL
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// forward column passes: R[nx][ny][Kzp] -> epilogue `mode`
+static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, int mode, F3Args A) {
+  const int a1 = pl.x_first_fwd ? 0 : 1;   // first forward axis = the strongly pruned one
+  const int a2 = 1 - a1;
+  const BoxAxis b1 = a1 == 0 ? pl.bx : pl.by, b2 = a2 == 0 ? pl.bx : pl.by;
+  const int n1 = axis_len(c->g, a1), n2 = axis_len(c->g, a2);
+  {
+    SWW_PROF(c, a1 == 0 ? "fft.F2 x-forward" : "fft.F2 y-forward");
+#define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp)
+    DISPATCH_AX(n1, a1, CALL)
+#undef CALL
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+  }
+  {
+    SWW_PROF(c, mode == 2 ? "fft.F3 last-forward+bin" : (mode == 1 ? "fft.F3 last-forward+ylm" : "fft.F3 last-forward+store"));
+#define CALL(NN, AA) launch_f3<NN, AA>(c, s, mode, b2, b1, Kz, Kzp, A)
+    DISPATCH_AX(n2, a2, CALL)
+#undef CALL
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -1234,7 +1293,7 @@ int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out) {
   Sm100State* s;
   SWW_TRY(get_state(c, &s));
   const Geo& g = c->g;
-  BoxAxis bx = full_axis(g.nx), by = full_axis(g.ny);
+  AxisPlan pl = make_plan(g, full_axis(g.nx), full_axis(g.ny));
   int Kz = g.nzh, Kzp = up8(Kz);
   ZArgs Z = {};
   Z.R = s->R;
@@ -1244,20 +1303,18 @@ int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out) {
   Z.scale = 1.0;
   Z.lm = -1;
   SWW_TRY(run_z(c, s, false, true, Z));
-  SWW_TRY(run_f2(c, s, by, Kzp));
   F3Args A = {};
   A.dst = out;
-  return run_f3(c, s, 0, bx, by, Kz, Kzp, A);
+  return run_forward_cols(c, s, pl, Kz, Kzp, 0, A);
 }
 
 int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out) {
   Sm100State* s;
   SWW_TRY(get_state(c, &s));
   const Geo& g = c->g;
-  BoxAxis bx = full_axis(g.nx), by = full_axis(g.ny);
+  AxisPlan pl = make_plan(g, full_axis(g.nx), full_axis(g.ny));
   int Kz = g.nzh, Kzp = up8(Kz);
-  SWW_TRY(run_i1(c, s, bx, by, Kz, Kzp, in, -1));
-  SWW_TRY(run_i2(c, s, by, Kzp));
+  SWW_TRY(run_inverse_cols(c, s, pl, Kz, Kzp, in, -1));
   ZArgs Z = {};
   Z.Q = s->Q;
   Z.Kz_in = Kz;
@@ -1274,7 +1331,7 @@ int sww_sm100_forward_box(sww_ctx* c, const double* real_in, const double* wmap,
   Sm100State* s;
   SWW_TRY(get_state(c, &s));
   const Geo& g = c->g;
-  BoxAxis bx = box_axis(g.nx, g.bx), by = box_axis(g.ny, g.by);
+  AxisPlan pl = make_plan(g, box_axis(g.nx, g.bx), box_axis(g.ny, g.by));
   int Kz = g.Kz, Kzp = up8(Kz);
   ZArgs Z = {};
   Z.R = s->R;
@@ -1285,8 +1342,7 @@ int sww_sm100_forward_box(sww_ctx* c, const double* real_in, const double* wmap,
   Z.scale = 1.0;
   Z.lm = lm_r;
   SWW_TRY(run_z(c, s, false, true, Z));
-  SWW_TRY(run_f2(c, s, by, Kzp));
-  return run_f3(c, s, mode, bx, by, Kz, Kzp, A);
+  return run_forward_cols(c, s, pl, Kz, Kzp, mode, A);
 }
 
 // inverse transform of the box part of `src` (optionally only shell `shell`) into a real map:
@@ -1303,10 +1359,9 @@ int sww_sm100_inverse_box(sww_ctx* c, const double2* src, int shell, int box_she
     b_y = s->shell_by[box_shell];
     b_z = s->shell_bz[box_shell];
   }
-  BoxAxis bx = box_axis(g.nx, b_x), by = box_axis(g.ny, b_y);
+  AxisPlan pl = make_plan(g, box_axis(g.nx, b_x), box_axis(g.ny, b_y));
   int Kz = b_z + 1 < g.nzh ? b_z + 1 : g.nzh, Kzp = up8(Kz);
-  SWW_TRY(run_i1(c, s, bx, by, Kz, Kzp, src, shell));
-  SWW_TRY(run_i2(c, s, by, Kzp));
+  SWW_TRY(run_inverse_cols(c, s, pl, Kz, Kzp, src, shell));
   ZArgs Z = {};
   Z.Q = s->Q;
   Z.Kz_in = Kz;
@@ -1325,12 +1380,11 @@ int sww_sm100_pk_row(sww_ctx* c, const double2* F, int shell, const double* wmap
   Sm100State* s;
   SWW_TRY(get_state(c, &s));
   const Geo& g = c->g;
-  BoxAxis bxi = box_axis(g.nx, s->shell_bx[shell]), byi = box_axis(g.ny, s->shell_by[shell]);
+  AxisPlan pli = make_plan(g, box_axis(g.nx, s->shell_bx[shell]), box_axis(g.ny, s->shell_by[shell]));
   int Kzi = s->shell_bz[shell] + 1, Kzpi = up8(Kzi);
-  BoxAxis bxo = box_axis(g.nx, g.bx), byo = box_axis(g.ny, g.by);
+  AxisPlan plo = make_plan(g, box_axis(g.nx, g.bx), box_axis(g.ny, g.by));
   int Kzo = g.Kz, Kzpo = up8(Kzo);
-  SWW_TRY(run_i1(c, s, bxi, byi, Kzi, Kzpi, F, shell));
-  SWW_TRY(run_i2(c, s, byi, Kzpi));
+  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, F, shell));
   ZArgs Z = {};
   Z.Q = s->Q;
   Z.Kz_in = Kzi;
@@ -1342,11 +1396,10 @@ int sww_sm100_pk_row(sww_ctx* c, const double2* F, int shell, const double* wmap
   Z.scale = inv_scale;
   Z.lm = -1;
   SWW_TRY(run_z(c, s, true, true, Z));
-  SWW_TRY(run_f2(c, s, byo, Kzpo));
   F3Args A = {};
   for (int q = 0; q < n_g; ++q) A.G[q] = G[q];
   A.n_g = n_g;
   A.scale = scale;
   A.out_row = out_row;
-  return run_f3(c, s, 2, bxo, byo, Kzo, Kzpo, A);
+  return run_forward_cols(c, s, plo, Kzo, Kzpo, 2, A);
 }
