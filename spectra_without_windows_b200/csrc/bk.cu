@@ -24,6 +24,7 @@
 int k_prep_pk(sww_ctx* c, const double* a, double* nCa, double* nAa, double* WS);
 int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
                              double2* spec, double2* const* out);
+size_t sww_sm100_qstack_bytes(const sww_ctx* c, int nb);
 int sww_gram_upper(sww_ctx* c, const double* A, const double* B, int m, int n, long long K, int row_limit,
                    double* C, int ldc, int col0);
 
@@ -249,6 +250,7 @@ struct BkBufs {
   double *tmp, *nCa, *nAa, *WS, *Wt, *Wc, *u;
   double2 *PS, *PST;  // compact product spectra [slot][box]
   double *Dt, *CD;    // tilde maps [n_b][N], C maps block [blk][N]
+  double2* Qstack;    // backend 1: intermediate planes of a batched inverse (up to 2 lmax + 2)
   int blk;
 };
 
@@ -311,6 +313,7 @@ static void bk_fisher_layout(sww_ctx* c, Arena& ar, BkBufs& b, int n_slots) {
   b.blk = choose_block(c);
   b.Dt = ar.alloc<double>((size_t)nb * N);
   b.CD = ar.alloc<double>((size_t)b.blk * N);
+  b.Qstack = ar.alloc<double2>(sww_sm100_qstack_bytes(c, SWW_MAX_ZBATCH) / sizeof(double2));
 }
 
 static void bk_small_layout(sww_ctx* c, Arena& ar, BkBufs& b) {
@@ -328,6 +331,7 @@ static void bk_small_layout(sww_ctx* c, Arena& ar, BkBufs& b) {
   b.Dt = ar.alloc<double>((size_t)(c->g.n_k + 9) * N);
   b.PS = ar.alloc<double2>(box_elems(c));
   b.u = ar.alloc<double>(N);
+  b.Qstack = ar.alloc<double2>(sww_sm100_qstack_bytes(c, SWW_MAX_ZBATCH) / sizeof(double2));
 }
 
 size_t sww_bk_pipeline_bytes(sww_ctx* c, int what) {
@@ -443,6 +447,36 @@ static int build_phi(sww_ctx* c, BkBufs& b, const PairTable& P, const double2* s
   const size_t be = box_elems(c);
   const double invN = 1.0 / (double)c->g.N;
   auto spec = [&](int i, int j, int l) { return spectra + (size_t)P.get(i, j, l) * be; };
+  if (c->fft_backend == 1) {
+    // fused: the first inverse pass gathers straight from the compact product spectra (no assembled
+    // spectrum), and all (2l+1)+1 inverse transforms of the map are summed in the z pass (one write).
+    GatherArgs ga[SWW_MAX_ZBATCH] = {};
+    int lms[SWW_MAX_ZBATCH];
+    int nbat = 0;
+    if (l_i == 0) {
+      ga[0].p[0] = spec(a, bb, 0); ga[0].s[0] = cc;
+      ga[0].p[1] = spec(a, cc, 0); ga[0].s[1] = bb;
+      ga[0].p[2] = spec(bb, cc, 0); ga[0].s[2] = a;
+      ga[0].n_terms = 3; ga[0].lm = -1; ga[0].coef = 1.0;
+      lms[0] = -1;
+      nbat = 1;
+    } else {
+      ga[0].p[0] = spec(a, cc, l_i); ga[0].s[0] = bb;
+      ga[0].p[1] = spec(bb, cc, l_i); ga[0].s[1] = a;
+      ga[0].n_terms = 2; ga[0].lm = -1; ga[0].coef = 1.0;
+      lms[0] = -1;
+      nbat = 1;
+      int lm0 = 0;
+      for (int l = 0; l < l_i; ++l) lm0 += 4 * l + 1;
+      for (int m = 0; m < 4 * l_i + 1; ++m, ++nbat) {
+        ga[nbat].p[0] = spec(a, bb, 0); ga[nbat].s[0] = cc;
+        ga[nbat].n_terms = 1; ga[nbat].lm = lm0 + m; ga[nbat].coef = lcoef(l_i);
+        lms[nbat] = lm0 + m;
+      }
+    }
+    c->n_fft += nbat;
+    return sww_sm100_inverse_multi(c, nbat, ga, cc, lms, wmap, invN, 0, b.Qstack, out);
+  }
   if (l_i == 0) {
     SWW_TRY(assemble(c, b, spec(a, bb, 0), cc, spec(a, cc, 0), bb, spec(bb, cc, 0), a, -1, 1.0));
     return inverse_weighted(c, b, cc, wmap, -1, invN, 1, out);

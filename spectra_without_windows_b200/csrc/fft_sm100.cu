@@ -161,7 +161,7 @@ __device__ __forceinline__ long long row_of(int a, int o, int ny) {
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
 pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ src, int shell,
-               const double2* __restrict__ twg, double2* __restrict__ P) {
+               const double2* __restrict__ twg, double2* __restrict__ P, GatherArgs ga, BoxAxis cbx, BoxAxis cby) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -180,7 +180,33 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
       const int iz = iz0 + cc;
       if (bA.has(ia) && iz < Kz) {
         long long cell = row_of<AX>(ia, io, g.ny) * g.nzh + iz;
-        if (shell < 0 || g.binmap[cell] == shell) v = src[cell];
+        if (ga.n_terms == 0) {
+          if (shell < 0 || g.binmap[cell] == shell) v = src[cell];
+        } else {
+          const int b = g.binmap[cell];
+          const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
+          const long long ci = ((long long)cbx.pos(ix) * cby.K + cby.pos(iy)) * g.Kz + iz;
+          bool any = false;
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            if (t < ga.n_terms && b == ga.s[t]) {
+              double2 q = ga.p[t][ci];
+              v.x += q.x;
+              v.y += q.y;
+              any = true;
+            }
+          if (any) {
+            double f = ga.coef;
+            if (ga.lm >= 0) {
+              double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
+              double rr = sqrt(kx * kx + ky * ky + kz * kz);
+              double inv = 1.0 / (1e-12 + rr);
+              f *= sww_ylm_dyn(ga.lm, kx * inv, ky * inv, kz * inv);
+            }
+            v.x *= f;
+            v.y *= f;
+          }
+        }
       }
       return v;
     });
@@ -470,174 +496,11 @@ struct ZArgs {
   double scale;
   int lm;          // >= 0: multiply the real row by Y_lm(r^)
   int accumulate;  // INV only: real_out += ...
+  // INV only: nb > 1 sums nb inverse transforms (planes Q + b*q_stride), each times Y_{lms[b]}(r^) (or 1)
+  int nb;
+  int lms[SWW_MAX_ZBATCH];
+  long long q_stride;
 };
-
-template <int H, bool INV, bool FWD, bool YLM>
-__global__ void __launch_bounds__(H / 2)
-pass_z_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g, int SP) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* tile = reinterpret_cast<double2*>(smem_raw);   // [H][9]
-  double2* twh = tile + H * FFT_LDT;                      // [H]    exp(-2 pi i j / H)
-  double2* twn = twh + H;                                 // [H+1]  exp(-2 pi i j / nz)
-  double2* stage = twn + (H + 8);                         // [8][H+9]
-  const int tid = threadIdx.x;
-  constexpr int NT = H / 2;
-  // seam radix: last stage of the inverse plan == first stage of the (reversed) forward plan
-  constexpr int RS = FFT_LAST_RADIX(H, false);
-  constexpr int IPT = 16 / RS;
-  constexpr int PS = H / RS;
-  for (int i = tid; i < H; i += NT) twh[i] = twh_g[i];
-  for (int i = tid; i <= H; i += NT) twn[i] = twn_g[i];
-  const long long groups = (long long)g.nx * g.ny / FFT_TZ;
-  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const long long row0 = grp * FFT_TZ;  // rows row0 .. row0+7 share ix (ny is a multiple of 8)
-    const int ix = (int)(row0 / g.ny);
-    const int iyb = (int)(row0 - (long long)ix * g.ny);
-    double2 u[IPT][RS];
-    __syncthreads();
-    if (INV) {
-      // stage the complex input rows (coalesced; loads batched four deep ahead of the stores)
-      {
-        const int tot = FFT_TZ * A.Kz_in;
-        for (int e0 = tid; e0 < tot; e0 += 4 * NT) {
-          double2 v[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            int e = e0 + q * NT;
-            if (e < tot) {
-              int r = e / A.Kz_in, k = e - r * A.Kz_in;
-              v[q] = A.Q[(row0 + r) * A.Kzp_in + k];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            int e = e0 + q * NT;
-            if (e < tot) {
-              int r = e / A.Kz_in, k = e - r * A.Kz_in;
-              stage[r * SP + k] = v[q];
-            }
-          }
-        }
-      }
-      __syncthreads();
-      // Y[k] = (Z[k] + conj Z[H-k]) + i (Z[k] - conj Z[H-k]) e^{+2 pi i k / nz}, built on the fly
-      fft_first<H, -1, false>(tile, tid, [&](int k, int r) {
-        double2 zk = (k < A.Kz_in) ? stage[r * SP + k] : make_double2(0.0, 0.0);
-        int hk = H - k;
-        double2 zh = (hk < A.Kz_in) ? stage[r * SP + hk] : make_double2(0.0, 0.0);
-        if (k == 0) {  // self-conjugate modes: imaginary parts are ignored (as cuFFT / np.real do)
-          zk.y = 0.0;
-          zh.y = 0.0;
-        }
-        double2 a = make_double2(zk.x + zh.x, zk.y - zh.y);
-        double2 d = make_double2(zk.x - zh.x, zk.y + zh.y);
-        double2 w = twn[k];
-        w.y = -w.y;
-        double2 b = c_mul(d, w);
-        return make_double2(a.x - b.y, a.y + b.x);
-      });
-      FFT_MID(H, -1, false, tile, twh, tid);
-      fft_last<H, -1, false, RS>(tile, twh, tid, u);
-    }
-    // real-space step on registers: element (s, r) is the pair x[2m], x[2m+1], m = bi + r*PS, row c.
-    // All global loads of the step are issued before any use (one exposed latency, not sixteen).
-    {
-      double2 wv[IPT][RS];
-      if (A.wmap) {
-#pragma unroll
-        for (int s = 0; s < IPT; ++s) {
-          const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
-#pragma unroll
-          for (int r = 0; r < RS; ++r)
-            wv[s][r] = *reinterpret_cast<const double2*>(A.wmap + (row0 + c) * g.nz + 2 * (bi + r * PS));
-        }
-      }
-      if (!INV) {
-#pragma unroll
-        for (int s = 0; s < IPT; ++s) {
-          const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
-#pragma unroll
-          for (int r = 0; r < RS; ++r)
-            u[s][r] = *reinterpret_cast<const double2*>(A.real_in + (row0 + c) * g.nz + 2 * (bi + r * PS));
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < IPT; ++s) {
-        const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
-#pragma unroll
-        for (int r = 0; r < RS; ++r) {
-          const int m = bi + r * PS;
-          double f0 = A.scale, f1 = A.scale;
-          if (A.wmap) {
-            f0 *= wv[s][r].x;
-            f1 *= wv[s][r].y;
-          }
-          if (YLM) {
-            double X = g.rax[0][ix], Y = g.rax[1][iyb + c];
-            double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
-            double r0 = sqrt(X * X + Y * Y + Z0 * Z0), r1 = sqrt(X * X + Y * Y + Z1 * Z1);
-            double i0 = 1.0 / (1e-12 + r0), i1 = 1.0 / (1e-12 + r1);
-            f0 *= sww_ylm_dyn(A.lm, X * i0, Y * i0, Z0 * i0);
-            f1 *= sww_ylm_dyn(A.lm, X * i1, Y * i1, Z1 * i1);
-          }
-          u[s][r].x *= f0;
-          u[s][r].y *= f1;
-        }
-      }
-      if (INV && !FWD) {
-        if (A.accumulate) {
-#pragma unroll
-          for (int s = 0; s < IPT; ++s) {
-            const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
-#pragma unroll
-            for (int r = 0; r < RS; ++r)
-              wv[s][r] = *reinterpret_cast<const double2*>(A.real_out + (row0 + c) * g.nz + 2 * (bi + r * PS));
-          }
-#pragma unroll
-          for (int s = 0; s < IPT; ++s)
-#pragma unroll
-            for (int r = 0; r < RS; ++r) {
-              u[s][r].x += wv[s][r].x;
-              u[s][r].y += wv[s][r].y;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < IPT; ++s) {
-          const int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
-#pragma unroll
-          for (int r = 0; r < RS; ++r)
-            *reinterpret_cast<double2*>(A.real_out + (row0 + c) * g.nz + 2 * (bi + r * PS)) = u[s][r];
-        }
-      }
-    }
-    if (FWD) {
-      if (INV) __syncthreads();   // every thread has finished reading the tile in the last inverse stage
-      fft_first_regs<H, 1, true, RS>(tile, tid, u);
-      MidStages<H, 1, true, 1, RS>::run(tile, twh, tid);
-      constexpr int RL = FFT_LAST_RADIX(H, true);
-      double2 v[16 / RL][RL];
-      fft_last<H, 1, true, RL>(tile, twh, tid, v);
-      __syncthreads();
-#pragma unroll
-      for (int s = 0; s < 16 / RL; ++s) {
-        int w_ = tid + s * NT, bi = w_ >> 3, c = w_ & 7;
-#pragma unroll
-        for (int r = 0; r < RL; ++r) tile[(bi + r * (H / RL)) * FFT_LDT + c] = v[s][r];
-      }
-      __syncthreads();
-      // T[k] = 1/2 (V[k] + conj V[H-k]) - i/2 e^{-2 pi i k/nz} (V[k] - conj V[H-k]),  V[H] = V[0]
-      for (int e = tid; e < FFT_TZ * A.Kz_out; e += NT) {
-        int r = e / A.Kz_out, k = e - r * A.Kz_out;
-        int k1 = (k == H) ? 0 : k, k2 = (k == 0 || k == H) ? 0 : H - k;
-        double2 v1 = tile[k1 * FFT_LDT + r], v2 = tile[k2 * FFT_LDT + r];
-        double2 ev = make_double2(0.5 * (v1.x + v2.x), 0.5 * (v1.y - v2.y));
-        double2 dv = make_double2(0.5 * (v1.x - v2.x), 0.5 * (v1.y + v2.y));
-        double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);  // (-i dv) * e^{-2 pi i k/nz}
-        A.R[(row0 + r) * A.Kzp_out + k] = make_double2(ev.x + od.x, ev.y + od.y);
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // Z pass, warp-per-row variant.  Each warp owns RW = max(1, 256/H) rows and a private padded
@@ -656,6 +519,14 @@ template <> struct WPlan<256> { static constexpr int NS = 3; static constexpr in
 template <> struct WPlan<512> { static constexpr int NS = 3; static constexpr int R[3] = {8, 8, 8}; };
 
 __device__ __forceinline__ int zpad(int i) { return i + (i >> 3); }
+
+// 1 / (1e-12 + sqrt(r2))  (pk/compute_pk_randoms.py:166) through one reciprocal square root:
+// 1/(e + r) = rs (1 - e rs + O((e rs)^2)), rs = 1/r; e rs <= 1e-12/|r| so the dropped term is < 1e-24.
+__device__ __forceinline__ double inv_norm_eps(double r2) {
+  if (r2 <= 0.0) return 1e12;
+  const double rs = rsqrt(r2);
+  return rs - 1e-12 * rs * rs;
+}
 
 template <int H, bool REV, int S>
 struct WRadix {
@@ -787,7 +658,9 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
   for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * WARPS) {
     const long long row0 = grp * RW;
     double2 u[IPS][SE];
-    constexpr bool EARLY_W = (IPS == 1);   // 16 values per lane (H = 512) leave no registers for an early prefetch
+    // early prefetch of the weights only where the registers allow it: not with 16 values per lane
+    // (H = 512) and not in the batched inverse-only variant (which carries an accumulator)
+    constexpr bool EARLY_W = (IPS == 1) && (FWD || !INV);
     double2 wv[EARLY_W ? IPS : 1][SE];
     // weights of the real-space step: issued first, consumed after the inverse transform
     if (EARLY_W && A.wmap) {
@@ -799,11 +672,12 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
           wv[s][r] = *reinterpret_cast<const double2*>(A.wmap + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
       }
     }
-    if (INV) {
+    // inverse transform of the rows of one plane -> registers u (outputs at m = bi + r*BPS)
+    auto do_inverse = [&](const double2* __restrict__ Qbase) {
       // 1. complex input rows -> buffer (natural positions, padded)
       __syncwarp();
       for (int rho = 0; rho < RW; ++rho) {
-        const double2* src = A.Q + (row0 + rho) * A.Kzp_in;
+        const double2* src = Qbase + (row0 + rho) * A.Kzp_in;
         double2* row = buf + rho * ROWLEN;
         for (int k0 = lane; k0 < A.Kz_in; k0 += 128) {
           double2 v[4];
@@ -865,6 +739,46 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         w_twiddle<SE, -1>(tabi + WTabOff<H, false, WPlan<H>::NS - 1>::value, BPS, bi, u[s]);
         dftR<SE, -1>(u[s]);
       }
+    };
+    if (INV) {
+      if (!FWD && A.nb > 1) {
+        // sum of nb inverse transforms, each times Y_lm(r^) (or 1): the real-space map is written once
+        double2 acc[IPS][SE];
+#pragma unroll
+        for (int s = 0; s < IPS; ++s)
+#pragma unroll
+          for (int r = 0; r < SE; ++r) acc[s][r] = make_double2(0.0, 0.0);
+        for (int bq = 0; bq < A.nb; ++bq) {
+          do_inverse(A.Q + (long long)bq * A.q_stride);
+          const int lmb = A.lms[bq];
+#pragma unroll
+          for (int s = 0; s < IPS; ++s) {
+            const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+#pragma unroll
+            for (int r = 0; r < SE; ++r) {
+              double f0 = 1.0, f1 = 1.0;
+              if (lmb >= 0) {
+                const long long row = row0 + rho;
+                const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny), m = bi + r * BPS;
+                double X = g.rax[0][ix], Y = g.rax[1][iy];
+                double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
+                const double xy2 = X * X + Y * Y;
+                const double i0 = inv_norm_eps(xy2 + Z0 * Z0), i1 = inv_norm_eps(xy2 + Z1 * Z1);
+                f0 = sww_ylm_dyn(lmb, X * i0, Y * i0, Z0 * i0);
+                f1 = sww_ylm_dyn(lmb, X * i1, Y * i1, Z1 * i1);
+              }
+              acc[s][r].x += f0 * u[s][r].x;
+              acc[s][r].y += f1 * u[s][r].y;
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < IPS; ++s)
+#pragma unroll
+          for (int r = 0; r < SE; ++r) u[s][r] = acc[s][r];
+      } else {
+        do_inverse(A.Q);
+      }
     } else {
 #pragma unroll
       for (int s = 0; s < IPS; ++s) {
@@ -891,13 +805,13 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
           f0 *= wv[ws][r].x;
           f1 *= wv[ws][r].y;
         }
-        if (YLM) {
+        if (YLM && !(INV && !FWD && A.nb > 1)) {
           const long long row = row0 + rho;
           const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny), m = bi + r * BPS;
           double X = g.rax[0][ix], Y = g.rax[1][iy];
           double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
-          double r0 = sqrt(X * X + Y * Y + Z0 * Z0), r1 = sqrt(X * X + Y * Y + Z1 * Z1);
-          double i0 = 1.0 / (1e-12 + r0), i1 = 1.0 / (1e-12 + r1);
+          const double xy2 = X * X + Y * Y;
+          const double i0 = inv_norm_eps(xy2 + Z0 * Z0), i1 = inv_norm_eps(xy2 + Z1 * Z1);
           f0 *= sww_ylm_dyn(A.lm, X * i0, Y * i0, Z0 * i0);
           f1 *= sww_ylm_dyn(A.lm, X * i1, Y * i1, Z1 * i1);
         }
@@ -1091,10 +1005,6 @@ static inline int grid_for_items(long long items, int per_sm) {
 static size_t col_smem(int N, int hist_doubles) {
   return (size_t)N * FFT_LDT * 16 + (size_t)N * 16 + (size_t)hist_doubles * 8;
 }
-static int z_stage_pitch(int Kz_in) { return (Kz_in + 8) | 1; }   // odd pitch: conflict-free transposed reads
-static size_t z_smem(int H, int Kz_in) {
-  return (size_t)H * FFT_LDT * 16 + (size_t)H * 16 + (size_t)(H + 8) * 16 + (size_t)8 * z_stage_pitch(Kz_in) * 16;
-}
 
 static int occ_for(size_t smem) {
   int o = (int)((227 * 1024) / (smem + 1024));
@@ -1104,6 +1014,12 @@ static int occ_for(size_t smem) {
 }
 
 // ---- column-pass launchers, generic in the transformed axis -------------------------------------
+static BoxAxis box_axis_of(int n, int b) {
+  int K = 2 * b + 1;
+  if (K >= n) return BoxAxis{n, n, n - 1};
+  return BoxAxis{n, K, b};
+}
+
 struct AxisPlan {
   BoxAxis bx, by;   // kept indices along x and y
   bool x_first_fwd; // forward: transform x before y (x is the more strongly pruned axis)
@@ -1120,21 +1036,23 @@ static AxisPlan make_plan(const Geo& g, BoxAxis bx, BoxAxis by) {
 static const double2* tw_of(Sm100State* s, int ax) { return ax == 0 ? s->tw_x : s->tw_y; }
 
 template <int N, int AX>
-static int launch_i1(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* src, int shell) {
+static int launch_i1(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* src, int shell,
+                     const GatherArgs& ga) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)bO.K * (Kzp / FFT_TZ);
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i1_kernel<N, AX>, smem));
-  pass_i1_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P);
+  pass_i1_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, ga,
+                                                         box_axis_of(c->g.nx, c->g.bx), box_axis_of(c->g.ny, c->g.by));
   return 0;
 }
 template <int N, int AX>
-static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp) {
+static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, double2* Qdst) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)nF * (Kzp / FFT_TZ);
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i2_kernel<N, AX>, smem));
-  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), s->Q);
+  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst);
   return 0;
 }
 template <int N, int AX>
@@ -1183,14 +1101,18 @@ static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO
 static int axis_len(const Geo& g, int ax) { return ax == 0 ? g.nx : g.ny; }
 
 // inverse column passes: spectrum (box, optional shell filter) -> Q[nx][ny][Kzp]
-static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, const double2* src, int shell) {
+static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, const double2* src, int shell,
+                            const GatherArgs* gap = nullptr, double2* Qdst = nullptr) {
+  GatherArgs ga = {};
+  if (gap) ga = *gap;
+  if (!Qdst) Qdst = s->Q;
   const int a1 = pl.x_first_fwd ? 1 : 0;   // first inverse axis = the weakly pruned one
   const int a2 = 1 - a1;
   const BoxAxis b1 = a1 == 0 ? pl.bx : pl.by, b2 = a2 == 0 ? pl.bx : pl.by;
   const int n1 = axis_len(c->g, a1), n2 = axis_len(c->g, a2);
   {
     SWW_PROF(c, a1 == 0 ? "fft.I1 x-inverse (gather)" : "fft.I1 y-inverse (gather)");
-#define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell)
+#define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell, ga)
     DISPATCH_AX(n1, a1, CALL)
 #undef CALL
     c->n_own++;
@@ -1198,7 +1120,7 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
   }
   {
     SWW_PROF(c, a2 == 0 ? "fft.I2 x-inverse" : "fft.I2 y-inverse");
-#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp)
+#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst)
     DISPATCH_AX(n2, a2, CALL)
 #undef CALL
     c->n_own++;
@@ -1402,4 +1324,45 @@ int sww_sm100_pk_row(sww_ctx* c, const double2* F, int shell, const double* wmap
   A.scale = scale;
   A.out_row = out_row;
   return run_forward_cols(c, s, plo, Kzo, Kzpo, 2, A);
+}
+
+// sum over nb gathered spectra of  wmap * scale * Y_{lms_r[b]}(r^) * IFT[ gather_b ]  -> real_out, one write.
+// Every gather is restricted to the box of shell `box_shell`; the nb intermediate planes live in qstack.
+int sww_sm100_inverse_multi(sww_ctx* c, int nb, const GatherArgs* gas, int box_shell, const int* lms_r,
+                            const double* wmap, double scale, int accumulate, double2* qstack, double* real_out) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  SWW_REQUIRE(nb >= 1 && nb <= SWW_MAX_ZBATCH, "inverse_multi: batch of %d planes", nb);
+  const Geo& g = c->g;
+  int b_x = g.bx, b_y = g.by, b_z = g.bz;
+  if (box_shell >= 0) {
+    b_x = s->shell_bx[box_shell];
+    b_y = s->shell_by[box_shell];
+    b_z = s->shell_bz[box_shell];
+  }
+  AxisPlan pl = make_plan(g, box_axis(g.nx, b_x), box_axis(g.ny, b_y));
+  int Kz = b_z + 1 < g.nzh ? b_z + 1 : g.nzh, Kzp = up8(Kz);
+  const long long stride = (long long)g.nx * g.ny * Kzp;
+  ZArgs Z = {};
+  bool any_ylm = false;
+  for (int b = 0; b < nb; ++b) {
+    SWW_TRY(run_inverse_cols(c, s, pl, Kz, Kzp, nullptr, -1, &gas[b], qstack + (long long)b * stride));
+    Z.lms[b] = lms_r[b];
+    any_ylm = any_ylm || lms_r[b] >= 0;
+  }
+  Z.Q = qstack;
+  Z.Kz_in = Kz;
+  Z.Kzp_in = Kzp;
+  Z.real_out = real_out;
+  Z.wmap = wmap;
+  Z.scale = scale;
+  Z.accumulate = accumulate;
+  Z.nb = nb;
+  Z.q_stride = stride;
+  Z.lm = (nb == 1) ? lms_r[0] : (any_ylm ? 0 : -1);   // selects the Y_lm-capable kernel variant
+  return run_z(c, s, true, false, Z);
+}
+
+size_t sww_sm100_qstack_bytes(const sww_ctx* c, int nb) {
+  return (size_t)nb * c->g.nx * c->g.ny * up8(c->g.Kz) * sizeof(double2);
 }

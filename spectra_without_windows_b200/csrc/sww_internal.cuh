@@ -165,6 +165,18 @@ struct F3Args {
   unsigned int* counter;
   double* out_row;
 };
+// gather description for the first inverse pass: sum of up to three compact box spectra, each kept only
+// inside its shell, times coef * Y_lm(k^)  (n_terms == 0: plain spectrum + optional shell filter)
+struct GatherArgs {
+  const double2* p[3];
+  int s[3];
+  int n_terms;
+  int lm;
+  double coef;
+};
+#define SWW_MAX_ZBATCH 10
+int sww_sm100_inverse_multi(sww_ctx* c, int nb, const GatherArgs* gas, int box_shell, const int* lms_r,
+                            const double* wmap, double scale, int accumulate, double2* qstack, double* real_out);
 int sww_sm100_forward_box(sww_ctx* c, const double* real_in, const double* wmap, int lm_r, int mode, F3Args A);
 int sww_sm100_inverse_box(sww_ctx* c, const double2* src, int filter_shell, int box_shell, const double* wmap, int lm_r,
                           double scale, int accumulate, double* real_out);
