@@ -76,6 +76,12 @@ int sww_set_fft_backend(sww_ctx* c, int backend);
 int sww_set_fields(sww_ctx* c, sww_devptr nbar, sww_devptr nbar_weight, sww_devptr nbar_A,
                    double shot_fac, double P_fkp);
 
+/* Optional cache of the real-space harmonics Y_lm(r^) for l > 0: `maps` is caller-owned device memory of
+ * sww_ylm_cache_bytes() bytes which the library fills; 0 disables the cache (harmonics are then
+ * re-evaluated in registers).  Trades (n_lm - 1) maps of HBM for the FP64 work of the z passes. */
+int sww_ylm_cache_bytes(sww_ctx* c, uint64_t* bytes);
+int sww_set_ylm_cache(sww_ctx* c, sww_devptr maps);
+
 /* ---- drop-in operators (mirrors of src/opt_utilities.py and src/covariances_pk.py) ---- */
 /* ft / ift  (src/opt_utilities.py:502-555) in complex128; inverse normalised by 1/N. */
 int sww_fft_c2c(sww_ctx* c, sww_devptr in, sww_devptr out, int inverse);

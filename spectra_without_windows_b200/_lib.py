@@ -35,6 +35,8 @@ SIGNATURES = {
     "sww_set_fft_backend": [ctxp, C.c_int],
     "sww_profile_enable": [ctxp, C.c_int],
     "sww_profile_report": [ctxp, C.c_char_p, u64],
+    "sww_ylm_cache_bytes": [ctxp, C.POINTER(u64)],
+    "sww_set_ylm_cache": [ctxp, u64],
     "sww_set_fields": [ctxp, u64, u64, u64, f64, f64],
     "sww_fft_c2c": [ctxp, u64, u64, C.c_int],
     "sww_fft_r2c": [ctxp, u64, u64],

@@ -500,6 +500,8 @@ struct ZArgs {
   int nb;
   int lms[SWW_MAX_ZBATCH];
   long long q_stride;
+  const double* ymaps;   // optional cache [lm-1][N] of Y_lm(r^)
+  long long N;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -751,6 +753,23 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         for (int bq = 0; bq < A.nb; ++bq) {
           do_inverse(A.Q + (long long)bq * A.q_stride);
           const int lmb = A.lms[bq];
+          if (lmb >= 1 && A.ymaps) {
+            const double* ym = A.ymaps + (long long)(lmb - 1) * A.N;
+#pragma unroll
+            for (int s = 0; s < IPS; ++s) {
+              const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+              double2 yv[SE];
+#pragma unroll
+              for (int r = 0; r < SE; ++r)
+                yv[r] = *reinterpret_cast<const double2*>(ym + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
+#pragma unroll
+              for (int r = 0; r < SE; ++r) {
+                acc[s][r].x += yv[r].x * u[s][r].x;
+                acc[s][r].y += yv[r].y * u[s][r].y;
+              }
+            }
+            continue;
+          }
 #pragma unroll
           for (int s = 0; s < IPS; ++s) {
             const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
@@ -805,7 +824,12 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
           f0 *= wv[ws][r].x;
           f1 *= wv[ws][r].y;
         }
-        if (YLM && !(INV && !FWD && A.nb > 1)) {
+        if (YLM && !(INV && !FWD && A.nb > 1) && A.lm >= 1 && A.ymaps) {
+          const double2 yv = *reinterpret_cast<const double2*>(A.ymaps + (long long)(A.lm - 1) * A.N + (row0 + rho) * g.nz +
+                                                               2 * (bi + r * BPS));
+          f0 *= yv.x;
+          f1 *= yv.y;
+        } else if (YLM && !(INV && !FWD && A.nb > 1)) {
           const long long row = row0 + rho;
           const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny), m = bi + r * BPS;
           double X = g.rax[0][ix], Y = g.rax[1][iy];
@@ -1169,6 +1193,8 @@ static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
 
 static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   SWW_PROF(c, inv && fwd ? "fft.Z c2r*w*r2c fused" : (inv ? "fft.Z c2r" : "fft.Z r2c"));
+  A.ymaps = c->ylm_maps;
+  A.N = c->g.N;
   const int H = c->g.nz / 2;
   const bool ylm = A.lm >= 0;
 #define M(HH)                                                      \

@@ -452,3 +452,39 @@ int k_paint(sww_ctx* c, const double* pos, const double* w, unsigned long long n
   SWW_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// optional cache of Y_lm(r^) maps, lm >= 1
+// ------------------------------------------------------------------------------------------
+__global__ void ylm_fill_kernel(Geo g, int lm, double* __restrict__ out) {
+  long long rows = (long long)g.nx * g.ny;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+    double X = g.rax[0][ix], Y = g.rax[1][iy];
+    for (int iz = threadIdx.x; iz < g.nz; iz += blockDim.x) {
+      double x, y, z;
+      unit_vec(X, Y, g.rax[2][iz], x, y, z);
+      out[row * g.nz + iz] = sww_ylm_dyn(lm, x, y, z);
+    }
+  }
+}
+
+extern "C" int sww_ylm_cache_bytes(sww_ctx* c, uint64_t* bytes) {
+  SWW_REQUIRE(c && bytes, "null argument");
+  *bytes = (uint64_t)(c->n_lm - 1) * c->g.N * sizeof(double);
+  return 0;
+}
+
+extern "C" int sww_set_ylm_cache(sww_ctx* c, sww_devptr maps) {
+  SWW_REQUIRE(c, "null context");
+  c->ylm_maps = nullptr;
+  if (!maps || c->n_lm <= 1) return 0;
+  double* m = (double*)maps;
+  for (int lm = 1; lm < c->n_lm; ++lm) {
+    ylm_fill_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, lm, m + (size_t)(lm - 1) * c->g.N);
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+  }
+  c->ylm_maps = m;
+  return 0;
+}

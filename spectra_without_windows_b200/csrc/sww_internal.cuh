@@ -104,6 +104,7 @@ struct sww_ctx {
   size_t fft_work_bytes = 0;   // bytes reserved for FFT scratch (cuFFT work area or the sm_100a pass buffers)
   size_t fft_work_cap = 0;
   void* sm100 = nullptr;       // Sm100State (fft_sm100.cu)
+  const double* ylm_maps = nullptr;   // optional cache [n_lm-1][N] of Y_lm(r^), lm >= 1
   // cuFFT
   cufftHandle plan_d2z = 0, plan_z2d = 0, plan_z2z = 0;
   bool have_z2z = false;

@@ -144,6 +144,15 @@ class Context:
         self.use_stream(t.cuda.current_stream(self.device))
         _lib.check(self.lib.sww_bind_workspace(self._h, self.workspace.data_ptr(), int(need)))
         self._fields = None
+        # optional cache of the Y_lm(r^) maps (l > 0): used when it costs < 15 % of the device memory
+        self._ylm_cache = None
+        if self.fft_backend == 1 and os.environ.get("SWW_YLM_CACHE", "auto") != "0":
+            b = _lib.u64(0)
+            _lib.check(self.lib.sww_ylm_cache_bytes(self._h, C.byref(b)))
+            total = t.cuda.get_device_properties(self.device).total_memory
+            if 0 < b.value <= 0.15 * total:
+                self._ylm_cache = t.empty(int(b.value), dtype=t.uint8, device=self.device)
+                _lib.check(self.lib.sww_set_ylm_cache(self._h, self._ylm_cache.data_ptr()))
 
     # -- plumbing
     def use_stream(self, stream):
