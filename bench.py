@@ -37,6 +37,9 @@ WORKLOADS = {
                bins=(0.0, 0.11, 0.01, 4), bk=True),
     "C4S": dict(grid=(128, 128, 128), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
                 bins=(0.0, 0.11, 0.01, 2), bk=True),
+    # pk data path (paint + q_alpha): config C1 of SURVEY 8d; a step = one catalogue
+    "C1": dict(grid=(128, 128, 128), box=(1000.0, 1000.0, 1000.0), box_center=(0.0, 0.0, 2000.0),
+               bins=(0.0, 0.25, 0.01, 4), data=True, n_gal=300000, n_ran=15000000),
     "S256": dict(grid=(256, 256, 256), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
                  bins=(0.0, 0.20, 0.005, 4)),
 }
@@ -144,6 +147,58 @@ def workload_config(name, mesh):
                mesh.dk, mesh.lmax, mesh.n_k * mesh.n_l),
             "n_b": mesh.n_k * mesh.n_l, "n_fft_min_per_realisation": n_fft_min(sum(2 * l + 1 for l in range(0, mesh.lmax + 1, 2)), mesh.n_k * mesh.n_l),
             "l2": "inputs>L2 (every map is >= 1 GB, L2 is 126 MB)" if mesh.N * 8 > 2 * 126e6 else "maps fit L2 partially; 512 MB scratch written between steps"}
+
+
+def run_pk_data(args, wl, mesh, rank, world, local, dev):
+    """pk data path (pk/compute_pk_data.py:133-206): TSC painting of galaxies and randoms + q_alpha."""
+    import torch
+    from spectra_without_windows_b200 import engine
+    ctx = engine.Context(mesh, local, ("pk_data",))
+    rax_d = [torch.from_numpy(a).to(dev) for a in mesh.rax]
+    nbar_r = uniform_nbar_r(rax_d, torch).contiguous()
+    ctx.set_fields(nbar_r * ALPHA, nbar_r * ALPHA, nbar_r, SHOT)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1001 + rank)
+    box = torch.tensor(wl["box"], dtype=torch.float64, device=dev)
+    bc = torch.tensor(wl["box_center"], dtype=torch.float64, device=dev)
+    dpos = (torch.rand((wl["n_gal"], 3), generator=g, device=dev, dtype=torch.float64) - 0.5) * box + bc
+    rpos = (torch.rand((wl["n_ran"], 3), generator=g, device=dev, dtype=torch.float64) - 0.5) * box + bc
+    dw = torch.ones(wl["n_gal"], dtype=torch.float64, device=dev)
+    rw = torch.ones(wl["n_ran"], dtype=torch.float64, device=dev)
+    alpha = wl["n_gal"] / wl["n_ran"]
+    v = mesh.v_cell
+
+    def step():
+        diff = ctx.paint(dpos, dw, wl["box_center"], scale=1.0 / v)
+        ctx.paint(rpos, rw, wl["box_center"], scale=-alpha / v, out=diff)
+        return ctx.pk_data_q(diff)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        q = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0.record()
+    for _ in range(args.steps):
+        diff = ctx.paint(dpos, dw, wl["box_center"], scale=1.0 / v)
+        ctx.paint(rpos, rw, wl["box_center"], scale=-alpha / v, out=diff)
+    ep1.record()
+    torch.cuda.synchronize()
+    pms = ep0.elapsed_time(ep1) / args.steps
+    npart = wl["n_gal"] + wl["n_ran"]
+    print(json.dumps({"metric": "pk data catalogues/s", "value": args.steps / (ms * 1e-3), "unit": "catalogues/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "C1: compute_pk_data (TSC paint of %d galaxies + %d randoms, q_alpha), mesh 128^3, n_b=%d"
+                                 % (wl["n_gal"], wl["n_ran"], ctx.n_b)},
+                      "paint_ms": pms, "paint_particles_per_s": npart / (pms * 1e-3),
+                      "paint_gbs_algorithmic": 32.0 * npart / (pms * 1e-3) / 1e9, "q_finite": bool(torch.isfinite(q).all())}))
 
 
 def run_bk(args, wl, mesh, rank, world, local, dev):
@@ -254,6 +309,8 @@ def main():
     mesh = engine.Mesh(wl["box"], wl["grid"], wl["box_center"], *wl["bins"])
     if wl.get("bk"):
         return run_bk(args, wl, mesh, rank, world, local, dev)
+    if wl.get("data"):
+        return run_pk_data(args, wl, mesh, rank, world, local, dev)
     ctx = engine.Context(mesh, local, ("pk_fisher",))
     if args.fft >= 0:
         ctx.set_fft_backend(args.fft)

@@ -705,18 +705,21 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int k = bi + r * BPR, hk = H - k;
-            double2 zk = (k < A.Kz_in) ? row[zpad(k)] : make_double2(0.0, 0.0);
-            double2 zh = (hk < A.Kz_in) ? row[zpad(hk)] : make_double2(0.0, 0.0);
-            if (k == 0) {
-              zk.y = 0.0;
-              zh.y = 0.0;
+            y[s][r] = make_double2(0.0, 0.0);
+            if (k < A.Kz_in || hk < A.Kz_in) {   // both halves empty for most k of a low shell
+              double2 zk = (k < A.Kz_in) ? row[zpad(k)] : make_double2(0.0, 0.0);
+              double2 zh = (hk < A.Kz_in) ? row[zpad(hk)] : make_double2(0.0, 0.0);
+              if (k == 0) {
+                zk.y = 0.0;
+                zh.y = 0.0;
+              }
+              double2 a = make_double2(zk.x + zh.x, zk.y - zh.y);
+              double2 d = make_double2(zk.x - zh.x, zk.y + zh.y);
+              double2 w = twn[k];
+              w.y = -w.y;
+              double2 b = c_mul(d, w);
+              y[s][r] = make_double2(a.x - b.y, a.y + b.x);
             }
-            double2 a = make_double2(zk.x + zh.x, zk.y - zh.y);
-            double2 d = make_double2(zk.x - zh.x, zk.y + zh.y);
-            double2 w = twn[k];
-            w.y = -w.y;
-            double2 b = c_mul(d, w);
-            y[s][r] = make_double2(a.x - b.y, a.y + b.x);
           }
           dftR<R, -1>(y[s]);
         }
