@@ -16,6 +16,7 @@
 //
 // The fused P_l Fisher row is I1 -> I2 -> Z(c2r * nW * r2c in shared memory) -> F2 -> F3(bin): the
 // real-space map u_alpha and its weighted transform never touch HBM.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -161,7 +162,8 @@ __device__ __forceinline__ long long row_of(int a, int o, int ny) {
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
 pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ src, int shell,
-               const double2* __restrict__ twg, double2* __restrict__ P, GatherArgs ga, BoxAxis cbx, BoxAxis cby) {
+               const double2* __restrict__ twg, double2* __restrict__ Pbase, GatherBatch gb, BoxAxis cbx, BoxAxis cby,
+               long long pstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -170,8 +172,13 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
   constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
-  const long long items = (long long)bO.K * ztiles;
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+  const long long per = (long long)bO.K * ztiles;
+  const long long items = per * (gb.nb > 0 ? gb.nb : 1);
+  for (long long it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
+    const int bat = (int)(it0 / per);
+    const long long it = it0 - (long long)bat * per;
+    const GatherArgs& ga = gb.ga[bat];
+    double2* __restrict__ P = Pbase + (long long)bat * pstride;
     const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
     const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
     __syncthreads();
@@ -228,8 +235,8 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
 // Second inverse pass (axis AX, box bA): P[ja][f][iz] -> Q[row][iz]; item = (f, z-tile), f < nF
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
-pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ P, const double2* __restrict__ twg,
-               double2* __restrict__ Q) {
+pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Pbase, const double2* __restrict__ twg,
+               double2* __restrict__ Qbase, int nb, long long pstride, long long qstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -238,8 +245,13 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
   constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
-  const long long items = (long long)nF * ztiles;
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+  const long long per = (long long)nF * ztiles;
+  const long long items = per * nb;
+  for (long long it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
+    const int bat = (int)(it0 / per);
+    const long long it = it0 - (long long)bat * per;
+    const double2* __restrict__ P = Pbase + (long long)bat * pstride;
+    double2* __restrict__ Q = Qbase + (long long)bat * qstride;
     const int f = (int)(it / ztiles), zt = (int)(it - (long long)f * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
@@ -1064,22 +1076,24 @@ static const double2* tw_of(Sm100State* s, int ax) { return ax == 0 ? s->tw_x : 
 
 template <int N, int AX>
 static int launch_i1(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* src, int shell,
-                     const GatherArgs& ga) {
+                     const GatherBatch& gb, long long pstride) {
   size_t smem = col_smem(N, 0);
-  long long items = (long long)bO.K * (Kzp / FFT_TZ);
+  long long items = (long long)bO.K * (Kzp / FFT_TZ) * (gb.nb > 0 ? gb.nb : 1);
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i1_kernel<N, AX>, smem));
-  pass_i1_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, ga,
-                                                         box_axis_of(c->g.nx, c->g.bx), box_axis_of(c->g.ny, c->g.by));
+  pass_i1_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, gb,
+                                                         box_axis_of(c->g.nx, c->g.bx), box_axis_of(c->g.ny, c->g.by),
+                                                         pstride);
   return 0;
 }
 template <int N, int AX>
-static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, double2* Qdst) {
+static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, double2* Qdst, int nb, long long pstride,
+                     long long qstride) {
   size_t smem = col_smem(N, 0);
-  long long items = (long long)nF * (Kzp / FFT_TZ);
+  long long items = (long long)nF * (Kzp / FFT_TZ) * nb;
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i2_kernel<N, AX>, smem));
-  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst);
+  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride);
   return 0;
 }
 template <int N, int AX>
@@ -1129,29 +1143,40 @@ static int axis_len(const Geo& g, int ax) { return ax == 0 ? g.nx : g.ny; }
 
 // inverse column passes: spectrum (box, optional shell filter) -> Q[nx][ny][Kzp]
 static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, const double2* src, int shell,
-                            const GatherArgs* gap = nullptr, double2* Qdst = nullptr) {
-  GatherArgs ga = {};
-  if (gap) ga = *gap;
+                            const GatherArgs* gap = nullptr, int nb = 1, double2* Qdst = nullptr, long long qstride = 0) {
   if (!Qdst) Qdst = s->Q;
   const int a1 = pl.x_first_fwd ? 1 : 0;   // first inverse axis = the weakly pruned one
   const int a2 = 1 - a1;
   const BoxAxis b1 = a1 == 0 ? pl.bx : pl.by, b2 = a2 == 0 ? pl.bx : pl.by;
   const int n1 = axis_len(c->g, a1), n2 = axis_len(c->g, a2);
-  {
-    SWW_PROF(c, a1 == 0 ? "fft.I1 x-inverse (gather)" : "fft.I1 y-inverse (gather)");
-#define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell, ga)
-    DISPATCH_AX(n1, a1, CALL)
+  // a batch shares the P buffer: plane stride = what one pruned plane of this box needs; the batch is
+  // processed in chunks of as many planes as fit
+  const long long pstride = (long long)b2.K * n1 * Kzp;
+  int chunk = (int)std::min<long long>(nb, (long long)(s->buf_elems / (size_t)pstride));
+  SWW_REQUIRE(chunk >= 1, "pass buffer too small for one pruned plane");
+  for (int b0 = 0; b0 < nb; b0 += chunk) {
+    const int nbc = std::min(chunk, nb - b0);
+    GatherBatch gb = {};
+    if (gap) {
+      gb.nb = nbc;
+      for (int b = 0; b < nbc; ++b) gb.ga[b] = gap[b0 + b];
+    }
+    {
+      SWW_PROF(c, a1 == 0 ? "fft.I1 x-inverse (gather)" : "fft.I1 y-inverse (gather)");
+#define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell, gb, pstride)
+      DISPATCH_AX(n1, a1, CALL)
 #undef CALL
-    c->n_own++;
-    SWW_CUDA(cudaGetLastError());
-  }
-  {
-    SWW_PROF(c, a2 == 0 ? "fft.I2 x-inverse" : "fft.I2 y-inverse");
-#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst)
-    DISPATCH_AX(n2, a2, CALL)
+      c->n_own++;
+      SWW_CUDA(cudaGetLastError());
+    }
+    {
+      SWW_PROF(c, a2 == 0 ? "fft.I2 x-inverse" : "fft.I2 y-inverse");
+#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst + (long long)b0 * qstride, nbc, pstride, qstride)
+      DISPATCH_AX(n2, a2, CALL)
 #undef CALL
-    c->n_own++;
-    SWW_CUDA(cudaGetLastError());
+      c->n_own++;
+      SWW_CUDA(cudaGetLastError());
+    }
   }
   return 0;
 }
@@ -1374,8 +1399,8 @@ int sww_sm100_inverse_multi(sww_ctx* c, int nb, const GatherArgs* gas, int box_s
   const long long stride = (long long)g.nx * g.ny * Kzp;
   ZArgs Z = {};
   bool any_ylm = false;
+  SWW_TRY(run_inverse_cols(c, s, pl, Kz, Kzp, nullptr, -1, gas, nb, qstack, stride));
   for (int b = 0; b < nb; ++b) {
-    SWW_TRY(run_inverse_cols(c, s, pl, Kz, Kzp, nullptr, -1, &gas[b], qstack + (long long)b * stride));
     Z.lms[b] = lms_r[b];
     any_ylm = any_ylm || lms_r[b] >= 0;
   }

@@ -176,6 +176,10 @@ struct GatherArgs {
   double coef;
 };
 #define SWW_MAX_ZBATCH 10
+struct GatherBatch {
+  GatherArgs ga[SWW_MAX_ZBATCH];
+  int nb;   // 0: plain spectrum mode
+};
 int sww_sm100_inverse_multi(sww_ctx* c, int nb, const GatherArgs* gas, int box_shell, const int* lms_r,
                             const double* wmap, double scale, int accumulate, double2* qstack, double* real_out);
 int sww_sm100_forward_box(sww_ctx* c, const double* real_in, const double* wmap, int lm_r, int mode, F3Args A);
