@@ -459,18 +459,22 @@ def main():
             kz_of = lambda kmax: min(int(np.floor(np.nextafter(kmax / kFz, 0))) + 1, nz // 2 + 1)
             kz_out = kz_of(mesh.k_hi[-1])
             kz_in_mean = float(np.mean([kz_of(k) for k in mesh.k_hi]))
-            bytes_launch = 8.0 * mesh.N + 16.0 * nx * ny * (kz_in_mean + kz_out)
+            rows_per_launch = max(1, round(n_b / prof[zkey]["launches"]))   # the n_l multipoles of one k bin share a launch
+            bytes_launch = 8.0 * mesh.N + rows_per_launch * 16.0 * nx * ny * (kz_in_mean + kz_out)
             dur = prof[zkey]["ms"] / prof[zkey]["launches"] * 1e-3
             traffic = None
             try:
                 if args.workload != "C2":
                     raise KeyError("the ncu capture was taken on C2")
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
+                tj = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+                if tj.get("rows_per_launch", 1) != rows_per_launch:
+                    raise KeyError("capture taken with a different batching")
+                traffic = tj["dram_bytes_per_launch"]
             except Exception:
                 pass
-            roof.update({"kernel": "pass_zw_kernel<256,INV,FWD> (fused z pass of one Fisher row), avg over %d launches of one realisation, CUDA events on the launching stream" % prof[zkey]["launches"],
+            roof.update({"kernel": "pass_zw_kernel<H,INV,FWD> (fused z pass: c2r * nW * r2c of the %d Fisher rows of one k bin), avg over %d launches of one realisation, CUDA events on the launching stream" % (rows_per_launch, prof[zkey]["launches"]),
                          "achieved": bytes_launch / dur / 1e9, "frac": bytes_launch / dur / 1e9 / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": dur * 1e3,
+                         "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": dur * 1e3, "rows_per_launch": rows_per_launch,
                          "share_of_step": prof[zkey]["ms"] / (ms / args.steps)})
         line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -188,7 +188,9 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
       if (bA.has(ia) && iz < Kz) {
         long long cell = row_of<AX>(ia, io, g.ny) * g.nzh + iz;
         if (ga.n_terms == 0) {
-          if (shell < 0 || g.binmap[cell] == shell) v = src[cell];
+          const double2* __restrict__ sp = gb.nb > 0 ? ga.src : src;
+          const int sh = gb.nb > 0 ? ga.shell : shell;
+          if (sh < 0 || g.binmap[cell] == sh) v = sp[cell];
         } else {
           const int b = g.binmap[cell];
           const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
@@ -278,8 +280,8 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
 // First forward column pass (axis AX, box bA): R[row][iz] -> P[ja][c][iz] (box rows only); item = (c, z-tile), c < nC
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
-pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ R, const double2* __restrict__ twg,
-               double2* __restrict__ P) {
+pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Rbase, const double2* __restrict__ twg,
+               double2* __restrict__ Pbase, int nb, long long rstride, long long pstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -288,8 +290,13 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
   constexpr int RL = FFT_LAST_RADIX(N, false);
   for (int i = tid; i < N; i += NT) tw[i] = twg[i];
   const int ztiles = Kzp / FFT_TZ;
-  const long long items = (long long)nC * ztiles;
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+  const long long per = (long long)nC * ztiles;
+  const long long items = per * nb;
+  for (long long it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
+    const int bat = (int)(it0 / per);
+    const long long it = it0 - (long long)bat * per;
+    const double2* __restrict__ R = Rbase + (long long)bat * rstride;
+    double2* __restrict__ P = Pbase + (long long)bat * pstride;
     const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
@@ -512,6 +519,7 @@ struct ZArgs {
   int nb;
   int lms[SWW_MAX_ZBATCH];
   long long q_stride;
+  long long r_stride;    // INV && FWD: nb > 1 transforms nb planes (Q + b*q_stride -> R + b*r_stride) per weight load
   const double* ymaps;   // optional cache [lm-1][N] of Y_lm(r^)
   long long N;
 };
@@ -757,6 +765,9 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         dftR<SE, -1>(u[s]);
       }
     };
+    // fused variant: nb > 1 transforms nb planes per weight load (the multipoles of one k bin)
+    const int nfb = (INV && FWD && A.nb > 1) ? A.nb : 1;
+    for (int fb = 0; fb < nfb; ++fb) {
     if (INV) {
       if (!FWD && A.nb > 1) {
         // sum of nb inverse transforms, each times Y_lm(r^) (or 1): the real-space map is written once
@@ -811,7 +822,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 #pragma unroll
           for (int r = 0; r < SE; ++r) u[s][r] = acc[s][r];
       } else {
-        do_inverse(A.Q);
+        do_inverse(A.Q + (long long)fb * A.q_stride);
       }
     } else {
 #pragma unroll
@@ -922,7 +933,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
       // T[k] = 1/2 (V[k] + conj V[H-k]) - i/2 e^{-2 pi i k/nz} (V[k] - conj V[H-k]),  V[H] = V[0]
       for (int rho = 0; rho < RW; ++rho) {
         const double2* row = buf + rho * ROWLEN;
-        double2* dst = A.R + (row0 + rho) * A.Kzp_out;
+        double2* dst = A.R + (long long)fb * A.r_stride + (row0 + rho) * A.Kzp_out;
         for (int k = lane; k < A.Kz_out; k += 32) {
           int k1 = (k == H) ? 0 : k, k2 = (k == 0 || k == H) ? 0 : H - k;
           double2 v1 = row[zpad(k1)], v2 = row[zpad(k2)];
@@ -933,6 +944,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         }
       }
     }
+    }   // fb
   }
 }
 
@@ -957,11 +969,17 @@ static std::vector<double2> make_tw(int n, int count) {
 
 static int up8(int k) { return (k + 7) & ~7; }
 
+// elements of each of the three pass buffers: one full plane, or n_l pruned planes (batched Fisher rows)
+static size_t pass_buf_elems(const sww_ctx* c) {
+  const Geo& g = c->g;
+  size_t full = (size_t)g.nx * g.ny * up8(g.nzh);
+  size_t batch = (size_t)c->n_l * g.nx * g.ny * up8(g.Kz);
+  return full > batch ? full : batch;
+}
+
 size_t sww_fft_sm100_work_bytes(const sww_ctx* c) {
   if (!sww_fft_sm100_supported(c)) return 0;
-  const Geo& g = c->g;
-  size_t e = (size_t)g.nx * g.ny * up8(g.nzh);
-  return 3 * e * sizeof(double2) + 1024;
+  return 3 * pass_buf_elems(c) * sizeof(double2) + 1024;
 }
 
 static int max_abs_idx(const sww_ctx* c, int axis, double kmax) {
@@ -1010,7 +1028,7 @@ void sww_fft_sm100_destroy(sww_ctx* c) {
 
 static int bind_bufs(sww_ctx* c, Sm100State* s) {
   SWW_REQUIRE(c->fft_work, "no workspace bound (sww_bind_workspace)");
-  size_t e = (size_t)c->g.nx * c->g.ny * up8(c->g.nzh);
+  size_t e = pass_buf_elems(c);
   SWW_REQUIRE(c->fft_work_cap >= 3 * e * sizeof(double2),
               "workspace was sized before the sm_100a FFT backend was selected; select it before binding");
   s->P = (double2*)c->fft_work;
@@ -1097,16 +1115,17 @@ static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, dou
   return 0;
 }
 template <int N, int AX>
-static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp) {
+static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int nb, long long rstride, long long pstride) {
   size_t smem = col_smem(N, 0);
-  long long items = (long long)nC * (Kzp / FFT_TZ);
+  long long items = (long long)nC * (Kzp / FFT_TZ) * nb;
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_f2_kernel<N, AX>, smem));
-  pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P);
+  pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride);
   return 0;
 }
 template <int N, int AX>
-static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, F3Args A) {
+static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, F3Args A,
+                     const double2* Psrc) {
   int hist = (mode == 2) ? (N / 2 / 32) * A.n_g * c->g.n_k : 0;
   size_t smem = col_smem(N, hist);
   long long items = (long long)bO.K * (Kzp / FFT_TZ);
@@ -1118,13 +1137,13 @@ static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO
   }
   if (mode == 0) {
     SWW_TRY(set_smem(pass_f3_kernel<N, AX, 0>, smem));
-    pass_f3_kernel<N, AX, 0><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, s->P, tw_of(s, AX), A);
+    pass_f3_kernel<N, AX, 0><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);
   } else if (mode == 1) {
     SWW_TRY(set_smem(pass_f3_kernel<N, AX, 1>, smem));
-    pass_f3_kernel<N, AX, 1><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, s->P, tw_of(s, AX), A);
+    pass_f3_kernel<N, AX, 1><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);
   } else {
     SWW_TRY(set_smem(pass_f3_kernel<N, AX, 2>, smem));
-    pass_f3_kernel<N, AX, 2><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, s->P, tw_of(s, AX), A);
+    pass_f3_kernel<N, AX, 2><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);
   }
   return 0;
 }
@@ -1182,22 +1201,27 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
 }
 
 // forward column passes: R[nx][ny][Kzp] -> epilogue `mode`
-static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, int mode, F3Args A) {
+static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, int mode, F3Args A,
+                            int nb = 1, long long rstride = 0, const F3Args* Ab = nullptr) {
   const int a1 = pl.x_first_fwd ? 0 : 1;   // first forward axis = the strongly pruned one
   const int a2 = 1 - a1;
   const BoxAxis b1 = a1 == 0 ? pl.bx : pl.by, b2 = a2 == 0 ? pl.bx : pl.by;
   const int n1 = axis_len(c->g, a1), n2 = axis_len(c->g, a2);
+  const long long pstride = (long long)b1.K * n2 * Kzp;
+  SWW_REQUIRE((size_t)pstride * nb <= s->buf_elems, "forward batch of %d planes does not fit the pass buffer", nb);
   {
     SWW_PROF(c, a1 == 0 ? "fft.F2 x-forward" : "fft.F2 y-forward");
-#define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp)
+#define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp, nb, rstride, pstride)
     DISPATCH_AX(n1, a1, CALL)
 #undef CALL
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
   }
-  {
+  for (int b = 0; b < nb; ++b) {
     SWW_PROF(c, mode == 2 ? "fft.F3 last-forward+bin" : (mode == 1 ? "fft.F3 last-forward+ylm" : "fft.F3 last-forward+store"));
-#define CALL(NN, AA) launch_f3<NN, AA>(c, s, mode, b2, b1, Kz, Kzp, A)
+    const F3Args& Ax = Ab ? Ab[b] : A;
+    const double2* Psrc = s->P + (long long)b * pstride;
+#define CALL(NN, AA) launch_f3<NN, AA>(c, s, mode, b2, b1, Kz, Kzp, Ax, Psrc)
     DISPATCH_AX(n2, a2, CALL)
 #undef CALL
     c->n_own++;
@@ -1419,4 +1443,46 @@ int sww_sm100_inverse_multi(sww_ctx* c, int nb, const GatherArgs* gas, int box_s
 
 size_t sww_sm100_qstack_bytes(const sww_ctx* c, int nb) {
   return (size_t)nb * c->g.nx * c->g.ny * up8(c->g.Kz) * sizeof(double2);
+}
+
+int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,
+                      const double2* const* G, int n_g, double scale, double* const* out_rows) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  SWW_REQUIRE(nrows >= 1 && nrows <= SWW_MAX_L, "pk_rows: %d rows", nrows);
+  const Geo& g = c->g;
+  AxisPlan pli = make_plan(g, box_axis(g.nx, s->shell_bx[shell]), box_axis(g.ny, s->shell_by[shell]));
+  int Kzi = s->shell_bz[shell] + 1, Kzpi = up8(Kzi);
+  AxisPlan plo = make_plan(g, box_axis(g.nx, g.bx), box_axis(g.ny, g.by));
+  int Kzo = g.Kz, Kzpo = up8(Kzo);
+  const long long qstride = (long long)g.nx * g.ny * Kzpi, rstride = (long long)g.nx * g.ny * Kzpo;
+  SWW_REQUIRE((size_t)rstride * nrows <= s->buf_elems, "pk_rows: pass buffers too small for %d planes", nrows);
+  GatherArgs ga[SWW_MAX_L] = {};
+  for (int b = 0; b < nrows; ++b) {
+    ga[b].src = F[b];
+    ga[b].shell = shell;
+  }
+  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride));
+  ZArgs Z = {};
+  Z.Q = s->Q;
+  Z.Kz_in = Kzi;
+  Z.Kzp_in = Kzpi;
+  Z.R = s->R;
+  Z.Kz_out = Kzo;
+  Z.Kzp_out = Kzpo;
+  Z.wmap = wmap;
+  Z.scale = inv_scale;
+  Z.lm = -1;
+  Z.nb = nrows;
+  Z.q_stride = qstride;
+  Z.r_stride = rstride;
+  SWW_TRY(run_z(c, s, true, true, Z));
+  F3Args Ab[SWW_MAX_L] = {};
+  for (int b = 0; b < nrows; ++b) {
+    for (int q = 0; q < n_g; ++q) Ab[b].G[q] = G[q];
+    Ab[b].n_g = n_g;
+    Ab[b].scale = scale;
+    Ab[b].out_row = out_rows[b];
+  }
+  return run_forward_cols(c, s, plo, Kzo, Kzpo, 2, Ab[0], nrows, rstride, Ab);
 }

@@ -158,11 +158,13 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
     SWW_TRY(sww_sm100_forward_box(c, b.WS, nullptr, -1, 2, A));
     c->n_fft++;
     // Fisher rows: I1 -> I2 -> Z(c2r * nW * r2c) -> F2 -> F3(bin); nothing but the row leaves the chip
-    for (int alpha = 0; alpha < n_b; ++alpha) {
-      int l_i = alpha / n_k, ka = alpha % n_k;
-      SWW_TRY(sww_sm100_pk_row(c, b.FC[l_i], ka, c->d_nW, 1.0 / N, (const double2* const*)b.G, n_l,
-                               0.5 / (N * c->v_cell), F + (size_t)alpha * n_b));
-      c->n_fft += 2;
+    // the n_l rows of one k bin share the shell box and the weight map: one batched chain per bin
+    for (int ka = 0; ka < n_k; ++ka) {
+      double* rows[SWW_MAX_L];
+      for (int l_i = 0; l_i < n_l; ++l_i) rows[l_i] = F + (size_t)(l_i * n_k + ka) * n_b;
+      SWW_TRY(sww_sm100_pk_rows(c, n_l, (const double2* const*)b.FC, ka, c->d_nW, 1.0 / N, (const double2* const*)b.G, n_l,
+                                0.5 / (N * c->v_cell), rows));
+      c->n_fft += 2 * n_l;
     }
     SWW_TRY(k_symmetrise(c, F, n_b));
     return 0;

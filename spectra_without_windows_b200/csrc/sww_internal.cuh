@@ -174,6 +174,8 @@ struct GatherArgs {
   int n_terms;
   int lm;
   double coef;
+  const double2* src;   // n_terms == 0: spectrum [nx][ny][nzh] ...
+  int shell;            // ... kept only inside this shell (< 0: whole box)
 };
 #define SWW_MAX_ZBATCH 10
 struct GatherBatch {
@@ -187,6 +189,9 @@ int sww_sm100_inverse_box(sww_ctx* c, const double2* src, int filter_shell, int 
                           double scale, int accumulate, double* real_out);
 int sww_sm100_pk_row(sww_ctx* c, const double2* F, int shell, const double* wmap, double inv_scale,
                      const double2* const* G, int n_g, double scale, double* out_row);
+// the same for nrows spectra sharing one shell (the multipoles of one k bin): the weight map is read once
+int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,
+                      const double2* const* G, int n_g, double scale, double* const* out_rows);
 
 // ---- kernels.cu (launch wrappers)
 int k_build_binmap(sww_ctx* c);
