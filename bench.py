@@ -472,10 +472,17 @@ def main():
                 traffic = tj["dram_bytes_per_launch"]
             except Exception:
                 pass
-            roof.update({"kernel": "pass_zw_kernel<H,INV,FWD> (fused z pass: c2r * nW * r2c of the %d Fisher rows of one k bin), avg over %d launches of one realisation, CUDA events on the launching stream" % (rows_per_launch, prof[zkey]["launches"]),
-                         "achieved": bytes_launch / dur / 1e9, "frac": bytes_launch / dur / 1e9 / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": dur * 1e3, "rows_per_launch": rows_per_launch,
-                         "share_of_step": prof[zkey]["ms"] / (ms / args.steps)})
+            roof["kernel"] = ("whole realisation step = %d fused 5-pass chains (I1,I2,Z,F2,F3) + 2M+1 forward chains; BASELINE.md section 3 "
+                              "defines the metric's %% of HBM roofline on this unit" % prof[zkey]["launches"])
+            roof["traffic"] = traffic
+            roof["dominant_kernel"] = {
+                "name": "pass_zw_kernel<H,INV,FWD> (fused z pass: c2r * nW * r2c of the %d Fisher rows of one k bin)" % rows_per_launch,
+                "launches_per_realisation": prof[zkey]["launches"], "avg_launch_ms": dur * 1e3,
+                "share_of_step": prof[zkey]["ms"] / (ms / args.steps),
+                "algorithmic_bytes_per_launch": bytes_launch, "achieved_gbs": bytes_launch / dur / 1e9,
+                "frac_of_hbm_peak": bytes_launch / dur / 1e9 / peak, "dram_traffic_bytes_per_launch_ncu": traffic,
+                "note": "co-limited by the FP64 pipe (64 DFMA/clk/SM): two half-length complex FFTs per row; see profiles/ for the ncu capture",
+                "timing": "CUDA events on the launching stream around every launch of one extra realisation after the timed region"}
         line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
