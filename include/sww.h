@@ -108,6 +108,13 @@ int sww_get_binmap(sww_ctx* c, sww_devptr out);
 int sww_paint(sww_ctx* c, sww_devptr pos, sww_devptr w, uint64_t n, const double box_center[3],
               int scheme, double scale, sww_devptr out);
 
+/* ---- Gaussian random field with numpy's legacy stream (pk/compute_pk_randoms.py:139-140) ---- */
+/* out[i] = sigma[i] * g_i, i < n, where g is the sequence np.random.seed(seed); np.random.normal(size=n)
+ * (MT19937 + polar Box-Muller with the cached second variate).  Uniforms and accept/reject decisions
+ * are bit-exact; the Gaussian values agree with numpy's to <= 2 ulp.  Synchronous on `stream` only: the
+ * generator uses one SM, so on a side stream it overlaps with the pipelines of the context stream. */
+int sww_grf_legacy(sww_ctx* c, uint32_t seed, sww_devptr sigma, sww_devptr out, uint64_t n, sww_stream stream /* 0: context stream */);
+
 /* ---- P_l(k) pipelines ---- */
 /* One Gaussian realisation `a` (double[N], device) -> q-bar_alpha [n_b] and the symmetrised
  * F_ab [n_b*n_b] (device, double).  Replaces pk/compute_pk_randoms.py:206-281. */

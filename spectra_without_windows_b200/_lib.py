@@ -47,6 +47,7 @@ SIGNATURES = {
     "sww_apply_c_alpha_single": [ctxp, u64, u64, f64, C.c_int, C.c_int, C.c_int, u64],
     "sww_get_binmap": [ctxp, u64],
     "sww_paint": [ctxp, u64, u64, u64, pd, C.c_int, f64, u64],
+    "sww_grf_legacy": [ctxp, C.c_uint32, u64, u64, u64, u64],
     "sww_pk_fisher_realisation": [ctxp, u64, u64, u64],
     "sww_pk_data_q": [ctxp, u64, u64],
     "sww_bk_set_triangles": [ctxp, C.POINTER(i32), i32],

@@ -1,0 +1,231 @@
+// Device-side reproduction of numpy's legacy Gaussian stream
+//     np.random.seed(s); np.random.normal(loc=0, scale=sigma, size=N)        (pk/compute_pk_randoms.py:139-140)
+// = MT19937 (init_genrand seeding) -> 53-bit doubles from word pairs -> polar Box-Muller with rejection,
+// second variate cached.  The host draws 5.4 s per 512^3 field on one core (SURVEY.md finding 5); this
+// removes the host from the Monte-Carlo loop.
+//
+//   * mt_words_kernel: ONE CTA walks the recurrence (it is inherently sequential in blocks of 624
+//     words, but 227 words of a block are independent: three sub-steps per block) and streams the
+//     tempered words to global memory;
+//   * polar attempts are aligned to groups of 4 words whatever their outcome, so acceptance is
+//     evaluated in parallel, ranked with a prefix sum, and accepted pairs are written in stream order
+//     [f*x2, f*x1] exactly as legacy_gauss caches them.
+// The uniform stream and the accept/reject decisions are bit-exact; the Gaussian values agree with
+// glibc's to the last bit or two (CUDA's log/sqrt are IEEE-accurate to <= 1 ulp).
+#include "sww_internal.cuh"
+
+#define MT_N 624
+#define MT_M 397
+
+__device__ __forceinline__ unsigned mt_mix(unsigned a, unsigned b, unsigned m) {
+  unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ unsigned mt_temper(unsigned y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+
+// state: 624 words in global memory (updated in place); writes nblocks*624 tempered words
+__global__ void __launch_bounds__(256) mt_words_kernel(unsigned* __restrict__ state, unsigned* __restrict__ out, long long nblocks) {
+  __shared__ unsigned mt[MT_N];
+  const int t = threadIdx.x;
+  for (int i = t; i < MT_N; i += 256) mt[i] = state[i];
+  __syncthreads();
+  for (long long b = 0; b < nblocks; ++b) {
+    unsigned v = 0;
+    // words 0..226: depend on old words only
+    if (t < 227) v = mt_mix(mt[t], mt[t + 1], mt[t + MT_M]);
+    __syncthreads();
+    if (t < 227) mt[t] = v;
+    __syncthreads();
+    // words 227..453: mt[k+397-624] = mt[k-227] is new
+    if (t < 227) v = mt_mix(mt[t + 227], mt[t + 228], mt[t]);
+    __syncthreads();
+    if (t < 227) mt[t + 227] = v;
+    __syncthreads();
+    // words 454..623
+    if (t < 170) {
+      int k = t + 454;
+      v = mt_mix(mt[k], mt[(k + 1) % MT_N], mt[k - 227]);
+    }
+    __syncthreads();
+    if (t < 170) mt[t + 454] = v;
+    __syncthreads();
+    unsigned* o = out + b * MT_N;
+    for (int i = t; i < MT_N; i += 256) o[i] = mt_temper(mt[i]);
+  }
+  __syncthreads();
+  for (int i = t; i < MT_N; i += 256) state[i] = mt[i];
+}
+
+__device__ __forceinline__ bool polar_attempt(const unsigned* __restrict__ w, long long i, double& x1, double& x2, double& r2) {
+  const uint4 q = *reinterpret_cast<const uint4*>(w + 4 * i);
+  const double d1 = ((double)(q.x >> 5) * 67108864.0 + (double)(q.y >> 6)) / 9007199254740992.0;
+  const double d2 = ((double)(q.z >> 5) * 67108864.0 + (double)(q.w >> 6)) / 9007199254740992.0;
+  x1 = __dsub_rn(__dmul_rn(2.0, d1), 1.0);
+  x2 = __dsub_rn(__dmul_rn(2.0, d2), 1.0);
+  r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+  return !(r2 >= 1.0 || r2 == 0.0);
+}
+
+#define PA_BLOCK 1024
+// pass 1: accepted attempts per block of 1024 attempts
+__global__ void __launch_bounds__(PA_BLOCK) polar_count_kernel(const unsigned* __restrict__ w, long long nattempts,
+                                                                unsigned* __restrict__ block_counts) {
+  __shared__ unsigned wc[PA_BLOCK / 32];
+  const long long i = (long long)blockIdx.x * PA_BLOCK + threadIdx.x;
+  double x1, x2, r2;
+  bool ok = (i < nattempts) && polar_attempt(w, i, x1, x2, r2);
+  unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned s = 0;
+    for (int k = 0; k < PA_BLOCK / 32; ++k) s += wc[k];
+    block_counts[blockIdx.x] = s;
+  }
+}
+
+// pass 2: exclusive scan of the block counts (single CTA), total appended at [nblocks]
+// offsets[nblocks] = accepted pairs of this chunk; *running = pairs emitted by earlier chunks (read by the emit
+// pass through offsets[nblocks+1], then advanced)
+__global__ void __launch_bounds__(1024) scan_counts_kernel(unsigned* __restrict__ counts, long long* __restrict__ offsets, int nblocks,
+                                                            long long* __restrict__ running) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (nblocks + 1023) / 1024;
+  long long s = 0;
+  for (int k = 0; k < per; ++k) {
+    int i = t * per + k;
+    if (i < nblocks) s += counts[i];
+  }
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    long long run = 0;
+    for (int k = 0; k < 1024; ++k) {
+      long long v = part[k];
+      part[k] = run;
+      run += v;
+    }
+    offsets[nblocks] = run;
+    offsets[nblocks + 1] = *running;
+    *running += run;
+  }
+  __syncthreads();
+  long long run = part[t];
+  for (int k = 0; k < per; ++k) {
+    int i = t * per + k;
+    if (i < nblocks) {
+      offsets[i] = run;
+      run += counts[i];
+    }
+  }
+}
+
+// pass 3: accepted attempt with stream rank j writes out[2j] = sigma*f*x2, out[2j+1] = sigma*f*x1
+__global__ void __launch_bounds__(PA_BLOCK) polar_emit_kernel(const unsigned* __restrict__ w, long long nattempts,
+                                                               const long long* __restrict__ offsets, int nblocks,
+                                                               const double* __restrict__ sigma, double* __restrict__ out,
+                                                               long long nout) {
+  __shared__ unsigned wc[PA_BLOCK / 32];
+  const long long i = (long long)blockIdx.x * PA_BLOCK + threadIdx.x;
+  double x1 = 0, x2 = 0, r2 = 1;
+  bool ok = (i < nattempts) && polar_attempt(w, i, x1, x2, r2);
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wc[warp] = __popc(m);
+  __syncthreads();
+  unsigned before = 0;
+  for (int k = 0; k < warp; ++k) before += wc[k];
+  if (!ok) return;
+  const long long j = offsets[nblocks + 1] + offsets[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
+  const double f = sqrt(-2.0 * log(r2) / r2);
+  const long long o = 2 * j;
+  if (o < nout) out[o] = 0.0 + sigma[o] * (f * x2);
+  if (o + 1 < nout) out[o + 1] = 0.0 + sigma[o + 1] * (f * x1);
+}
+
+struct RngScratch {
+  unsigned* state = nullptr;
+  unsigned* words = nullptr;
+  unsigned* counts = nullptr;
+  long long* offsets = nullptr;
+  long long* running = nullptr;
+  long long cap_attempts = 0;
+};
+static RngScratch g_rng;
+
+static int rng_reserve(long long attempts) {
+  if (attempts <= g_rng.cap_attempts) return 0;
+  if (g_rng.words) {
+    cudaFree(g_rng.words);
+    cudaFree(g_rng.counts);
+    cudaFree(g_rng.offsets);
+  }
+  if (!g_rng.state) {
+    SWW_CUDA(cudaMalloc(&g_rng.state, MT_N * sizeof(unsigned)));
+    SWW_CUDA(cudaMalloc(&g_rng.running, sizeof(long long)));
+  }
+  long long nb = (attempts + PA_BLOCK - 1) / PA_BLOCK;
+  SWW_CUDA(cudaMalloc(&g_rng.words, (size_t)(attempts * 4 + MT_N) * sizeof(unsigned)));
+  SWW_CUDA(cudaMalloc(&g_rng.counts, (size_t)(nb + 1) * sizeof(unsigned)));
+  SWW_CUDA(cudaMalloc(&g_rng.offsets, (size_t)(nb + 2) * sizeof(long long)));
+  g_rng.cap_attempts = attempts;
+  return 0;
+}
+
+// out[i] = sigma[i] * gauss_i, i < n, with the numpy legacy stream of `seed`
+extern "C" int sww_grf_legacy(sww_ctx* c, uint32_t seed, sww_devptr sigma_, sww_devptr out_, uint64_t n, sww_stream stream_) {
+  SWW_REQUIRE(c && sigma_ && out_ && n > 0, "null argument");
+  // runs on `stream_` (0: the context stream) and returns when the field is complete on that stream; the
+  // generator occupies a single SM, so a side stream overlaps it with the Fisher kernels of another field
+  struct StreamSwap {
+    sww_ctx* c;
+    cudaStream_t old;
+    StreamSwap(sww_ctx* c_, cudaStream_t s) : c(c_), old(c_->stream) { if (s) c->stream = s; }
+    ~StreamSwap() { c->stream = old; }
+  } swap_(c, (cudaStream_t)stream_);
+  SWW_PROF(c, "rng.legacy gaussian field");
+  const double* sigma = (const double*)sigma_;
+  double* out = (double*)out_;
+  // chunks of 624*2^14 words = 2.56 M attempts (a whole number of MT blocks)
+  const long long blocks_per_chunk = 4LL << 14;                 // x624 words, divisible by 4 words per attempt
+  const long long att_per_chunk = blocks_per_chunk * MT_N / 4;
+  SWW_TRY(rng_reserve(att_per_chunk));
+  // init_genrand seeding (numpy mt19937_seed)
+  unsigned h[MT_N];
+  unsigned s = seed;
+  for (int pos = 0; pos < MT_N; ++pos) {
+    h[pos] = s;
+    s = 1812433253u * (s ^ (s >> 30)) + (unsigned)pos + 1u;
+  }
+  SWW_CUDA(cudaMemcpyAsync(g_rng.state, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));   // pageable source: staged before return
+  SWW_CUDA(cudaMemsetAsync(g_rng.running, 0, sizeof(long long), c->stream));
+  const long long need_pairs = ((long long)n + 1) / 2;
+  const int nb = (int)((att_per_chunk + PA_BLOCK - 1) / PA_BLOCK);
+  // accepted pairs per chunk ~ Binomial(A, pi/4): plan the chunk count 8 sigma on the safe side, no read-back per chunk
+  const double p = 0.78539816339744831, sd = sqrt((double)att_per_chunk * p * (1.0 - p));
+  long long chunks = (long long)ceil((double)need_pairs / ((double)att_per_chunk * p - 8.0 * sd));
+  long long done_pairs = 0;
+  while (done_pairs < need_pairs) {
+    for (long long k = 0; k < chunks; ++k) {
+      mt_words_kernel<<<1, 256, 0, c->stream>>>(g_rng.state, g_rng.words, blocks_per_chunk);
+      polar_count_kernel<<<nb, PA_BLOCK, 0, c->stream>>>(g_rng.words, att_per_chunk, g_rng.counts);
+      scan_counts_kernel<<<1, 1024, 0, c->stream>>>(g_rng.counts, g_rng.offsets, nb, g_rng.running);
+      polar_emit_kernel<<<nb, PA_BLOCK, 0, c->stream>>>(g_rng.words, att_per_chunk, g_rng.offsets, nb, sigma, out, (long long)n);
+      c->n_own += 4;
+    }
+    SWW_CUDA(cudaGetLastError());
+    // one read-back at the end guards the (astronomically unlikely) shortfall
+    SWW_CUDA(cudaMemcpyAsync(&done_pairs, g_rng.running, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    SWW_CUDA(cudaStreamSynchronize(c->stream));
+    chunks = 1;
+  }
+  return 0;
+}

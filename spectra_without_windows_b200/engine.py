@@ -227,6 +227,46 @@ class Context:
         self.set_fields(nbar, nbar.copy(), nbar_A, shot_fac, P_fkp)
         return nbar_A
 
+    # -- Gaussian fields
+    def grf_legacy(self, seed, sigma, out=None, stream=None):
+        """Device-side `np.random.seed(seed); np.random.normal(0, sigma, sigma.shape)` (numpy legacy stream).
+        With `stream` (a torch stream) the generator runs there and overlaps with work on the context stream."""
+        sigma = self.dev(sigma)
+        if out is None:
+            out = self.empty(tuple(sigma.shape))
+        _lib.check(self.lib.sww_grf_legacy(self._h, int(seed) & 0xFFFFFFFF, sigma.data_ptr(), out.data_ptr(), int(sigma.numel()),
+                                           0 if stream is None else stream.cuda_stream))
+        return out
+
+    def field_pipeline(self, seeds, sigma):
+        """Iterate device-generated legacy fields, generating field i+1 on a side stream while the caller's
+        work on field i runs on the context stream.  Yields (seed, field tensor)."""
+        t = torch()
+        sigma = self.dev(sigma)
+        seeds = list(seeds)
+        if not seeds:
+            return
+        side = t.cuda.Stream(device=self.device)
+        bufs = [self.empty(tuple(sigma.shape)) for _ in range(2)]
+        main = self.stream
+        side.wait_stream(main)
+        self.grf_legacy(seeds[0], sigma, bufs[0], stream=side)
+        done = t.cuda.Event()
+        done.record(side)
+        used = []                       # used[i]: the caller's work on field i has been enqueued up to here
+        for i, s in enumerate(seeds):
+            main.wait_event(done)
+            yield s, bufs[i % 2]
+            ev = t.cuda.Event()
+            ev.record(main)
+            used.append(ev)
+            if i + 1 < len(seeds):
+                if i >= 1:
+                    side.wait_event(used[i - 1])    # buffer (i+1)%2 was last read by the work on field i-1
+                self.grf_legacy(seeds[i + 1], sigma, bufs[(i + 1) % 2], stream=side)   # overlaps the work on field i
+                done = t.cuda.Event()
+                done.record(side)
+
     # -- P_l(k)
     def pk_fisher(self, a, fish_out=None, qbar_out=None):
         """One realisation -> (F [n_b,n_b] symmetrised, qbar [n_b]) on the device."""

@@ -1,0 +1,39 @@
+"""Device-side numpy-legacy Gaussian stream vs numpy itself."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_legacy_gaussian_stream_matches_numpy(world):
+    from spectra_without_windows_b200 import engine
+    w = world("toyC")
+    mesh = engine.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    ctx = engine.get_context(mesh, 0, ("ops", "pk_fisher", "pk_data"))
+    rng = np.random.default_rng(0)
+    for seed, shape in [(1, (20, 18, 15)), (2, (7,)), (12345, (64, 64, 128)), (4294967295, (33, 1, 5)), (77, (200, 160, 170))]:
+        sigma = rng.random(shape) + 0.25
+        np.random.seed(seed)
+        ref = np.random.normal(loc=0.0, scale=sigma, size=sigma.shape)
+        got = ctx.grf_legacy(seed, sigma).cpu().numpy()
+        assert got.shape == ref.shape
+        # identical stream positions (same accept/reject decisions): values agree to the last bits
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-14, seed
+        assert np.mean(got == ref) > 0.5
+
+
+def test_fisher_from_device_field_matches_host_field(world):
+    """A Fisher matrix from the device-generated field agrees with the host-RNG one far below 1e-9."""
+    from spectra_without_windows_b200 import engine
+    w = world("toyD")
+    mesh = engine.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    ctx = engine.Context(mesh, 0, ("pk_fisher",))
+    nbar_A = ctx.set_fields_from_randoms_density(w.nbar_r, w.alpha, w.shot_fac)
+    sig = np.sqrt(nbar_A)
+    np.random.seed(3)
+    a_host = np.random.normal(loc=0.0, scale=sig, size=sig.shape)
+    F0, q0 = ctx.pk_fisher(a_host)
+    F1, q1 = ctx.pk_fisher(ctx.grf_legacy(3, sig))
+    e = float((F1 - F0).abs().max() / F0.abs().max())
+    assert e < 1e-12
+    ctx.close()
