@@ -82,6 +82,14 @@ int sww_set_fields(sww_ctx* c, sww_devptr nbar, sww_devptr nbar_weight, sww_devp
 int sww_ylm_cache_bytes(sww_ctx* c, uint64_t* bytes);
 int sww_set_ylm_cache(sww_ctx* c, sww_devptr maps);
 
+/* include_pix (the .param boolean, paramfiles/boss_nC.param:64): forward-model the pixel window.  In the
+ * Fisher matrix, q-bar and q_alpha the MAS operators cancel between C^-1 and C_,alpha, so only the
+ * preparation of the maps changes: a -> M a in the C^-1 branch, A^-1 a -> M^-1 A^-1 a in the other, and the
+ * data-only MAS factors are dropped (src/covariances_pk.py:155-163,371-372,386-389,396-397). */
+int sww_set_include_pix(sww_ctx* c, int include_pix);
+/* out = IFT[ MAS^power * FT[x] ]  (power = +1 / -1), the building block of the include_pix mirrors */
+int sww_mas_filter(sww_ctx* c, sww_devptr x, int power, sww_devptr out);
+
 /* ---- drop-in operators (mirrors of src/opt_utilities.py and src/covariances_pk.py) ---- */
 /* ft / ift  (src/opt_utilities.py:502-555) in complex128; inverse normalised by 1/N. */
 int sww_fft_c2c(sww_ctx* c, sww_devptr in, sww_devptr out, int inverse);

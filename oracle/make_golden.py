@@ -31,12 +31,12 @@ def parse_txt(path):
     return np.loadtxt(path, comments="#")
 
 
-def run_world(name, fp64=True):
+def run_world(name, fp64=True, include_pix=False, rand_nbar=False):
     w = syn.make_world(name)
     root = tempfile.mkdtemp(prefix="sww_gold_")
     out = {}
     try:
-        p = syn.write_world_files(w, root)
+        p = syn.write_world_files(w, root, include_pix=include_pix, rand_nbar=rand_nbar)
         ou, cp = rh.bind_world(w, fp64=fp64)
         mc, od = root + "/mc/", root + "/out/"
         # ---- pk Fisher realisations (pk/compute_pk_randoms.py), then data (pk/compute_pk_data.py)
@@ -53,7 +53,7 @@ def run_world(name, fp64=True):
         out["pk_txt"] = np.asarray(open(f).read())
         out["pk_p"] = parse_txt(f)
         # ---- function-level q_alpha (the script does not save it): pk/compute_pk_data.py:137-206
-        if fp64:
+        if fp64 and not include_pix and not rand_nbar:
             out.update(function_level(w, ou, cp))
         # ---- bk Fisher pair r=1 (seeds 2,3) then bk data
         cnt = rh.run_script("bk/compute_bk_randoms.py", 1, p)
@@ -119,7 +119,13 @@ def function_level(w, ou, cp):
 def main(argv):
     names = argv[1:] or ["toyA", "toyB", "toyC"]
     os.makedirs(GOLD, exist_ok=True)
-    for n in names:
+    for n in [x for x in names if "+" in x]:
+        # variants: toyA+pix (include_pix = True), toyA+rand (rand_nbar = True)
+        base, var = n.split("+")
+        g = run_world(base, fp64=True, include_pix=(var == "pix"), rand_nbar=(var == "rand"))
+        np.savez_compressed(os.path.join(GOLD, "%s_%s.npz" % (base, var)), **g)
+        print(n, "pk", g["pk_fish_1"].shape, "bk", g["bk_fish_1"].shape)
+    for n in [x for x in names if "+" not in x]:
         g = run_world(n, fp64=True)
         c = run_world(n, fp64=False)
         for k in ("pk_fish_1", "pk_qbar_1", "pk_p", "bk_fish_1", "bk_p"):

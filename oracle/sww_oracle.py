@@ -124,17 +124,23 @@ def compute_filters(kmin, kmax, dk):
 
 
 # ----------------------------------------------------------------------------- operators
-def applyCinv_fkp(x, nbar, v_cell, shot_fac, P_fkp=1e4):
-    """FKP C^-1 (src/covariances_pk.py:126-164, include_pix=False branch), complex128 buffer."""
+def applyCinv_fkp(x, nbar, v_cell, shot_fac, P_fkp=1e4, MAS=None):
+    """FKP C^-1 (src/covariances_pk.py:126-164), complex128 buffer.  MAS given = include_pix=True
+    branch (:155-156, :161-162)."""
     w = nbar * (nbar * P_fkp + shot_fac)
     out = np.zeros(x.shape, dtype=np.complex128)
+    tmp = ift(ft(x) * MAS) if MAS is not None else x
     f = nbar > 0
-    out[f] = x[f] / w[f]
+    out[f] = tmp[f] / w[f]
+    if MAS is not None:
+        return ift(MAS * ft(out)) * v_cell
     return out * v_cell
 
 
-def applyN(x, nbar, v_cell, shot_fac):
-    """src/covariances_pk.py:97-124, include_pix=False branch."""
+def applyN(x, nbar, v_cell, shot_fac, MAS=None):
+    """src/covariances_pk.py:97-124 (MAS given = include_pix=True branch, :122)."""
+    if MAS is not None:
+        return shot_fac * ift(1.0 / MAS * ft(nbar * ift(ft(x) / MAS))) / v_cell
     return shot_fac * nbar * x / v_cell
 
 
@@ -142,7 +148,9 @@ class Setup:
     """Everything the four scripts build between 'LOAD DATA' and the estimator proper
     (pk/compute_pk_randoms.py:135-202; identical blocks in the other three scripts)."""
 
-    def __init__(self, box, grid, box_center, nbar_r, alpha, shot_fac, kmin, kmax, dk, lmax):
+    def __init__(self, box, grid, box_center, nbar_r, alpha, shot_fac, kmin, kmax, dk, lmax, include_pix=False,
+                 nbar_override=None):
+        self.include_pix = include_pix
         self.box = np.asarray(box, float)
         self.grid = np.asarray(grid, int)
         self.v_cell = 1.0 * self.box.prod() / (1.0 * self.grid.prod())
@@ -156,11 +164,14 @@ class Setup:
         self.nbar_A = nbar_A
         self.nbar = nbar_r * alpha            # load_nbar(config, ., alpha_ran), opt_utilities.py:180
         self.nbar_weight = self.nbar.copy()
+        if nbar_override is not None:         # rand_nbar=True: n from painted randoms (pk/compute_pk_randoms.py:174-176)
+            self.nbar = nbar_override.copy()
         k_grids, r_grids = load_coord_grids(box, grid, box_center)
         self.k_norm = np.sqrt(np.sum(k_grids ** 2.0, axis=0))
         self.k_hat = k_grids / (1e-12 + self.k_norm)
         self.r_hat = r_grids / (1e-12 + np.sqrt(np.sum(r_grids ** 2.0, axis=0)))
         self.MAS = load_MAS(box, grid)
+        self.pix = self.MAS if include_pix else None      # passed to the operators as their MAS argument
         self.Y = compute_spherical_harmonic_functions(lmax)
         self.filt = compute_filters(kmin, kmax, dk)
 
@@ -176,12 +187,16 @@ class Setup:
     def applyC_alpha(self, x, data=False):
         """All n_b derivative maps C_,alpha x (src/covariances_pk.py:329-401, include_pix=False)."""
         out = []
-        tmp = x * self.nbar
+        pix = self.include_pix
+        tmp = ift(ft(x) / self.MAS) * self.nbar if pix else x * self.nbar          # :371-374
         for l_i in range(self.n_l):
-            f = self.ylm_sum(tmp, l_i, 2 if data else 0)
+            f = self.ylm_sum(tmp, l_i, 2 if (data and not pix) else 0)             # :386-389
             for a in range(self.n_k):
                 t2 = 4.0 * np.pi / (4.0 * l_i + 1.0) * self.filt(a, self.k_norm) * f
-                out.append(self.nbar * ift(t2) / self.v_cell)
+                if pix:
+                    out.append(ift(ft(self.nbar * ift(t2)) / self.MAS) / self.v_cell)  # :396-397
+                else:
+                    out.append(self.nbar * ift(t2) / self.v_cell)
         return out
 
     def grf(self, seed):
@@ -194,15 +209,21 @@ class Setup:
 def pk_fisher_realisation(S: Setup, a):
     """q-bar_alpha [n_b] and symmetrised F_ab [n_b,n_b] of one Gaussian realisation `a`
     (pk/compute_pk_randoms.py:206-281, the non-spilling flow :229-241, :264-274)."""
-    Cinv_a = np.real(applyCinv_fkp(a, S.nbar_weight, S.v_cell, S.shot_fac))
+    Cinv_a = np.real(applyCinv_fkp(a, S.nbar_weight, S.v_cell, S.shot_fac, MAS=S.pix))
     Ainv_a = a / S.nbar_A
-    N_Ainv_a = applyN(Ainv_a, S.nbar, S.v_cell, S.shot_fac)
+    N_Ainv_a = applyN(Ainv_a, S.nbar, S.v_cell, S.shot_fac, MAS=S.pix)
     C_a_Cinv = S.applyC_alpha(Cinv_a)
     C_a_Ainv = S.applyC_alpha(Ainv_a)
     nb = len(C_a_Cinv)
-    U = [applyCinv_fkp(C_a_Cinv[i], S.nbar_weight, S.v_cell, S.shot_fac) for i in range(nb)]
+    U = [applyCinv_fkp(C_a_Cinv[i], S.nbar_weight, S.v_cell, S.shot_fac, MAS=S.pix) for i in range(nb)]
     fish = np.zeros((nb, nb))
     qbar = np.zeros(nb)
+    if S.include_pix:      # complex maps with O(1e-17) imaginary parts: the reference sums complex products (:267-274)
+        V = np.asarray([v.ravel() for v in C_a_Ainv])
+        for i in range(nb):
+            qbar[i] = 0.5 * np.real(np.sum(U[i] * N_Ainv_a))
+            fish[i] = 0.5 * np.real(V @ U[i].ravel())
+        return qbar, 0.5 * (fish + fish.T)
     V = np.asarray([np.real(v).ravel() for v in C_a_Ainv])
     for i in range(nb):
         qbar[i] = 0.5 * np.real(np.sum(U[i] * N_Ainv_a))
@@ -212,7 +233,7 @@ def pk_fisher_realisation(S: Setup, a):
 
 def pk_data_q(S: Setup, diff):
     """q_alpha of a painted data-minus-randoms map (pk/compute_pk_data.py:191-206)."""
-    Cinv_d = applyCinv_fkp(diff, S.nbar_weight, S.v_cell, S.shot_fac)
+    Cinv_d = applyCinv_fkp(diff, S.nbar_weight, S.v_cell, S.shot_fac, MAS=S.pix)
     C_a = S.applyC_alpha(Cinv_d, data=True)
     return np.asarray([np.real(np.sum(Cinv_d * c)) / 2.0 for c in C_a])
 
@@ -277,13 +298,15 @@ def triangle_bins(kmin, kmax, dk, n_k):
 def compute_g_a(S: Setup, a_map, data=False):
     """g_i^l and tilde-g_i^l maps (bk/compute_bk_randoms.py:222-267).  With data=True only g is
     returned and the extra MAS factor of bk/compute_bk_data.py:259-283 is applied."""
-    Cinv = applyCinv_fkp(a_map, S.nbar_weight, S.v_cell, S.shot_fac)
-    nC = S.nbar * Cinv
+    Cinv = applyCinv_fkp(a_map, S.nbar_weight, S.v_cell, S.shot_fac, MAS=S.pix)
+    pix = S.include_pix
+    nC = ift(ft(Cinv) / S.MAS) * S.nbar if pix else S.nbar * Cinv                      # :235-240 / data :267-270
     g, tg = [], []
     if not data:
-        nA = S.nbar * (a_map / S.nbar_A)
+        Ainv = a_map / S.nbar_A
+        nA = ift(ft(Ainv) / S.MAS) * S.nbar if pix else S.nbar * Ainv
     for l_i in range(S.n_l):
-        fC = S.ylm_sum(nC, l_i, 1 if data else 0) * (4.0 * np.pi / (4.0 * l_i + 1.0))
+        fC = S.ylm_sum(nC, l_i, 1 if (data and not pix) else 0) * (4.0 * np.pi / (4.0 * l_i + 1.0))
         g.append([ift(S.filt(i, S.k_norm) * fC) for i in range(S.n_k)])
         if not data:
             fA = S.ylm_sum(nA, l_i) * (4.0 * np.pi / (4.0 * l_i + 1.0))
@@ -293,7 +316,10 @@ def compute_g_a(S: Setup, a_map, data=False):
 
 def _phi1(S, g, a, b, c, l_i):
     """n IFT[Theta_c FT[g_a^0 g_b^l]]/v_cell (bk/compute_bk_randoms.py:278-311)."""
-    return np.real(ift(ft(g[0][a] * g[l_i][b]) * S.filt(c, S.k_norm)) * S.nbar / S.v_cell)
+    gabc = ift(ft(g[0][a] * g[l_i][b]) * S.filt(c, S.k_norm))
+    if S.include_pix:
+        return np.real(ift(ft(gabc * S.nbar) / S.MAS) / S.v_cell)                      # :304-306
+    return np.real(gabc * S.nbar / S.v_cell)
 
 
 def _phi2(S, g, a, b, c, l_i):
@@ -301,7 +327,10 @@ def _phi2(S, g, a, b, c, l_i):
     fg = ft(g[0][a] * g[0][b]) * S.filt(c, S.k_norm)
     out = 0.0
     for Y in S.Y[l_i]:
-        out = out + np.real(ift(Y(*S.k_hat) * fg) * (Y(*S.r_hat) * S.nbar / S.v_cell))
+        if S.include_pix:                                                               # :344-346
+            out = out + np.real(ift(ft(ift(Y(*S.k_hat) * fg) * S.nbar) / S.MAS) / S.v_cell * Y(*S.r_hat))
+        else:
+            out = out + np.real(ift(Y(*S.k_hat) * fg) * (Y(*S.r_hat) * S.nbar / S.v_cell))
     return out * (4.0 * np.pi / (4.0 * l_i + 1.0))
 
 
@@ -360,7 +389,7 @@ def bk_fisher_pair(S: Setup, aA, aB, return_g=False):
             l_i, (a, b, c) = idx // nt, tris[idx % nt]
             tphi[X].append(phi_alpha(S, tg, a, b, c, l_i).ravel())
             p = phi_alpha(S, g, a, b, c, l_i)
-            cphi[X].append(np.real(applyCinv_fkp(p, S.nbar_weight, S.v_cell, S.shot_fac)).ravel())
+            cphi[X].append(np.real(applyCinv_fkp(p, S.nbar_weight, S.v_cell, S.shot_fac, MAS=S.pix)).ravel())
     D = delta_abc(S, tris)
     F = np.zeros((nb, nb))
     TA, TB = np.asarray(tphi["A"]), np.asarray(tphi["B"])

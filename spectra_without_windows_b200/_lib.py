@@ -38,6 +38,8 @@ SIGNATURES = {
     "sww_ylm_cache_bytes": [ctxp, C.POINTER(u64)],
     "sww_set_ylm_cache": [ctxp, u64],
     "sww_set_fields": [ctxp, u64, u64, u64, f64, f64],
+    "sww_set_include_pix": [ctxp, C.c_int],
+    "sww_mas_filter": [ctxp, u64, C.c_int, u64],
     "sww_fft_c2c": [ctxp, u64, u64, C.c_int],
     "sww_fft_r2c": [ctxp, u64, u64],
     "sww_fft_c2r": [ctxp, u64, u64],

@@ -1,8 +1,8 @@
 """Drop-in mirror of the reference's src/covariances_pk.py FKP operators, backed by libsww.so.
 
-Same names, argument order and meaning as the reference; ndarray in -> ndarray out.  Only the
-branch every shipped paramfile uses is implemented on the GPU (`include_pix=False`, FKP weights);
-the other branches raise (SURVEY.md section 8f rows N1/N2 -- not yet built, never a CPU fallback).
+Same names, argument order and meaning as the reference; ndarray in -> ndarray out.  FKP weights, both values of `include_pix`;
+`include_pix=True` is composed from the same kernels plus the k-space MAS filter; ML weights raise
+(SURVEY.md section 8f row N1 -- not yet built, never a CPU fallback).
 """
 from __future__ import annotations
 
@@ -11,9 +11,10 @@ import numpy as np
 from . import engine
 
 
-def _need_no_pix(include_pix):
-    if include_pix:
-        raise Exception("include_pix=True (forward-modelled pixellation) is not implemented on the B200 path yet")
+def _mesh_context(input_map, MAS_mat):
+    """Context whose MAS tables match the caller's mesh (the MAS window only depends on the grid size)."""
+    from .opt_utilities import _fft_ctx
+    return _fft_ctx(np.asarray(input_map).shape)
 
 
 def _info(k_grids, r_grids):
@@ -40,20 +41,29 @@ def _any_context(input_map):
 
 def applyN(input_map, nbar, MAS_mat, v_cell, shot_fac, include_pix=True):
     """src/covariances_pk.py:97-124 (include_pix=False branch): shot_fac*nbar*input_map/v_cell."""
-    _need_no_pix(include_pix)
     ctx = _any_context(input_map)
-    return ctx.apply_n(np.real(input_map), nbar, float(v_cell), float(shot_fac)).cpu().numpy()
+    x = np.real(input_map)
+    if include_pix:   # shot*ift(1/MAS*ft(nbar*ift(ft(x)/MAS)))/v_cell   (:122)
+        y = ctx.apply_n(ctx.mas_filter(x, -1), nbar, float(v_cell), float(shot_fac))
+        return ctx.mas_filter(y, -1).cpu().numpy()
+    return ctx.apply_n(x, nbar, float(v_cell), float(shot_fac)).cpu().numpy()
 
 
 def applyCinv_fkp(input_map, nbar, MAS_mat, v_cell, shot_fac, P_fkp=1e4, include_pix=True):
     """src/covariances_pk.py:126-164 (include_pix=False branch).  Returns a complex128 map like the
     FP64-promoted reference (the reference's buffer is complex64, :154)."""
-    _need_no_pix(include_pix)
     ctx = _any_context(input_map)
     x = np.asarray(input_map)
-    out = ctx.apply_cinv_fkp(np.real(x), nbar, float(v_cell), float(shot_fac), float(P_fkp)).cpu().numpy().astype(np.complex128)
+
+    def one(part):
+        if include_pix:   # ift(MAS*ft(ratio))*v_cell with ratio from ift(ft(x)*MAS)   (:155-162)
+            t = ctx.apply_cinv_fkp(ctx.mas_filter(part, +1), nbar, float(v_cell), float(shot_fac), float(P_fkp))
+            return ctx.mas_filter(t, +1).cpu().numpy()
+        return ctx.apply_cinv_fkp(part, nbar, float(v_cell), float(shot_fac), float(P_fkp)).cpu().numpy()
+
+    out = one(np.real(x)).astype(np.complex128)
     if np.iscomplexobj(x):
-        out = out + 1j * ctx.apply_cinv_fkp(np.imag(x), nbar, float(v_cell), float(shot_fac), float(P_fkp)).cpu().numpy()
+        out = out + 1j * one(np.imag(x))
     return out
 
 
@@ -61,22 +71,28 @@ def applyC_alpha_single(input_map, nbar, MAS_mat, Y_lms, k_grids, r_grids, v_cel
                         include_pix=True, data=False):
     """src/covariances_pk.py:404-466 (include_pix=False): one derivative map C_,alpha x for multipole
     index i and k-bin a."""
-    _need_no_pix(include_pix)
     lmax = 2 * (len(Y_lms) - 1)
     ctx = _context(k_grids, r_grids, k_filters, lmax)
+    if include_pix:   # ift(ft(nbar*ift(tmp2))/MAS)/v_cell with tmp_map = ift(ft(x)/MAS)*nbar, no MAS^2   (:444-464)
+        y = ctx.apply_c_alpha_single(ctx.mas_filter(np.real(input_map), -1), nbar, float(v_cell), int(i), int(a), False)
+        return ctx.mas_filter(y, -1).cpu().numpy().astype(np.complex128)
     return ctx.apply_c_alpha_single(np.real(input_map), nbar, float(v_cell), int(i), int(a), data).cpu().numpy().astype(np.complex128)
 
 
 def applyC_alpha(input_map, nbar, MAS_mat, Y_lms, k_grids, r_grids, v_cell, k_filters, k_norm, n_k, lmax,
                  include_pix=True, data=False):
     """src/covariances_pk.py:329-401 (include_pix=False): list of the n_b derivative maps."""
-    _need_no_pix(include_pix)
     ctx = _context(k_grids, r_grids, k_filters, lmax)
     x, n = ctx.dev(np.real(input_map)), ctx.dev(nbar)
+    if include_pix:
+        x = ctx.mas_filter(x, -1)
     out = []
     for l_i in range(lmax // 2 + 1):
         for a in range(n_k):
-            out.append(ctx.apply_c_alpha_single(x, n, float(v_cell), l_i, a, data).cpu().numpy().astype(np.complex128))
+            y = ctx.apply_c_alpha_single(x, n, float(v_cell), l_i, a, data and not include_pix)
+            if include_pix:
+                y = ctx.mas_filter(y, -1)
+            out.append(y.cpu().numpy().astype(np.complex128))
     return out
 
 

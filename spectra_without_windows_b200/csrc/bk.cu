@@ -21,7 +21,6 @@
 
 #define SMS 148
 
-int k_prep_pk(sww_ctx* c, const double* a, double* nCa, double* nAa, double* WS);
 int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
                              double2* spec, double2* const* out);
 size_t sww_sm100_qstack_bytes(const sww_ctx* c, int nb);
@@ -373,11 +372,24 @@ static int gmaps(sww_ctx* c, BkBufs& b, const double* a, int data, double* g_out
   const size_t N = c->g.N;
   const double invN = 1.0 / (double)c->g.N;
   if (data) {
-    // f = n C^-1 d, spectra carry one MAS factor (bk/compute_bk_data.py:259-276)
-    SWW_TRY(k_cinv_fkp(c, a, c->nbar_w, c->v_cell, c->shot, c->P_fkp, b.nCa, c->nbar));
-    SWW_TRY(sww_ylm_project_internal(c, b.nCa, 1, true, true, b.tmp, b.X, b.FC));
+    // f = n C^-1 d, spectra carry one MAS factor (bk/compute_bk_data.py:259-276); include_pix: f = n v D_w M d
+    // and no MAS factor (:267-268)
+    const double* d_in = a;
+    if (c->include_pix) {
+      SWW_TRY(sww_mas_filter_internal(c, a, +1, b.X, b.tmp));
+      d_in = b.tmp;
+    }
+    SWW_TRY(k_cinv_fkp(c, d_in, c->nbar_w, c->v_cell, c->shot, c->P_fkp, b.nCa, c->nbar));
+    SWW_TRY(sww_ylm_project_internal(c, b.nCa, c->include_pix ? 0 : 1, true, true, b.tmp, b.X, b.FC));
   } else {
-    SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS));
+    if (c->include_pix) {
+      SWW_TRY(sww_mas_filter_internal(c, a, +1, b.X, b.nCa));
+      SWW_TRY(k_div(c, a, c->nbar_A, b.nAa));
+      SWW_TRY(sww_mas_filter_internal(c, b.nAa, -1, b.X, b.tmp));
+      SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS, b.nCa, b.tmp));
+    } else {
+      SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS));
+    }
     SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
     SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
   }
@@ -436,6 +448,55 @@ static int inverse_weighted(sww_ctx* c, BkBufs& b, int box_shell, const double* 
   SWW_TRY(sww_c2r(c, b.X, b.u));
   acc_real_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, b.u, wmap, lm, scale, first, out);
   return launch_ok(c);
+}
+
+static int assemble(sww_ctx* c, BkBufs& b, const double2* p0, int s0, const double2* p1, int s1, const double2* p2,
+                    int s2, int lm, double coef);
+
+// include_pix = True: the MAS operators do not cancel for l > 0 because Y_lm(r^) multiplies OUTSIDE M^-1
+// (bk/compute_bk_randoms.py:304-306, :344-346):
+//     phi = 1/v [ M^-1(n psi_1) + 4pi/(2l+1) sum_m Y_lm(r^) M^-1(n psi_m) ],   C^-1 phi = v M D_w M phi.
+// Every term costs one pruned inverse plus one full transform pair; rarely-used branch, not tuned.
+static int build_phi_pix(sww_ctx* c, BkBufs& b, const PairTable& P, const double2* spectra, int alpha, bool apply_cinv,
+                         double* out) {
+  const int nt = c->n_tri;
+  const int l_i = alpha / nt, t = alpha % nt;
+  const int a = c->tris[3 * t], bb = c->tris[3 * t + 1], cc = c->tris[3 * t + 2];
+  const size_t be = box_elems(c);
+  const double invN = 1.0 / (double)c->g.N;
+  auto spec = [&](int i, int j, int l) { return spectra + (size_t)P.get(i, j, l) * be; };
+  // term: X assembled -> u = n IFT[X] -> M^-1 u -> out (+)= scale * Y_lm(r^) * (M^-1 u)
+  auto term = [&](int lm, int first) -> int {
+    if (c->fft_backend == 1) {
+      SWW_TRY(sww_sm100_inverse_box(c, b.X, -1, -1, c->nbar, -1, invN, 0, b.u));
+      c->n_fft++;
+    } else {
+      SWW_TRY(sww_c2r(c, b.X, b.tmp));
+      SWW_TRY(k_mul(c, b.tmp, c->nbar, invN, b.u));
+    }
+    SWW_TRY(sww_mas_filter_internal(c, b.u, -1, b.X, b.u));
+    acc_real_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, b.u, nullptr, lm, 1.0 / c->v_cell, first, out);
+    return launch_ok(c);
+  };
+  if (l_i == 0) {
+    SWW_TRY(assemble(c, b, spec(a, bb, 0), cc, spec(a, cc, 0), bb, spec(bb, cc, 0), a, -1, 1.0));
+    SWW_TRY(term(-1, 1));
+  } else {
+    SWW_TRY(assemble(c, b, spec(a, cc, l_i), bb, spec(bb, cc, l_i), a, nullptr, 0, -1, 1.0));
+    SWW_TRY(term(-1, 1));
+    int lm0 = 0;
+    for (int l = 0; l < l_i; ++l) lm0 += 4 * l + 1;
+    for (int m = 0; m < 4 * l_i + 1; ++m) {
+      SWW_TRY(assemble(c, b, spec(a, bb, 0), cc, nullptr, 0, nullptr, 0, lm0 + m, lcoef(l_i)));
+      SWW_TRY(term(lm0 + m, 0));
+    }
+  }
+  if (apply_cinv) {   // v M D_w M phi
+    SWW_TRY(sww_mas_filter_internal(c, out, +1, b.X, out));
+    SWW_TRY(k_cinv_fkp(c, out, c->nbar_w, c->v_cell, c->shot, c->P_fkp, out, nullptr));
+    SWW_TRY(sww_mas_filter_internal(c, out, +1, b.X, out));
+  }
+  return 0;
 }
 
 // one symmetrised phi difference map (kind = compact spectra PS or PST), weighted by wmap
@@ -551,12 +612,22 @@ extern "C" int sww_bk_fisher_pair(sww_ctx* c, sww_devptr aA, sww_devptr aB, sww_
     }
   }
   // tilde-phi difference maps, all resident
-  for (int al = 0; al < nb; ++al) SWW_TRY(build_phi(c, b, P, b.PST, al, b.Wt, b.Dt + (size_t)al * N));
+  for (int al = 0; al < nb; ++al) {
+    if (c->include_pix)
+      SWW_TRY(build_phi_pix(c, b, P, b.PST, al, false, b.Dt + (size_t)al * N));
+    else
+      SWW_TRY(build_phi(c, b, P, b.PST, al, b.Wt, b.Dt + (size_t)al * N));
+  }
   // C^-1 phi difference maps in column blocks; Gram against the resident tilde maps (rows alpha <= beta only)
   SWW_CUDA(cudaMemsetAsync(F, 0, sizeof(double) * (size_t)nb * nb, c->stream));
   for (int b0 = 0; b0 < nb; b0 += b.blk) {
     int nbk = (b0 + b.blk <= nb) ? b.blk : nb - b0;
-    for (int j = 0; j < nbk; ++j) SWW_TRY(build_phi(c, b, P, b.PS, b0 + j, b.Wc, b.CD + (size_t)j * N));
+    for (int j = 0; j < nbk; ++j) {
+      if (c->include_pix)
+        SWW_TRY(build_phi_pix(c, b, P, b.PS, b0 + j, true, b.CD + (size_t)j * N));
+      else
+        SWW_TRY(build_phi(c, b, P, b.PS, b0 + j, b.Wc, b.CD + (size_t)j * N));
+    }
     SWW_TRY(sww_gram_upper(c, b.Dt, b.CD, b0 + nbk, nbk, (long long)N, b0 + nbk, F, nb, b0));
   }
   bk_finalize_kernel<<<sww_grid_for((long long)nb * nb, 256), 256, 0, c->stream>>>(F, (const double*)delta, nb);

@@ -77,16 +77,17 @@ int k_prep_static(sww_ctx* c) {
 }
 
 // nCa = n C^-1 a ; nAa = n A^-1 a ; WS = W * (N A^-1 a)
+// include_pix: a_c = M a replaces a in the C^-1 branch, ainv_in = M^-1 (a / n_A) replaces a / n_A
 __global__ void prep_pk_kernel(long long N, const double* __restrict__ a, const double* __restrict__ n,
                                const double* __restrict__ nw, const double* __restrict__ nA, double shot, double P,
                                double v_cell, double* __restrict__ nCa, double* __restrict__ nAa,
-                               double* __restrict__ WS) {
+                               double* __restrict__ WS, const double* __restrict__ a_c, const double* __restrict__ ainv_in) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-    double x = a[i], nn = n[i], w = nw[i];
+    double x = a_c ? a_c[i] : a[i], nn = n[i], w = nw[i];
     double fkp = w * (w * P + shot);
     bool on = w > 0;
     double cinv = on ? (x / fkp) * v_cell : 0.0;
-    double ainv = x / nA[i];
+    double ainv = ainv_in ? ainv_in[i] : a[i] / nA[i];
     nCa[i] = cinv * nn;
     nAa[i] = ainv * nn;
     double NAa = shot * nn * ainv / v_cell;
@@ -94,9 +95,9 @@ __global__ void prep_pk_kernel(long long N, const double* __restrict__ a, const 
   }
 }
 
-int k_prep_pk(sww_ctx* c, const double* a, double* nCa, double* nAa, double* WS) {
+int k_prep_pk(sww_ctx* c, const double* a, double* nCa, double* nAa, double* WS, const double* a_c, const double* ainv) {
   prep_pk_kernel<<<SMS * 8, 256, 0, c->stream>>>(c->g.N, a, c->nbar, c->nbar_w, c->nbar_A, c->shot, c->P_fkp,
-                                                c->v_cell, nCa, nAa, WS);
+                                                c->v_cell, nCa, nAa, WS, a_c, ainv);
   c->n_own++;
   SWW_CUDA(cudaGetLastError());
   return 0;
@@ -487,4 +488,49 @@ extern "C" int sww_set_ylm_cache(sww_ctx* c, sww_devptr maps) {
   }
   c->ylm_maps = m;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// include_pix building blocks: element-wise division and the k-space MAS filter
+// ------------------------------------------------------------------------------------------
+__global__ void div_kernel(long long N, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] / b[i];
+}
+
+int k_div(sww_ctx* c, const double* a, const double* b, double* out) {
+  div_kernel<<<SMS * 8, 256, 0, c->stream>>>(c->g.N, a, b, out);
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void mas_mul_kernel(Geo g, double2* __restrict__ spec, int power, double scale) {
+  long long rows = (long long)g.nx * g.ny;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+    double mxy = g.mas[0][ix] * g.mas[1][iy];
+    for (int iz = threadIdx.x; iz < g.nzh; iz += blockDim.x) {
+      double m = mxy * g.mas[2][iz];
+      double f = (power > 0 ? m : 1.0 / m) * scale;
+      double2 v = spec[row * g.nzh + iz];
+      v.x *= f;
+      v.y *= f;
+      spec[row * g.nzh + iz] = v;
+    }
+  }
+}
+
+int k_mas_mul(sww_ctx* c, double2* spec, int power, double scale) {
+  mas_mul_kernel<<<SMS * 8, 128, 0, c->stream>>>(c->g, spec, power, scale);
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out = IFT[MAS^power FT[x]]; spec: complex scratch [Nc] (x may alias out)
+int sww_mas_filter_internal(sww_ctx* c, const double* x, int power, double2* spec, double* out) {
+  SWW_TRY(sww_r2c(c, x, spec));
+  SWW_TRY(k_mas_mul(c, spec, power, 1.0 / (double)c->g.N));
+  return sww_c2r(c, spec, out);
 }

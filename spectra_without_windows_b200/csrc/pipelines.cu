@@ -145,7 +145,16 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
   const int n_k = c->g.n_k, n_l = c->n_l, n_b = n_k * n_l;
   const double N = (double)c->g.N;
 
-  SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS));
+  if (c->include_pix) {
+    // a_c = M a ; ainv = M^-1 (a / n_A): two extra full transforms pairs, everything else is unchanged
+    SWW_REQUIRE(b.X && b.tmp, "include_pix needs the full workspace (unset SWW_TIGHT_WS)");
+    SWW_TRY(sww_mas_filter_internal(c, a, +1, b.X, b.nCa));
+    SWW_TRY(k_div(c, a, c->nbar_A, b.nAa));
+    SWW_TRY(sww_mas_filter_internal(c, b.nAa, -1, b.X, b.tmp));
+    SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS, b.nCa, b.tmp));
+  } else {
+    SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS));
+  }
   SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
   SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
   // q-bar: one transform of W N A^-1 a, then one binning pass against F^C_l
@@ -192,9 +201,14 @@ extern "C" int sww_pk_data_q(sww_ctx* c, sww_devptr diff_, sww_devptr q_out) {
   pk_data_layout(c, c->ar, b);
   CHECK_ARENA(c);
   const double N = (double)c->g.N;
-  // f = n C^-1 d
-  SWW_TRY(k_cinv_fkp(c, (const double*)diff_, c->nbar_w, c->v_cell, c->shot, c->P_fkp, b.f, c->nbar));
-  SWW_TRY(sww_ylm_project_internal(c, b.f, 2, true, true, b.tmp, b.spec, b.FD));
+  // f = n C^-1 d   (include_pix: f = n v D_w M d, and no MAS^2 factor: src/covariances_pk.py:386-389)
+  const double* d_in = (const double*)diff_;
+  if (c->include_pix) {
+    SWW_TRY(sww_mas_filter_internal(c, d_in, +1, b.spec, b.tmp));
+    d_in = b.tmp;
+  }
+  SWW_TRY(k_cinv_fkp(c, d_in, c->nbar_w, c->v_cell, c->shot, c->P_fkp, b.f, c->nbar));
+  SWW_TRY(sww_ylm_project_internal(c, b.f, c->include_pix ? 0 : 2, true, true, b.tmp, b.spec, b.FD));
   if (c->fft_backend == 1) {
     F3Args A = {};
     for (int q = 0; q < c->n_l; ++q) A.G[q] = b.FD[q];
@@ -285,4 +299,19 @@ extern "C" int sww_paint(sww_ctx* c, sww_devptr pos, sww_devptr w, uint64_t n, c
   SWW_REQUIRE(scheme == 2 || scheme == 3, "scheme must be 2 (CIC) or 3 (TSC)");
   SWW_REQUIRE(n == 0 || (pos && w), "null catalogue pointer");
   return k_paint(c, (const double*)pos, (const double*)w, n, box_center, scheme, scale, (double*)out);
+}
+
+extern "C" int sww_set_include_pix(sww_ctx* c, int include_pix) {
+  SWW_REQUIRE(c, "null context");
+  c->include_pix = include_pix != 0;
+  return 0;
+}
+
+extern "C" int sww_mas_filter(sww_ctx* c, sww_devptr x, int power, sww_devptr out) {
+  CHECK_READY(c);
+  SWW_REQUIRE(x && out && (power == 1 || power == -1), "mas_filter: bad argument");
+  OpsBufs b;
+  ops_layout(c, c->ar, b);
+  CHECK_ARENA(c);
+  return sww_mas_filter_internal(c, (const double*)x, power, b.spec, (double*)out);
 }

@@ -109,6 +109,7 @@ struct sww_ctx {
   cufftHandle plan_d2z = 0, plan_z2d = 0, plan_z2z = 0;
   bool have_z2z = false;
   int fft_backend = 0;
+  bool include_pix = false;
   bool tight_ws = false;   // SWW_TIGHT_WS=1: size the workspace for the selected FFT backend only
   // bk
   std::vector<int> tris;
@@ -196,7 +197,11 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
 // ---- kernels.cu (launch wrappers)
 int k_build_binmap(sww_ctx* c);
 int k_prep_static(sww_ctx* c);  // nW map
-int k_prep_pk(sww_ctx* c, const double* a, double* nCa, double* nAa, double* WS);
+int k_prep_pk(sww_ctx* c, const double* a, double* nCa, double* nAa, double* WS, const double* a_c = nullptr,
+              const double* ainv = nullptr);
+int k_div(sww_ctx* c, const double* a, const double* b, double* out);
+int k_mas_mul(sww_ctx* c, double2* spec, int power, double scale);
+int sww_mas_filter_internal(sww_ctx* c, const double* x, int power, double2* spec, double* out);
 int k_cinv_fkp(sww_ctx* c, const double* x, const double* nw, double v_cell, double shot, double P, double* out,
                const double* post_mul);
 int k_apply_n(sww_ctx* c, const double* x, const double* nbar, double v_cell, double shot, double* out);

@@ -59,8 +59,6 @@ class Params:
     def unsupported(self):
         if self.wtype == 1:
             raise Exception("weights = ML is not implemented on the B200 path yet (SURVEY.md section 8f row N1)")
-        if self.include_pix:
-            raise Exception("include_pix = True is not implemented on the B200 path yet (SURVEY.md section 8f row N2)")
 
     def ktag(self):
         return "k%.3f_%.3f_%.3f_l%d" % (self.k_min, self.k_max, self.dk, self.lmax)
@@ -108,6 +106,7 @@ def _setup(P: Params, sim_no, pipelines, paint_data):
         else:
             diff = d
     ctx.set_fields(nbar, nbar_mask, nbar_A, shot_fac)
+    ctx.set_include_pix(P.include_pix)
     return ctx, mesh, nbar_A, alpha_ran, shot_fac, diff
 
 

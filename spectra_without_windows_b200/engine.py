@@ -227,6 +227,18 @@ class Context:
         self.set_fields(nbar, nbar.copy(), nbar_A, shot_fac, P_fkp)
         return nbar_A
 
+    def set_include_pix(self, flag):
+        """The `include_pix` .param boolean: forward-model the pixel window (MAS) in the covariance."""
+        _lib.check(self.lib.sww_set_include_pix(self._h, int(bool(flag))))
+        self.include_pix = bool(flag)
+
+    def mas_filter(self, x, power):
+        """IFT[MAS^power FT[x]] (power = +1 / -1)."""
+        x = self.dev(x)
+        out = self.empty(self.mesh.shape)
+        _lib.check(self.lib.sww_mas_filter(self._h, x.data_ptr(), int(power), out.data_ptr()))
+        return out
+
     # -- Gaussian fields
     def grf_legacy(self, seed, sigma, out=None, stream=None):
         """Device-side `np.random.seed(seed); np.random.normal(0, sigma, sigma.shape)` (numpy legacy stream).

@@ -196,8 +196,8 @@ output = {out}
 [settings]
 weights = FKP
 N_mc = {nmc}
-include_pix = False
-rand_nbar = False
+include_pix = {include_pix}
+rand_nbar = {rand_nbar}
 fiducial_pk = None
 use_qbar = {use_qbar}
 nbar_unif = 1e-3
@@ -205,7 +205,7 @@ low_mem = True
 """
 
 
-def write_world_files(w: World, root: str, use_qbar=True, N_mc=None):
+def write_world_files(w: World, root: str, use_qbar=True, N_mc=None, include_pix=False, rand_nbar=False):
     """Write the .param file, the nbar map and .npz Cartesian catalogues under `root`.
     Returns the param-file path."""
     out, mc, tmp = root + "/out/", root + "/mc/", root + "/tmp/"
@@ -220,5 +220,6 @@ def write_world_files(w: World, root: str, use_qbar=True, N_mc=None):
         f.write(PARAM_TEMPLATE.format(name=w.name, data_file=dfile, randoms_file=rfile, pk=w.pk_bins,
                                       bk=w.bk_bins, g=w.grid, type=w.type, zmin=w.zmin, zmax=w.zmax,
                                       b=w.box, h=w.h_fid, om=w.OmegaM_fid, tmp=tmp + w.type, mc=mc, out=out,
-                                      nmc=(w.N_mc if N_mc is None else N_mc), use_qbar=use_qbar))
+                                      nmc=(w.N_mc if N_mc is None else N_mc), use_qbar=use_qbar,
+                                      include_pix=include_pix, rand_nbar=rand_nbar))
     return pfile

@@ -80,3 +80,36 @@ def test_shipped_precision_gap_documented(name, golden):
     for k in ("pk_fish_1", "pk_qbar_1", "bk_fish_1"):
         e = relerr(g["c64_" + k], g[k])
         assert 1e-10 < e < 1e-4, (k, e)
+
+
+def _variant_setup(w, which, variant):
+    kmin, kmax, dk, lmax = w.pk_bins if which == "pk" else w.bk_bins
+    kw = {}
+    if variant == "pix":
+        kw["include_pix"] = True
+    if variant == "rand":      # n(r) from the painted randoms (src/opt_utilities.py:262-267)
+        _, rnd = orc.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box, w.grid, w.box_center)
+        kw["nbar_override"] = rnd
+    return orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax, **kw)
+
+
+@pytest.mark.parametrize("variant", ["pix", "rand"])
+def test_param_booleans_match_reference_scripts(variant, world, golden):
+    """include_pix = True and rand_nbar = True (the remaining .param booleans) against the unmodified
+    reference scripts run with those settings."""
+    w, g = world("toyA"), golden("toyA_" + variant)
+    S = _variant_setup(w, "pk", variant)
+    for r in (1, 2):
+        qbar, F = orc.pk_fisher_realisation(S, S.grf(r))
+        assert relerr(F, g["pk_fish_%d" % r]) < 1e-11
+        assert relerr(qbar, g["pk_qbar_%d" % r]) < 1e-11
+    diff, _ = orc.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box, w.grid, w.box_center)
+    q = orc.pk_data_q(S, diff)
+    p = orc.pk_solve(g["pk_fish_comb"], q, g["pk_bias_comb"])
+    assert relerr(p, g["pk_p"][:, 1:].T.ravel()) < 2e-8
+    Sb = _variant_setup(w, "bk", variant)
+    F, (gA, tgA), (gB, tgB) = orc.bk_fisher_pair(Sb, Sb.grf(2), Sb.grf(3), return_g=True)
+    assert relerr(F, g["bk_fish_1"]) < 1e-10
+    qb = orc.bk_data_q(Sb, diff, mc_maps=[(gA, tgA), (gB, tgB)], N_mc=2)
+    pb = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qb)
+    assert relerr(pb, g["bk_p"][:, 3:].T.ravel()) < 2e-8
