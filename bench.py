@@ -35,6 +35,10 @@ WORKLOADS = {
     # bispectrum Fisher (a step = one PAIR of realisations): 256^3, k in [0,0.11] dk=0.01, l<=4 -> 191 triangles, n_b=573
     "C4": dict(grid=(256, 256, 256), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
                bins=(0.0, 0.11, 0.01, 4), bk=True),
+    # bispectrum data path (config 3 of BASELINE.json): 256^3, k in [0,0.11] dk=0.01, l = 0,2; a step = one data catalogue's
+    # g-maps + 3-field term + the 1-field term over N_mc = 10 resident bias simulations
+    "C3": dict(grid=(256, 256, 256), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
+               bins=(0.0, 0.11, 0.01, 2), bk=True, bk_data=True, n_mc=10),
     "C4S": dict(grid=(128, 128, 128), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
                 bins=(0.0, 0.11, 0.01, 2), bk=True),
     # pk data path (paint + q_alpha): config C1 of SURVEY 8d; a step = one catalogue
@@ -201,6 +205,62 @@ def run_pk_data(args, wl, mesh, rank, world, local, dev):
                       "paint_gbs_algorithmic": 32.0 * npart / (pms * 1e-3) / 1e9, "q_finite": bool(torch.isfinite(q).all())}))
 
 
+def run_bk_data(args, wl, mesh, rank, world, local, dev):
+    """Bispectrum data path (bk/compute_bk_data.py:250-406): g-maps of the data, 3-field term, 1-field term over N_mc
+    bias simulations whose g-maps are resident in HBM (the reference reloads them from .npz per simulation)."""
+    import torch
+    from spectra_without_windows_b200 import engine
+    ctx = engine.Context(mesh, local, ("bk_fisher", "bk_data"))
+    rax_d = [torch.from_numpy(a).to(dev) for a in mesh.rax]
+    nbar_r = survey_nbar_r(rax_d, torch).contiguous()
+    nbar = (nbar_r * ALPHA).contiguous()
+    nbar_A = nbar_r.clone()
+    nbar_A[nbar_A == 0] = float(nbar_r[nbar_r != 0].min()) * 0.01
+    ctx.set_fields(nbar, nbar, nbar_A, SHOT)
+    sig = torch.sqrt(nbar_A)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    diff = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * torch.sqrt(nbar)
+    aA = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig
+    aB = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig
+    _, (gA, tgA, gB, tgB) = ctx.bk_fisher_pair(aA, aB)
+    n_mc = wl["n_mc"]
+
+    def step():
+        gd = ctx.bk_gmaps(diff, data=True)
+        q = ctx.bk_q3(gd)
+        for i in range(n_mc // 2):
+            ctx.bk_q1_accumulate(gd, gA, tgA, n_mc, q)
+            ctx.bk_q1_accumulate(gd, gB, tgB, n_mc, q)
+        return q
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    own0, _ = ctx.launch_counts()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        q = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    own1, _ = ctx.launch_counts()
+    ctx.profile(True)
+    step()
+    prof = {k: {"launches": n, "ms": round(m_, 3)} for k, (n, m_) in ctx.profile_report().items()}
+    ctx.profile(False)
+    print(json.dumps({"metric": "bk data catalogues/s", "value": args.steps / (ms * 1e-3), "unit": "catalogues/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "C3: compute_bk_data (g-maps, 3-field term, 1-field term over N_mc=%d resident bias simulations), "
+                                 "mesh 256^3, k in [0,0.11] dk=0.01 l=0,2, %d triangles" % (n_mc, ctx.n_tri), "l2": "inputs>L2"},
+                      "gpu_launches": int(own1 - own0), "clocks": clocks, "profile_one_step": prof,
+                      "q_finite": bool(torch.isfinite(q).all())}))
+
+
 def run_bk(args, wl, mesh, rank, world, local, dev):
     """Bispectrum Fisher: one step = one pair of realisations (bk/compute_bk_randoms.py)."""
     import torch
@@ -307,6 +367,8 @@ def main():
     if big:
         os.environ["SWW_TIGHT_WS"] = "1"     # 1024^3: size the workspace for the fused chains only
     mesh = engine.Mesh(wl["box"], wl["grid"], wl["box_center"], *wl["bins"])
+    if wl.get("bk_data"):
+        return run_bk_data(args, wl, mesh, rank, world, local, dev)
     if wl.get("bk"):
         return run_bk(args, wl, mesh, rank, world, local, dev)
     if wl.get("data"):

@@ -24,6 +24,7 @@
 int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
                              double2* spec, double2* const* out);
 size_t sww_sm100_qstack_bytes(const sww_ctx* c, int nb);
+int sww_gram3(sww_ctx* c, const double* X, const double* Y, const double* Z, int ni, int nj, int nz, long long K, double* C);
 int sww_gram_upper(sww_ctx* c, const double* A, const double* B, int m, int n, long long K, int row_limit,
                    double* C, int ldc, int col0);
 
@@ -735,6 +736,24 @@ extern "C" int sww_bk_q3(sww_ctx* c, sww_devptr g_, sww_devptr q_out) {
   return tb.flush();
 }
 
+// q[t][l] += w * (T1[a,b,lc] + T1[b,a,lc] + T2[a,b,lc] + T2[b,a,lc] + T3[a,b,lc] + T3[b,a,lc])
+__global__ void q1_assemble_kernel(const int* __restrict__ tris, int n_tri, int n_l, int n_k, const double* __restrict__ T,
+                                   double w, double* __restrict__ q) {
+  const int nz = n_l * n_k;
+  const long long tsz = (long long)n_k * n_k * nz;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_tri * n_l; idx += gridDim.x * blockDim.x) {
+    int t = idx / n_l, l = idx - t * n_l;
+    int a = tris[3 * t], b = tris[3 * t + 1], c = tris[3 * t + 2];
+    int col = l * n_k + c;
+    long long ab = ((long long)a * n_k + b) * nz + col, ba = ((long long)b * n_k + a) * nz + col;
+    // the reference adds the two triple sums in this order (bk/compute_bk_data.py:402-403)
+    double s1 = T[ab] + T[tsz + ba] + T[2 * tsz + ab];          // g_a gm_b tg_c + g_b gm_c tg_a + g_c gm_a tg_b
+    double s2 = T[tsz + ab] + T[ba] + T[2 * tsz + ba];          // g_a tg_b gm_c + g_b tg_c gm_a + g_c tg_a gm_b
+    q[idx] += w * s1;
+    q[idx] += w * s2;
+  }
+}
+
 // 1-field term of one MC simulation (bk/compute_bk_data.py:380-403)
 extern "C" int sww_bk_q1_accumulate(sww_ctx* c, sww_devptr g_, sww_devptr gm_, sww_devptr tgm_, double inv_two_nmc,
                                     sww_devptr q_inout) {
@@ -744,6 +763,24 @@ extern "C" int sww_bk_q1_accumulate(sww_ctx* c, sww_devptr g_, sww_devptr gm_, s
   const double *g = (const double*)g_, *gm = (const double*)gm_, *tg = (const double*)tgm_;
   const size_t N = c->g.N;
   const int n_k = c->g.n_k;
+  if (n_k >= 4 && n_k <= 32 && N % 2 == 0) {
+    // three trilinear Grams on the FP64 tensor cores instead of 6 n_tri n_l full-map triple products:
+    //   T1[i,j,(l,c)] = sum g_i gm_j tg_c^l ;  T2 = sum g_i tg_j gm_c^l ;  T3 = sum gm_i tg_j g_c^l
+    const int nz = c->n_l * n_k;
+    const size_t tsz = (size_t)n_k * n_k * nz;
+    if (c->q1_scratch_elems < 3 * tsz) {
+      if (c->d_q1_scratch) cudaFree(c->d_q1_scratch);
+      SWW_CUDA(cudaMalloc(&c->d_q1_scratch, 3 * tsz * sizeof(double)));
+      c->q1_scratch_elems = 3 * tsz;
+    }
+    double* T = c->d_q1_scratch;
+    SWW_TRY(sww_gram3(c, g, gm, tg, n_k, n_k, nz, (long long)N, T));
+    SWW_TRY(sww_gram3(c, g, tg, gm, n_k, n_k, nz, (long long)N, T + tsz));
+    SWW_TRY(sww_gram3(c, gm, tg, g, n_k, n_k, nz, (long long)N, T + 2 * tsz));
+    q1_assemble_kernel<<<sww_grid_for((long long)c->n_tri * c->n_l, 128), 128, 0, c->stream>>>(c->d_tris, c->n_tri, c->n_l, n_k, T,
+                                                                                         -inv_two_nmc, (double*)q_inout);
+    return launch_ok(c);
+  }
   TermBatcher tb(c, (double*)q_inout);
   auto M = [&](const double* base, int l, int i) { return base + ((size_t)l * n_k + i) * N; };
   const double w = -inv_two_nmc;

@@ -158,6 +158,164 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int kspli
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Trilinear Gram   C[i*nj + j][c] = sum_k X[i][k] Y[j][k] Z[c][k]
+// (the 1-field term of bk/compute_bk_data.py:380-403 is six such contractions per MC simulation).
+// Same tiling as above, but the A operand is never materialised: the fragment is the product of two
+// shared-memory rows, formed in registers right before the DMMA.
+// ------------------------------------------------------------------------------------------
+#define G3_XROWS 36
+#define G3_YROWS 32
+#define G3_ZROWS 40
+struct Gram3Stage {
+  double X[G3_XROWS][KC + KPAD];
+  double Y[G3_YROWS][KC + KPAD];
+  double Z[G3_ZROWS][KC + KPAD];
+};
+struct Gram3Smem {
+  Gram3Stage s[STAGES];
+};
+
+// Tile: 128 (i,j) rows x 8 NJ columns.  Warps 0-3 and 4-7 cover the same four 32-row slabs and split each
+// K chunk in halves (the column count is small, so the second warp column of the plain Gram would idle);
+// the two halves are summed through shared memory at the end.
+template <int NJ>
+__global__ void __launch_bounds__(GTHREADS, 1)
+gram3_dmma_kernel(const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z, int ni, int nj,
+                  int nz, long long K, long long chunks_per_split, double* __restrict__ partial, int Mpad, int Npad) {
+  constexpr int TN3 = 8 * NJ;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Gram3Smem& S = *reinterpret_cast<Gram3Smem*>(smem_raw);
+  const int mt = blockIdx.x, nt = blockIdx.y, ks = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 3, wk = warp >> 2;
+  const long long total_chunks = (K + KC - 1) / KC;
+  long long c_begin = (long long)ks * chunks_per_split;
+  long long c_end = c_begin + chunks_per_split;
+  if (c_end > total_chunks) c_end = total_chunks;
+  const int row0 = mt * TM, col0 = nt * TN3;
+  const int m = ni * nj;
+  const int i_first = row0 / nj;                       // first X row this tile needs
+  int i_last = (row0 + TM - 1) / nj;
+  if (i_last > ni - 1) i_last = ni - 1;
+  const int nxr = i_last - i_first + 1;                // <= G3_XROWS (checked on the host)
+
+  double acc[4][NJ][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // load slots: every thread copies the same (row, 16-byte piece) of each chunk, so the source pointer and the
+  // shared-memory offset are computed once; per chunk only the K offset moves.  K is even (checked on the host).
+  constexpr int PITCH = KC + KPAD;
+  constexpr int STAGE_DOUBLES = (int)(sizeof(Gram3Stage) / sizeof(double));
+  constexpr int MAXSLOT = ((G3_XROWS + G3_YROWS + G3_ZROWS) * (KC / 2) + GTHREADS - 1) / GTHREADS;
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const int rows = nxr + nj + TN3;
+  const double* src[MAXSLOT];
+  int dst[MAXSLOT], kq0[MAXSLOT];
+#pragma unroll
+  for (int sl = 0; sl < MAXSLOT; ++sl) {
+    int v = tid + sl * GTHREADS;
+    int r = v / (KC / 2), q = 2 * (v - r * (KC / 2));
+    src[sl] = nullptr;
+    dst[sl] = 0;
+    kq0[sl] = q;
+    if (r < nxr) {
+      src[sl] = X + (long long)(i_first + r) * K + q;
+      dst[sl] = (int)(&S.s[0].X[r][q] - sm);
+    } else if (r < nxr + nj) {
+      src[sl] = Y + (long long)(r - nxr) * K + q;
+      dst[sl] = (int)(&S.s[0].Y[r - nxr][q] - sm);
+    } else if (r < rows) {
+      int rr = r - nxr - nj;
+      dst[sl] = (int)(&S.s[0].Z[rr][q] - sm);
+      src[sl] = (col0 + rr < nz) ? Z + (long long)(col0 + rr) * K + q : nullptr;
+      if (!src[sl]) kq0[sl] = -1;                      // zero-fill row
+    } else {
+      kq0[sl] = -2;                                    // no work
+    }
+  }
+  auto load_stage = [&](int stage, long long chunk) {
+    const long long k0 = chunk * KC;
+#pragma unroll
+    for (int sl = 0; sl < MAXSLOT; ++sl) {
+      if (kq0[sl] == -2) continue;
+      bool ok = kq0[sl] >= 0 && k0 + kq0[sl] + 1 < K;
+      cp_async16(sm + stage * STAGE_DOUBLES + dst[sl], ok ? (const void*)(src[sl] + k0) : (const void*)X, ok);
+    }
+  };
+
+  // operand rows of this thread: A rows (lane>>2) + 8 i of the warp slab -> (X row, Y row); rows past m compute
+  // garbage into the padded part of the partial tile, which the reduction never reads
+  const int kk = lane & 3;
+  const double *xp[4], *yp[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = row0 + wm * 32 + (lane >> 2) + 8 * i;
+    int rr = r < m ? r : row0;
+    xp[i] = &S.s[0].X[rr / nj - i_first][wk * (KC / 2) + kk];
+    yp[i] = &S.s[0].Y[rr % nj][wk * (KC / 2) + kk];
+  }
+  const double* zp = &S.s[0].Z[lane >> 2][wk * (KC / 2) + kk];
+  const long long nchunks = c_end > c_begin ? c_end - c_begin : 0;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nchunks) load_stage(s, c_begin + s);
+    cp_async_commit();
+  }
+  int st = 0;
+  for (long long it = 0; it < nchunks; ++it) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      long long nx = it + STAGES - 1;
+      int sn = st + STAGES - 1;
+      if (sn >= STAGES) sn -= STAGES;
+      if (nx < nchunks) load_stage(sn, c_begin + nx);
+      cp_async_commit();
+    }
+    const int so = st * STAGE_DOUBLES;
+#pragma unroll
+    for (int k4 = 0; k4 < KC / 2; k4 += 4) {
+      double a[4], b[NJ];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = xp[i][so + k4] * yp[i][so + k4];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) b[j] = zp[so + 8 * j * PITCH + k4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (++st == STAGES) st = 0;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // sum the two K halves: warps 4-7 park their accumulators in (now idle) shared memory
+  double2* park = reinterpret_cast<double2*>(smem_raw);          // [4 warps][4*NJ][32 lanes]
+  if (wk == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) park[(wm * 4 * NJ + i * NJ + j) * 32 + lane] = make_double2(acc[i][j][0], acc[i][j][1]);
+  }
+  __syncthreads();
+  if (wk == 0) {
+    double* P = partial + (long long)ks * Mpad * Npad;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        double2 o = park[(wm * 4 * NJ + i * NJ + j) * 32 + lane];
+        int r = row0 + wm * 32 + 8 * i + (lane >> 2);
+        int cidx = col0 + 8 * j + 2 * (lane & 3);
+        *reinterpret_cast<double2*>(&P[(long long)r * Npad + cidx]) = make_double2(acc[i][j][0] + o.x, acc[i][j][1] + o.y);
+      }
+  }
+}
+
 static double* g_partial = nullptr;
 static size_t g_partial_bytes = 0;
 
@@ -208,4 +366,51 @@ extern "C" int sww_gram_f64(sww_ctx* c, sww_devptr A, sww_devptr B, int32_t m, i
                             sww_devptr C) {
   SWW_REQUIRE(c && A && B && C, "null argument");
   return gram_run(c, (const double*)A, (const double*)B, m, n, (long long)N, accumulate, (double*)C, n, 0);
+}
+
+template <int NJ>
+static int gram3_launch(sww_ctx* c, const double* X, const double* Y, const double* Z, int ni, int nj, int nz, long long K,
+                        double* C) {
+  const int m = ni * nj, TN3 = 8 * NJ;
+  int mtiles = (m + TM - 1) / TM, ntiles = (nz + TN3 - 1) / TN3;
+  int Mpad = mtiles * TM, Npad = ntiles * TN3;
+  long long total_chunks = (K + KC - 1) / KC;
+  int ksplit = (148 * 2 + mtiles * ntiles - 1) / (mtiles * ntiles);
+  if (ksplit > total_chunks) ksplit = (int)total_chunks;
+  if (ksplit < 1) ksplit = 1;
+  long long cps = (total_chunks + ksplit - 1) / ksplit;
+  ksplit = (int)((total_chunks + cps - 1) / cps);
+  size_t need = (size_t)ksplit * Mpad * Npad * sizeof(double);
+  if (need > g_partial_bytes) {
+    if (g_partial) cudaFree(g_partial);
+    SWW_CUDA(cudaMalloc(&g_partial, need));
+    g_partial_bytes = need;
+  }
+  size_t smem = sizeof(Gram3Smem);
+  SWW_CUDA(cudaFuncSetAttribute(gram3_dmma_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(mtiles, ntiles, ksplit);
+  gram3_dmma_kernel<NJ><<<grid, GTHREADS, smem, c->stream>>>(X, Y, Z, ni, nj, nz, K, cps, g_partial, Mpad, Npad);
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  gram_reduce_kernel<<<sww_grid_for((long long)m * nz, 256), 256, 0, c->stream>>>(g_partial, ksplit, Mpad, Npad, m, nz, 0, C, nz, 0);
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// C[(i*nj + j) * nz + c] = sum_k X[i][k] Y[j][k] Z[c][k]
+int sww_gram3(sww_ctx* c, const double* X, const double* Y, const double* Z, int ni, int nj, int nz, long long K, double* C) {
+  SWW_REQUIRE(ni > 0 && nj >= 4 && nj <= G3_YROWS && nz > 0, "gram3: unsupported operand counts");
+  SWW_REQUIRE(TM / nj + 2 <= G3_XROWS, "gram3: too many X rows per tile");
+  SWW_REQUIRE(K % 2 == 0 && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)Z % 16 == 0), "gram3: operands must be 16-byte aligned with an even cell count");
+  SWW_PROF(c, "gram3.dmma f64");
+  // column blocks of 24, 32 or 40: whichever pads nz least
+  int best = 3, waste = 1 << 30;
+  for (int nj8 = 3; nj8 <= 5; ++nj8) {
+    int w = (nz + 8 * nj8 - 1) / (8 * nj8) * 8 * nj8 - nz;
+    if (w < waste) { waste = w; best = nj8; }
+  }
+  if (best == 3) return gram3_launch<3>(c, X, Y, Z, ni, nj, nz, K, C);
+  if (best == 4) return gram3_launch<4>(c, X, Y, Z, ni, nj, nz, K, C);
+  return gram3_launch<5>(c, X, Y, Z, ni, nj, nz, K, C);
 }

@@ -121,6 +121,8 @@ struct sww_ctx {
   double* d_partial = nullptr;
   size_t partial_elems = 0;
   unsigned int* d_counter = nullptr;
+  double* d_q1_scratch = nullptr;
+  size_t q1_scratch_elems = 0;
   // profiling
   bool prof_on = false;
   std::vector<std::string> prof_names;
