@@ -107,8 +107,8 @@ extern "C" int sww_ctx_create(const sww_geometry* geo, sww_ctx** out) {
   g.binmap = c->d_binmap;
   c->partial_elems = (size_t)148 * 4 * SWW_MAX_L * SWW_MAX_BINS;
   SWW_CUDA(cudaMalloc(&c->d_partial, c->partial_elems * sizeof(double)));
-  SWW_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
-  SWW_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int)));
+  SWW_CUDA(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
+  SWW_CUDA(cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned int)));
   SWW_TRY(k_build_binmap(c));
   SWW_TRY(sww_fft_init(c));
   SWW_CUDA(cudaStreamSynchronize(c->stream));

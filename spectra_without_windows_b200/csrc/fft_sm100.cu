@@ -349,7 +349,12 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
   const int ztiles = Kzp / FFT_TZ;
   const long long items = (long long)bO.K * ztiles;
   const bool nz_even = (g.nz % 2) == 0;
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+  // MODE 2 row batch: block = blk * nrows + row
+  const int nrows = (MODE == 2 && A.nrows > 1) ? A.nrows : 1;
+  const int row = (int)(blockIdx.x % (unsigned)nrows), blk = (int)(blockIdx.x / (unsigned)nrows);
+  const int nblk = (int)(gridDim.x / (unsigned)nrows);
+  if (MODE == 2 && nrows > 1) P += (long long)row * A.row_pstride;
+  for (long long it = blk; it < items; it += nblk) {
     const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
     const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
     __syncthreads();
@@ -359,7 +364,25 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
     double2 u[16 / RL][RL];
     fft_last<N, 1, false, RL>(tile, tw, tid, u);
     // epilogue straight from registers (uniform trip count: the warp collectives of MODE 2 are safe)
-    if (MODE != 2) {
+    if (MODE == 3) {
+      // shell-ordered store: all permutation loads first (the compiler cannot hoist them over the stores)
+      int pq[16 / RL][RL];
+#pragma unroll
+      for (int s = 0; s < 16 / RL; ++s) {
+        const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7, iz = iz0 + cc;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          const int ia = bi + r * (N / RL);
+          const bool inb = bA.has(ia) && iz < Kz;
+          pq[s][r] = inb ? __ldg(&A.perm[((long long)jo * bA.K + bA.pos(ia)) * Kzp + iz]) : -1;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 16 / RL; ++s)
+#pragma unroll
+        for (int r = 0; r < RL; ++r)
+          if (pq[s][r] >= 0) A.sorted_dst[pq[s][r]] = u[s][r];
+    } else if (MODE != 2) {
 #pragma unroll
       for (int s = 0; s < 16 / RL; ++s) {
         const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7, iz = iz0 + cc;
@@ -405,48 +428,65 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
         for (int r = 0; r < RL; ++r) tile[(bi + r * (N / RL)) * FFT_LDT + cc] = u[s][r];
       }
       __syncthreads();
-      constexpr int GRP = 4;
-      const int total = bA.K * FFT_TZ;
-      for (int e0 = 0; e0 < total; e0 += GRP * NT) {   // uniform trip count (warp collectives below)
-        int bq[GRP];
-        long long cellq[GRP];
-        int ixq[GRP];
+      // |k| is even in the transformed axis, so the cells (+j, iz) and (-j, iz) share a bin: each lane takes
+      // such a pair.  Lane = (16 consecutive j) x (2 consecutive iz); along j the bin index only changes in
+      // contiguous runs, so a segmented shuffle reduction over the 16 same-parity lanes (4 steps) leaves
+      // every run's sum in its head lane, and heads of one parity hold distinct bins: two conflict-free
+      // rounds of adds into the warp-private histogram.  Fixed order -> deterministic.
+      constexpr int GRP = 2;
+      const bool full = (bA.K == N);
+      const int npos = full ? N / 2 + 1 : bA.b + 1;
+      const int nsteps = (npos + 15) >> 4;
+      const int nitems = nsteps * 4;                     // (step, iz pair)
+      const int par = lane & 1, sub = lane >> 1;
+      for (int q0 = warp; q0 < nitems; q0 += GRP * NW) { // uniform per warp (collectives below)
+        int bq[GRP], jq[GRP], ccq[GRP];
+        long long cellp[GRP], cellm[GRP];
+        bool mir[GRP];
 #pragma unroll
         for (int j = 0; j < GRP; ++j) {
-          const int e = e0 + j * NT + tid;
-          const int ja = e >> 3, cc = e & 7, iz = iz0 + cc;
-          const bool inb = (e < total) && iz < Kz;
-          ixq[j] = inb ? bA.idx(ja) : 0;
-          cellq[j] = row_of<AX>(ixq[j], io, g.ny) * g.nzh + iz;
-          bq[j] = inb ? (int)g.binmap[cellq[j]] : SWW_NO_BIN;
+          const int q = q0 + j * NW;
+          const int stp = q >> 2, cc = ((q & 3) << 1) + par, iz = iz0 + cc;
+          const int ja = (stp << 4) + sub;
+          const bool inb = (q < nitems) && ja < npos && iz < Kz;
+          jq[j] = inb ? ja : 0;
+          ccq[j] = cc;
+          mir[j] = inb && ja > 0 && (!full || ja < N / 2);
+          cellp[j] = row_of<AX>(jq[j], io, g.ny) * g.nzh + iz;
+          cellm[j] = row_of<AX>(mir[j] ? N - jq[j] : 0, io, g.ny) * g.nzh + iz;
+          bq[j] = inb ? (int)g.binmap[cellp[j]] : SWW_NO_BIN;
         }
-        double2 Gq[GRP][3];
+        double2 Gp[GRP][3], Gm[GRP][3];
 #pragma unroll
         for (int j = 0; j < GRP; ++j)
 #pragma unroll
           for (int q = 0; q < 3; ++q)
-            if (q < A.n_g && bq[j] != SWW_NO_BIN) Gq[j][q] = A.G[q][cellq[j]];
+            if (q < A.n_g && bq[j] != SWW_NO_BIN) {
+              Gp[j][q] = A.G[q][cellp[j]];
+              if (mir[j]) Gm[j][q] = A.G[q][cellm[j]];
+            }
 #pragma unroll
         for (int j = 0; j < GRP; ++j) {
-          const int cc = tid & 7, iz = iz0 + cc;
-          const int b = bq[j];
+          const int bn = bq[j];
           double v[3] = {0.0, 0.0, 0.0};
-          if (b != SWW_NO_BIN) {
-            const double2 t = tile[ixq[j] * FFT_LDT + cc];
+          if (bn != SWW_NO_BIN) {
+            const int iz = iz0 + ccq[j];
             const double wq = (iz == 0 || (nz_even && iz == g.nz / 2)) ? 1.0 : 2.0;
+            const double2 t = tile[jq[j] * FFT_LDT + ccq[j]];
+            double2 tm = make_double2(0.0, 0.0);
+            if (mir[j]) tm = tile[(N - jq[j]) * FFT_LDT + ccq[j]];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-              if (q < A.n_g) v[q] = wq * (t.x * Gq[j][q].x + t.y * Gq[j][q].y);
+              if (q < A.n_g) {
+                double sacc = t.x * Gp[j][q].x + t.y * Gp[j][q].y;
+                if (mir[j]) sacc += tm.x * Gm[j][q].x + tm.y * Gm[j][q].y;
+                v[q] = wq * sacc;
+              }
           }
-          // The 8 lanes of a quarter-warp hold 8 consecutive iz of one (ix, iy): |k| grows with iz, so
-          // equal bins form contiguous runs.  Segmented shuffle reduction over the runs (3 steps), then
-          // the run heads add into the warp-private histogram, one 8-lane row at a time (rows may
-          // share a bin; within a row the heads' bins are distinct).  Fixed order -> deterministic.
-          const int l8 = lane & 7;
 #pragma unroll
-          for (int d = 1; d < 8; d <<= 1) {
-            const int nbk = __shfl_down_sync(0xffffffffu, b, d);
-            const bool take = (l8 + d < 8) && (nbk == b);
+          for (int d = 2; d < 32; d <<= 1) {
+            const int nbk = __shfl_down_sync(0xffffffffu, bn, d);
+            const bool take = (lane + d < 32) && (nbk == bn);
 #pragma unroll
             for (int q = 0; q < 3; ++q)
               if (q < A.n_g) {
@@ -454,14 +494,14 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
                 if (take) v[q] += nv;
               }
           }
-          const int pbk = __shfl_up_sync(0xffffffffu, b, 1);
-          const bool head = (b != SWW_NO_BIN) && (l8 == 0 || pbk != b);
+          const int pbk = __shfl_up_sync(0xffffffffu, bn, 2);
+          const bool head = (bn != SWW_NO_BIN) && (lane < 2 || pbk != bn);
 #pragma unroll
-          for (int rowq = 0; rowq < 4; ++rowq) {
-            if (head && (lane >> 3) == rowq) {
+          for (int rq = 0; rq < 2; ++rq) {
+            if (head && par == rq) {
 #pragma unroll
               for (int q = 0; q < 3; ++q)
-                if (q < A.n_g) hist[warp * nb + q * g.n_k + b] += v[q];
+                if (q < A.n_g) hist[warp * nb + q * g.n_k + bn] += v[q];
             }
             __syncwarp();
           }
@@ -470,27 +510,31 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
     }
   }
   if (MODE == 2) {
+    const int row_ = (int)(blockIdx.x % (unsigned)nrows);
+    double* out_row = nrows > 1 ? A.out_rows[row_] : A.out_row;
+    double* partial = A.partial + (long long)row_ * nblk * nb;
+    unsigned int* counter = A.counter + row_;
     __syncthreads();
     for (int j = tid; j < nb; j += NT) {
       double sm = 0.0;
       for (int w = 0; w < NW; ++w) sm += hist[w * nb + j];
-      A.partial[(long long)blockIdx.x * nb + j] = sm;
+      partial[(long long)blk * nb + j] = sm;
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-      unsigned t = atomicAdd(A.counter, 1u);
-      is_last = (t == gridDim.x - 1);
+      unsigned t = atomicAdd(counter, 1u);
+      is_last = (t == (unsigned)nblk - 1);
     }
     __syncthreads();
     if (is_last) {
       __threadfence();
       for (int j = tid; j < nb; j += NT) {
         double sm = 0.0;
-        for (unsigned bl = 0; bl < gridDim.x; ++bl) sm += A.partial[(long long)bl * nb + j];
-        A.out_row[j] = sm * A.scale;
+        for (int bl = 0; bl < nblk; ++bl) sm += partial[(long long)bl * nb + j];
+        out_row[j] = sm * A.scale;
       }
-      if (tid == 0) *A.counter = 0;
+      if (tid == 0) *counter = 0;
     }
   }
 }
@@ -956,6 +1000,13 @@ struct Sm100State {
   double2 *P = nullptr, *Q = nullptr, *R = nullptr;
   size_t buf_elems = 0;
   std::vector<int> shell_bx, shell_by, shell_bz;  // per-bin inverse boxes
+  // shell order of the output box (built on first use)
+  int shell_state = 0;          // 0: not built, 1: ready, -1: unsupported
+  long long S = 0;              // in-shell modes
+  int* d_perm = nullptr;        // [Ko][Ka][Kzp] -> position in shell order, or -1
+  int4* d_chunks = nullptr;     // (start, len, bin, 0)
+  int* d_bin_chunk = nullptr;   // [n_k + 1] chunk range of every bin
+  int n_chunks = 0;
 };
 
 static std::vector<double2> make_tw(int n, int count) {
@@ -1022,6 +1073,9 @@ void sww_fft_sm100_destroy(sww_ctx* c) {
   cudaFree(s->tw_y);
   cudaFree(s->tw_h);
   cudaFree(s->tw_n);
+  if (s->d_perm) cudaFree(s->d_perm);
+  if (s->d_chunks) cudaFree(s->d_chunks);
+  if (s->d_bin_chunk) cudaFree(s->d_bin_chunk);
   delete s;
   c->sm100 = nullptr;
 }
@@ -1129,8 +1183,11 @@ static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO
   int hist = (mode == 2) ? (N / 2 / 32) * A.n_g * c->g.n_k : 0;
   size_t smem = col_smem(N, hist);
   long long items = (long long)bO.K * (Kzp / FFT_TZ);
-  int grid = grid_for_items(items, occ_for(smem));
+  const int nrows = (mode == 2 && A.nrows > 1) ? A.nrows : 1;
+  int grid = grid_for_items(items * nrows, occ_for(smem));
+  if (nrows > 1) grid = std::max(1, grid / nrows) * nrows;
   if (mode == 2) {
+    SWW_REQUIRE(nrows <= 16, "F3 bin: too many rows in a batch");
     SWW_REQUIRE((size_t)grid * A.n_g * c->g.n_k <= c->partial_elems, "F3 bin: partial buffer too small");
     A.partial = c->d_partial;
     A.counter = c->d_counter;
@@ -1141,6 +1198,9 @@ static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO
   } else if (mode == 1) {
     SWW_TRY(set_smem(pass_f3_kernel<N, AX, 1>, smem));
     pass_f3_kernel<N, AX, 1><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);
+  } else if (mode == 3) {
+    SWW_TRY(set_smem(pass_f3_kernel<N, AX, 3>, smem));
+    pass_f3_kernel<N, AX, 3><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);
   } else {
     SWW_TRY(set_smem(pass_f3_kernel<N, AX, 2>, smem));
     pass_f3_kernel<N, AX, 2><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);
@@ -1217,8 +1277,24 @@ static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
   }
+  if (mode == 2 && nb > 1 && Ab && nb <= SWW_MAX_L) {
+    // one launch bins all rows of the batch against the shared G maps
+    SWW_PROF(c, "fft.F3 last-forward+bin");
+    F3Args Ax = Ab[0];
+    Ax.nrows = nb;
+    Ax.row_pstride = pstride;
+    for (int b = 0; b < nb; ++b) Ax.out_rows[b] = Ab[b].out_row;
+    const double2* Psrc = s->P;
+#define CALL(NN, AA) launch_f3<NN, AA>(c, s, mode, b2, b1, Kz, Kzp, Ax, Psrc)
+    DISPATCH_AX(n2, a2, CALL)
+#undef CALL
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
   for (int b = 0; b < nb; ++b) {
-    SWW_PROF(c, mode == 2 ? "fft.F3 last-forward+bin" : (mode == 1 ? "fft.F3 last-forward+ylm" : "fft.F3 last-forward+store"));
+    SWW_PROF(c, mode == 2 ? "fft.F3 last-forward+bin"
+                          : (mode == 1 ? "fft.F3 last-forward+ylm" : (mode == 3 ? "fft.F3 last-fwd+shell-store" : "fft.F3 last-forward+store")));
     const F3Args& Ax = Ab ? Ab[b] : A;
     const double2* Psrc = s->P + (long long)b * pstride;
 #define CALL(NN, AA) launch_f3<NN, AA>(c, s, mode, b2, b1, Kz, Kzp, Ax, Psrc)
@@ -1443,6 +1519,250 @@ int sww_sm100_inverse_multi(sww_ctx* c, int nb, const GatherArgs* gas, int box_s
 
 size_t sww_sm100_qstack_bytes(const sww_ctx* c, int nb) {
   return (size_t)nb * c->g.nx * c->g.ny * up8(c->g.Kz) * sizeof(double2);
+}
+
+// ------------------------------------------------------------------------------------------
+// Shell-ordered spectra.  The Fisher row F[alpha][(l', b)] = scale * sum_{k in b} w Re[conj(U_alpha) G_l'] needs a
+// k-shell reduction of every transformed row.  Instead of binning inside the last forward pass, that pass
+// scatters the modes that fall in a bin into SHELL ORDER -- sorted by (bin, outer index, inner index, iz), a
+// static permutation of the output box -- so that bin b of every row is one contiguous segment, and the
+// reduction becomes a set of segmented dot products with perfectly coalesced reads (shell_dot_kernel), against
+// G maps sorted once per realisation with the half-spectrum weight folded in.
+// ------------------------------------------------------------------------------------------
+#define SHELL_CH 4096      // modes per chunk (a chunk never straddles a bin)
+#define SHELL_RT 8         // rows per CTA
+
+static int build_shell_order(sww_ctx* c, Sm100State* s) {
+  if (s->shell_state != 0) return 0;
+  const Geo& g = c->g;
+  AxisPlan pl = make_plan(g, box_axis(g.nx, g.bx), box_axis(g.ny, g.by));
+  const int a1 = pl.x_first_fwd ? 0 : 1, a2 = 1 - a1;
+  const BoxAxis bO = a1 == 0 ? pl.bx : pl.by, bA = a2 == 0 ? pl.bx : pl.by;
+  const int Kz = g.Kz, Kzp = up8(Kz);
+  std::vector<uint8_t> bm((size_t)g.nx * g.ny * g.nzh);
+  SWW_CUDA(cudaMemcpy(bm.data(), g.binmap, bm.size(), cudaMemcpyDeviceToHost));
+  std::vector<long long> cnt(g.n_k + 1, 0);
+  auto cell_of = [&](int jo, int ja, int iz) -> size_t {
+    int io = bO.idx(jo), ia = bA.idx(ja);
+    int ix = a2 == 0 ? ia : io, iy = a2 == 0 ? io : ia;
+    return ((size_t)ix * g.ny + iy) * g.nzh + iz;
+  };
+  for (int jo = 0; jo < bO.K; ++jo)
+    for (int ja = 0; ja < bA.K; ++ja)
+      for (int iz = 0; iz < Kz; ++iz) {
+        int b = bm[cell_of(jo, ja, iz)];
+        if (b != SWW_NO_BIN) cnt[b]++;
+      }
+  std::vector<long long> off(g.n_k + 1, 0);
+  for (int b = 0; b < g.n_k; ++b) off[b + 1] = off[b] + cnt[b];
+  const long long S = off[g.n_k];
+  if (S <= 0 || S >= (1LL << 31)) {
+    s->shell_state = -1;
+    return 0;
+  }
+  std::vector<int> perm((size_t)bO.K * bA.K * Kzp, -1);
+  std::vector<long long> cur(off.begin(), off.end() - 1);
+  for (int jo = 0; jo < bO.K; ++jo)
+    for (int ja = 0; ja < bA.K; ++ja)
+      for (int iz = 0; iz < Kz; ++iz) {
+        int b = bm[cell_of(jo, ja, iz)];
+        if (b != SWW_NO_BIN) perm[((size_t)jo * bA.K + ja) * Kzp + iz] = (int)cur[b]++;
+      }
+  std::vector<int4> chunks;
+  std::vector<int> bin_chunk(g.n_k + 1, 0);
+  for (int b = 0; b < g.n_k; ++b) {
+    bin_chunk[b] = (int)chunks.size();
+    for (long long st = off[b]; st < off[b + 1]; st += SHELL_CH) {
+      long long len = std::min<long long>(SHELL_CH, off[b + 1] - st);
+      chunks.push_back(make_int4((int)st, (int)len, b, 0));
+    }
+  }
+  bin_chunk[g.n_k] = (int)chunks.size();
+  SWW_CUDA(cudaMalloc(&s->d_perm, perm.size() * sizeof(int)));
+  SWW_CUDA(cudaMemcpy(s->d_perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  SWW_CUDA(cudaMalloc(&s->d_chunks, std::max<size_t>(1, chunks.size()) * sizeof(int4)));
+  SWW_CUDA(cudaMemcpy(s->d_chunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  SWW_CUDA(cudaMalloc(&s->d_bin_chunk, bin_chunk.size() * sizeof(int)));
+  SWW_CUDA(cudaMemcpy(s->d_bin_chunk, bin_chunk.data(), bin_chunk.size() * sizeof(int), cudaMemcpyHostToDevice));
+  s->S = S;
+  s->n_chunks = (int)chunks.size();
+  s->shell_state = 1;
+  return 0;
+}
+
+long long sww_sm100_shell_cells(sww_ctx* c) {
+  if (!sww_fft_sm100_supported(c) || sww_fft_sm100_init(c) != 0) return 0;
+  Sm100State* s = (Sm100State*)c->sm100;
+  if (build_shell_order(c, s) != 0 || s->shell_state != 1) return 0;
+  return s->S;
+}
+int sww_sm100_shell_chunks(sww_ctx* c) {
+  Sm100State* s = (Sm100State*)c->sm100;
+  return s && s->shell_state == 1 ? s->n_chunks : 0;
+}
+
+// Gs[q][perm] = w(iz) * G_q[cell]
+__global__ void shell_sort_g_kernel(Geo g, BoxAxis bA, BoxAxis bO, int ax, int Kz, int Kzp, const int* __restrict__ perm,
+                                    long long S, F3Args A, double2* __restrict__ Gs) {
+  const long long total = (long long)bO.K * bA.K * Kzp;
+  const bool nz_even = (g.nz % 2) == 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = perm[i];
+    if (p < 0) continue;
+    const int iz = (int)(i % Kzp);
+    const long long r = i / Kzp;
+    const int ja = (int)(r % bA.K), jo = (int)(r / bA.K);
+    const int ia = bA.idx(ja), io = bO.idx(jo);
+    const long long cell = (ax == 0 ? (long long)ia * g.ny + io : (long long)io * g.ny + ia) * g.nzh + iz;
+    const double w = (iz == 0 || (nz_even && iz == g.nz / 2)) ? 1.0 : 2.0;
+    for (int q = 0; q < A.n_g; ++q) {
+      double2 v = A.G[q][cell];
+      Gs[(long long)q * S + p] = make_double2(w * v.x, w * v.y);
+    }
+  }
+}
+
+int sww_sm100_shell_sort_g(sww_ctx* c, const double2* const* G, int n_g, double2* Gs) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  SWW_REQUIRE(s->shell_state == 1, "shell order not available");
+  SWW_PROF(c, "shell.sort G");
+  const Geo& g = c->g;
+  AxisPlan pl = make_plan(g, box_axis(g.nx, g.bx), box_axis(g.ny, g.by));
+  const int a1 = pl.x_first_fwd ? 0 : 1, a2 = 1 - a1;
+  const BoxAxis bO = a1 == 0 ? pl.bx : pl.by, bA = a2 == 0 ? pl.bx : pl.by;
+  F3Args A = {};
+  for (int q = 0; q < n_g; ++q) A.G[q] = G[q];
+  A.n_g = n_g;
+  shell_sort_g_kernel<<<SMS * 8, 256, 0, c->stream>>>(g, bA, bO, a2, g.Kz, up8(g.Kz), s->d_perm, s->S, A, Gs);
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// partial[(chunk * R + r) * 3 + q] = sum_{i in chunk} Re[conj(Us[r][i]) Gs[q][i]]
+// block = chunk * ntile + tile (tile fastest: the CTAs sharing a chunk's G segment run together -> L2 hits)
+__global__ void __launch_bounds__(256)
+shell_dot_kernel(const double2* __restrict__ Us, int R, long long S, const double2* __restrict__ Gs, int n_g,
+                 const int4* __restrict__ chunks, int ntile, double* __restrict__ partial) {
+  __shared__ double red[8][SHELL_RT * 3];
+  const int chunk = blockIdx.x / ntile, tile = blockIdx.x - chunk * ntile;
+  const int4 ch = chunks[chunk];
+  const int r0 = tile * SHELL_RT;
+  const int nr = min(SHELL_RT, R - r0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double acc[SHELL_RT][3];
+#pragma unroll
+  for (int r = 0; r < SHELL_RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 0.0;
+  const double2* __restrict__ Up = Us + (long long)r0 * S + ch.x;
+  const double2* __restrict__ Gp = Gs + ch.x;
+  for (int i = tid; i < ch.y; i += 256) {
+    double2 gq[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) gq[q] = q < n_g ? Gp[(long long)q * S + i] : make_double2(0.0, 0.0);
+    double2 u[SHELL_RT];
+#pragma unroll
+    for (int r = 0; r < SHELL_RT; ++r) u[r] = r < nr ? Up[(long long)r * S + i] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int r = 0; r < SHELL_RT; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc[r][q] += u[r].x * gq[q].x + u[r].y * gq[q].y;
+  }
+#pragma unroll
+  for (int r = 0; r < SHELL_RT; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double v = acc[r][q];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) red[warp][r * 3 + q] = v;
+    }
+  __syncthreads();
+  if (tid < SHELL_RT * 3) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][tid];
+    const int r = tid / 3, q = tid - 3 * r;
+    if (r < nr) partial[((long long)chunk * R + r0 + r) * 3 + q] = v;
+  }
+}
+
+// F row of (local row r): shell ka0 + r / n_l, multipole r % n_l;  F[row][q * n_k + b] = scale * sum of the bin's chunks
+__global__ void shell_dot_reduce_kernel(const double* __restrict__ partial, int R, int n_g, int n_k, int n_l, int ka0,
+                                        const int* __restrict__ bin_chunk, double scale, double* __restrict__ F) {
+  const int total = R * n_g * n_k;
+  const int n_b = n_k * n_l;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx % n_k, q = (idx / n_k) % n_g, r = idx / (n_k * n_g);
+    double v = 0.0;
+    for (int ch = bin_chunk[b]; ch < bin_chunk[b + 1]; ++ch) v += partial[((long long)ch * R + r) * 3 + q];
+    const int ka = ka0 + r / n_l, l_i = r % n_l;
+    F[(long long)(l_i * n_k + ka) * n_b + q * n_k + b] = v * scale;
+  }
+}
+
+int sww_sm100_shell_dot(sww_ctx* c, const double2* Us, int R, const double2* Gs, int n_g, double scale, double* partial,
+                        double* F, int n_l, int ka0) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  SWW_REQUIRE(s->shell_state == 1 && R >= 1 && n_g >= 1 && n_g <= 3, "shell_dot: bad arguments");
+  const int ntile = (R + SHELL_RT - 1) / SHELL_RT;
+  {
+    SWW_PROF(c, "shell.dot rows x G");
+    shell_dot_kernel<<<(unsigned)((long long)s->n_chunks * ntile), 256, 0, c->stream>>>(Us, R, s->S, Gs, n_g, s->d_chunks, ntile,
+                                                                                       partial);
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+  }
+  {
+    SWW_PROF(c, "shell.dot reduce");
+    shell_dot_reduce_kernel<<<sww_grid_for((long long)R * n_g * c->g.n_k, 128), 128, 0, c->stream>>>(
+        partial, R, n_g, c->g.n_k, n_l, ka0, s->d_bin_chunk, scale, F);
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// the n_l rows of shell `shell`: I1 -> I2 -> Z(c2r * wmap * r2c) -> F2 -> F3(store in shell order) into Us_rows[b * S]
+int sww_sm100_pk_rows_store(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,
+                            double2* Us_rows) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  SWW_REQUIRE(nrows >= 1 && nrows <= SWW_MAX_L && s->shell_state == 1, "pk_rows_store: %d rows", nrows);
+  const Geo& g = c->g;
+  AxisPlan pli = make_plan(g, box_axis(g.nx, s->shell_bx[shell]), box_axis(g.ny, s->shell_by[shell]));
+  int Kzi = s->shell_bz[shell] + 1, Kzpi = up8(Kzi);
+  AxisPlan plo = make_plan(g, box_axis(g.nx, g.bx), box_axis(g.ny, g.by));
+  int Kzo = g.Kz, Kzpo = up8(Kzo);
+  const long long qstride = (long long)g.nx * g.ny * Kzpi, rstride = (long long)g.nx * g.ny * Kzpo;
+  SWW_REQUIRE((size_t)rstride * nrows <= s->buf_elems, "pk_rows: pass buffers too small for %d planes", nrows);
+  GatherArgs ga[SWW_MAX_L] = {};
+  for (int b = 0; b < nrows; ++b) {
+    ga[b].src = F[b];
+    ga[b].shell = shell;
+  }
+  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride));
+  ZArgs Z = {};
+  Z.Q = s->Q;
+  Z.Kz_in = Kzi;
+  Z.Kzp_in = Kzpi;
+  Z.R = s->R;
+  Z.Kz_out = Kzo;
+  Z.Kzp_out = Kzpo;
+  Z.wmap = wmap;
+  Z.scale = inv_scale;
+  Z.lm = -1;
+  Z.nb = nrows;
+  Z.q_stride = qstride;
+  Z.r_stride = rstride;
+  SWW_TRY(run_z(c, s, true, true, Z));
+  F3Args Ab[SWW_MAX_L] = {};
+  for (int b = 0; b < nrows; ++b) {
+    Ab[b].perm = s->d_perm;
+    Ab[b].sorted_dst = Us_rows + (long long)b * s->S;
+  }
+  return run_forward_cols(c, s, plo, Kzo, Kzpo, 3, Ab[0], nrows, rstride, Ab);
 }
 
 int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,

@@ -9,6 +9,8 @@
 // (the reference materialises 2 n_b maps or spills them to disk: pk/compute_pk_randoms.py:220-274).
 #include <cmath>
 
+#include <algorithm>
+#include <cstdlib>
 #include "sww_internal.cuh"
 
 static inline double lcoef(int l_i) { return 4.0 * M_PI / (4.0 * l_i + 1.0); }
@@ -49,6 +51,10 @@ int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool wi
 struct PkFisherBufs {
   double *nCa, *nAa, *WS, *tmp, *row;
   double2 *FC[SWW_MAX_L], *G[SWW_MAX_L], *X;
+  // shell-ordered rows (sm_100a backend): Us[shell_rows][S], Gs[n_l][S], partial sums of the segmented products
+  double2 *Us = nullptr, *Gs = nullptr;
+  double* sp = nullptr;
+  long long S = 0;
 };
 
 static void pk_fisher_layout(sww_ctx* c, Arena& ar, PkFisherBufs& b) {
@@ -64,6 +70,26 @@ static void pk_fisher_layout(sww_ctx* c, Arena& ar, PkFisherBufs& b) {
   b.nAa = ar.alloc<double>(N);
   b.WS = ar.alloc<double>(N);
   b.row = ar.alloc<double>((size_t)c->n_l * c->g.n_k);
+  if (c->fft_backend == 1 && !getenv("SWW_NO_SHELL_STORE")) {
+    const long long S = sww_sm100_shell_cells(c);
+    if (S > 0 && c->shell_rows < 0) {
+      // rows kept in shell order between two segmented-product launches: all n_b of them if they fit the budget
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      double budget = (c->tight_ws ? 0.10 : 0.20) * (double)total_b;
+      if (const char* e = getenv("SWW_SHELL_STORE_GB")) budget = atof(e) * 1e9;
+      long long rows = (long long)(budget / ((double)S * sizeof(double2)));
+      const int n_b = c->n_l * c->g.n_k;
+      if (rows > n_b) rows = n_b;
+      c->shell_rows = (int)(rows / c->n_l) * c->n_l;
+    }
+    if (S > 0 && c->shell_rows >= c->n_l) {
+      b.S = S;
+      b.Us = ar.alloc<double2>((size_t)c->shell_rows * S);
+      b.Gs = ar.alloc<double2>((size_t)c->n_l * S);
+      b.sp = ar.alloc<double>((size_t)sww_sm100_shell_chunks(c) * c->shell_rows * 3);
+    }
+  }
 }
 
 struct PkDataBufs {
@@ -168,6 +194,22 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
     c->n_fft++;
     // Fisher rows: I1 -> I2 -> Z(c2r * nW * r2c) -> F2 -> F3(bin); nothing but the row leaves the chip
     // the n_l rows of one k bin share the shell box and the weight map: one batched chain per bin
+    if (b.Us) {
+      // rows go to HBM in shell order; every block of shells ends with one segmented-product launch
+      SWW_TRY(sww_sm100_shell_sort_g(c, (const double2* const*)b.G, n_l, b.Gs));
+      const int spb = c->shell_rows / n_l;
+      for (int ka0 = 0; ka0 < n_k; ka0 += spb) {
+        const int nsh = std::min(spb, n_k - ka0);
+        for (int k = 0; k < nsh; ++k) {
+          SWW_TRY(sww_sm100_pk_rows_store(c, n_l, (const double2* const*)b.FC, ka0 + k, c->d_nW, 1.0 / N,
+                                          b.Us + (size_t)k * n_l * b.S));
+          c->n_fft += 2 * n_l;
+        }
+        SWW_TRY(sww_sm100_shell_dot(c, b.Us, nsh * n_l, b.Gs, n_l, 0.5 / (N * c->v_cell), b.sp, F, n_l, ka0));
+      }
+      SWW_TRY(k_symmetrise(c, F, n_b));
+      return 0;
+    }
     for (int ka = 0; ka < n_k; ++ka) {
       double* rows[SWW_MAX_L];
       for (int l_i = 0; l_i < n_l; ++l_i) rows[l_i] = F + (size_t)(l_i * n_k + ka) * n_b;

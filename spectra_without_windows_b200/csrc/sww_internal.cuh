@@ -121,6 +121,7 @@ struct sww_ctx {
   double* d_partial = nullptr;
   size_t partial_elems = 0;
   unsigned int* d_counter = nullptr;
+  int shell_rows = -1;   // rows of the shell-ordered store (-1: not decided yet)
   double* d_q1_scratch = nullptr;
   size_t q1_scratch_elems = 0;
   // profiling
@@ -168,6 +169,14 @@ struct F3Args {
   double* partial;
   unsigned int* counter;
   double* out_row;
+  // MODE 2 batch: nrows planes (P + r * row_pstride) binned against the same G maps in one launch; consecutive
+  // CTAs take consecutive rows of the same columns, so the G reads of rows 1.. hit in L2
+  int nrows;
+  long long row_pstride;
+  double* out_rows[SWW_MAX_L];
+  // MODE 3: store the in-shell modes in shell order (perm[box cell] = position or -1)
+  const int* perm;
+  double2* sorted_dst;
 };
 // gather description for the first inverse pass: sum of up to three compact box spectra, each kept only
 // inside its shell, times coef * Y_lm(k^)  (n_terms == 0: plain spectrum + optional shell filter)
@@ -193,6 +202,14 @@ int sww_sm100_inverse_box(sww_ctx* c, const double2* src, int filter_shell, int 
 int sww_sm100_pk_row(sww_ctx* c, const double2* F, int shell, const double* wmap, double inv_scale,
                      const double2* const* G, int n_g, double scale, double* out_row);
 // the same for nrows spectra sharing one shell (the multipoles of one k bin): the weight map is read once
+// shell-ordered Fisher rows (see "shell-ordered spectra" in fft_sm100.cu)
+long long sww_sm100_shell_cells(sww_ctx* c);          // S: modes of the output box that fall in a k bin (0: unsupported)
+int sww_sm100_shell_chunks(sww_ctx* c);
+int sww_sm100_shell_sort_g(sww_ctx* c, const double2* const* G, int n_g, double2* Gs);
+int sww_sm100_pk_rows_store(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,
+                            double2* Us_rows);
+int sww_sm100_shell_dot(sww_ctx* c, const double2* Us, int R, const double2* Gs, int n_g, double scale, double* partial,
+                        double* F, int n_l, int ka0);
 int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,
                       const double2* const* G, int n_g, double scale, double* const* out_rows);
 

@@ -202,8 +202,9 @@ class Context:
         _lib.check(self.lib.sww_profile_report(self._h, buf, len(buf)))
         out = {}
         for line in buf.value.decode().splitlines():
-            name, n, ms = line[:28].strip(), line[28:].split()[0], line[28:].split()[1]
-            out[name] = (int(n), float(ms))
+            parts = line.rsplit(None, 2)     # "<name> <launches> <ms>"
+            if len(parts) == 3:
+                out[parts[0].strip()] = (int(parts[1]), float(parts[2]))
         return out
 
     def set_fft_backend(self, backend: int):
