@@ -701,7 +701,7 @@ __device__ __forceinline__ void w_mid_stages(double2* buf, const double2* tw, in
 }
 
 template <int H, bool INV, bool FWD, bool YLM>
-__global__ void __launch_bounds__(256, (H >= 512 ? 1 : 2))
+__global__ void __launch_bounds__(256, ((H >= 512 && INV) ? 1 : 2))
 pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = 8;
@@ -716,13 +716,33 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
   double2* bufs = tabf + TF;                             // [WARPS][RW*ROWLEN (+8)]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double2* buf = bufs + warp * (RW * ROWLEN + 8);
+  // fused variant: the complex input rows of the NEXT plane stream into a second per-warp buffer (cp.async)
+  // while the current plane is transformed, so no row waits on a DRAM round trip
+  constexpr bool PREF = INV && FWD;
+  double2* inb = PREF ? bufs + WARPS * (RW * ROWLEN + 8) + warp * (RW * ROWLEN + 8) : buf;
   for (int i = tid; i <= H; i += 256) twn[i] = twn_g[i];
   w_fill_tab<H, false, 0>(tabi, twh_g, tid, 256);
   w_fill_tab<H, true, 0>(tabf, twh_g, tid, 256);
   __syncthreads();
   const long long ngroups = (long long)g.nx * g.ny / RW;
+  if (PREF) {
+    const long long g0 = (long long)blockIdx.x * WARPS + warp;
+    if (g0 < ngroups) {
+      for (int rho = 0; rho < RW; ++rho) {
+        const double2* src = A.Q + (g0 * RW + rho) * A.Kzp_in;
+        double2* row = inb + rho * ROWLEN;
+        for (int k = lane; k < A.Kz_in; k += 32) {
+          unsigned sa = (unsigned)__cvta_generic_to_shared(row + zpad(k));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
+  }
   for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * WARPS) {
     const long long row0 = grp * RW;
+    const int nfb_all = (INV && FWD && A.nb > 1) ? A.nb : 1;
+    int cur_fb = 0;
     double2 u[IPS][SE];
     // early prefetch of the weights only where the registers allow it: not with 16 values per lane
     // (H = 512) and not in the batched inverse-only variant (which carries an accumulator)
@@ -739,9 +759,23 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
       }
     }
     // inverse transform of the rows of one plane -> registers u (outputs at m = bi + r*BPS)
+    auto prefetch_rows = [&](const double2* __restrict__ Qbase, long long r0) {
+      for (int rho = 0; rho < RW; ++rho) {
+        const double2* src = Qbase + (r0 + rho) * A.Kzp_in;
+        double2* row = inb + rho * ROWLEN;
+        for (int k = lane; k < A.Kz_in; k += 32) {
+          unsigned sa = (unsigned)__cvta_generic_to_shared(row + zpad(k));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
     auto do_inverse = [&](const double2* __restrict__ Qbase) {
       // 1. complex input rows -> buffer (natural positions, padded)
       __syncwarp();
+      if (PREF) {
+        asm volatile("cp.async.wait_group 0;\n" ::);
+      } else
       for (int rho = 0; rho < RW; ++rho) {
         const double2* src = Qbase + (row0 + rho) * A.Kzp_in;
         double2* row = buf + rho * ROWLEN;
@@ -765,7 +799,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 #pragma unroll
         for (int s = 0; s < IPT; ++s) {
           const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
-          const double2* row = buf + rho * ROWLEN;
+          const double2* row = inb + rho * ROWLEN;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int k = bi + r * BPR, hk = H - k;
@@ -788,6 +822,12 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
           dftR<R, -1>(y[s]);
         }
         __syncwarp();
+        if (PREF) {
+          // the staging buffer is free again: start the copy of the next plane of this warp
+          const bool wrap = cur_fb + 1 >= nfb_all;
+          const long long ngrp = wrap ? grp + (long long)gridDim.x * WARPS : grp;
+          if (ngrp < ngroups) prefetch_rows(A.Q + (wrap ? 0LL : (long long)(cur_fb + 1) * A.q_stride), ngrp * RW);
+        }
 #pragma unroll
         for (int s = 0; s < IPT; ++s) {
           const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
@@ -810,8 +850,9 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
       }
     };
     // fused variant: nb > 1 transforms nb planes per weight load (the multipoles of one k bin)
-    const int nfb = (INV && FWD && A.nb > 1) ? A.nb : 1;
+    const int nfb = nfb_all;
     for (int fb = 0; fb < nfb; ++fb) {
+    cur_fb = fb;
     if (INV) {
       if (!FWD && A.nb > 1) {
         // sum of nb inverse transforms, each times Y_lm(r^) (or 1): the real-space map is written once
@@ -1310,7 +1351,7 @@ template <int H, bool INV, bool FWD, bool YLM>
 static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
   constexpr int WARPS = 8;
   size_t smem = (size_t)(H + 8 + WTabSize<H, false>::value + WTabSize<H, true>::value) * 16 +
-                (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16;
+                (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16 * ((INV && FWD) ? 2 : 1);
   long long ngroups = (long long)c->g.nx * c->g.ny / WGeo<H>::RW;
   long long ctas = (ngroups + WARPS - 1) / WARPS;
   int grid = (int)(ctas < SMS * 2 ? ctas : SMS * 2);

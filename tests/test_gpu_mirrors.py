@@ -47,5 +47,11 @@ def test_mirror_call_surface(world):
         assert relerr(maps[i], np.real(ref[i])) < 1e-12
     one = cp.applyC_alpha_single(x, S.nbar, MAS, Y, k_grids, r_grids, S.v_cell, filt, k_norm, 2, 3, include_pix=False)
     assert relerr(one, np.real(S.applyC_alpha(x)[2 * n_k + 3])) < 1e-12
+    # include_pix = True branches (src/covariances_pk.py:122, :155-162)
+    got = cp.applyCinv_fkp(x, S.nbar, MAS, S.v_cell, w.shot_fac, include_pix=True)
+    assert relerr(got, orc.applyCinv_fkp(x, S.nbar, S.v_cell, w.shot_fac, MAS=MAS)) < 1e-12
+    got = cp.applyN(x, S.nbar, MAS, S.v_cell, w.shot_fac, include_pix=True)
+    assert relerr(got, orc.applyN(x, S.nbar, S.v_cell, w.shot_fac, MAS=MAS)) < 1e-12
+    # ML weights are not built (dead code in the shipped reference): loud failure, never a CPU fallback
     with pytest.raises(Exception):
-        cp.applyCinv_fkp(x, S.nbar, MAS, S.v_cell, w.shot_fac, include_pix=True)
+        cp.applyCinv(x)
