@@ -18,6 +18,7 @@
 // real-space map u_alpha and its weighted transform never touch HBM.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "fft_core.cuh"
@@ -1034,6 +1035,181 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused z pass for nz = 512 (H = 256 = 16 x 16): c2r * wmap * r2c with TWO exchanges through shared
+// memory per row instead of the eleven of the generic warp-per-row kernel above, which is bound by the
+// 128 B/clk shared-memory crossbar, not by the FP64 pipe.
+//   * a warp owns two rows; lane = (row rho, butterfly b < 16) holds 16 complex values of its row;
+//   * both half-length transforms are two radix-16 stages: stage 0 straight from registers (inverse: the
+//     Hermitian pre-processing of the staged input row; forward: the weighted outputs of the inverse),
+//     one exchange (store at 16 b + r, load at b + 16 r, pitch 17 -> conflict-free), stage 1 with the
+//     inter-stage twiddles W_256^(b r) built from four lane-constant registers (w, w^2, w^4, w^8);
+//   * the r2c post-processing pairs V[k] with V[H-k], which lives in lane 16 - b at register 15 - r:
+//     one shuffle per output, no pass through shared memory; only k < Kz_out <= 128 is produced (r < 8);
+//   * input rows of the next plane stream into a per-warp staging buffer with cp.async.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+template <int DIR>
+__device__ __forceinline__ void twiddle16(double2* u, double2 w1, double2 w2, double2 w4, double2 w8) {
+  if (DIR < 0) {
+    w1.y = -w1.y;
+    w2.y = -w2.y;
+    w4.y = -w4.y;
+    w8.y = -w8.y;
+  }
+#pragma unroll
+  for (int j = 8; j < 16; ++j) u[j] = c_mul(u[j], w8);
+  u[1] = c_mul(u[1], w1);
+  u[9] = c_mul(u[9], w1);
+  u[2] = c_mul(u[2], w2);
+  u[10] = c_mul(u[10], w2);
+  {
+    const double2 w3 = c_mul(w1, w2);
+    u[3] = c_mul(u[3], w3);
+    u[11] = c_mul(u[11], w3);
+    const double2 w7 = c_mul(w3, w4);
+    u[7] = c_mul(u[7], w7);
+    u[15] = c_mul(u[15], w7);
+  }
+  u[4] = c_mul(u[4], w4);
+  u[12] = c_mul(u[12], w4);
+  {
+    const double2 w5 = c_mul(w1, w4);
+    u[5] = c_mul(u[5], w5);
+    u[13] = c_mul(u[13], w5);
+  }
+  {
+    const double2 w6 = c_mul(w2, w4);
+    u[6] = c_mul(u[6], w6);
+    u[14] = c_mul(u[14], w6);
+  }
+}
+
+#define Z16_H 256
+#define Z16_ROW 272   // 256 + one pad slot per 16
+
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g, int in_len) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = Z16_H, ROW = Z16_ROW;
+  double2* twn = reinterpret_cast<double2*>(smem_raw);   // [H + 8]  exp(-2 pi i j / nz), j <= H
+  double2* bufs = twn + (H + 8);                         // [WARPS][2 * ROW] exchange buffers
+  double2* inbs = bufs + WARPS * 2 * ROW;                // [WARPS][2 * in_len] staged input rows
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rho = lane >> 4, b = lane & 15;
+  double2* buf = bufs + warp * 2 * ROW + rho * ROW;
+  double2* inw = inbs + warp * 2 * in_len;
+  const double2* inb = inw + rho * in_len;
+  for (int i = tid; i <= H; i += WARPS * 32) twn[i] = twn_g[i];
+  const double2 w1 = twh_g[b], w2 = twh_g[2 * b], w4 = twh_g[4 * b], w8 = twh_g[(8 * b) & (H - 1)];
+  __syncthreads();
+  const long long ngroups = (long long)g.nx * g.ny / 2;
+  const long long gstep = (long long)gridDim.x * WARPS;
+  const int nfb = A.nb > 1 ? A.nb : 1;
+  const int Kz_in = A.Kz_in, Kz_out = A.Kz_out;
+  const double half = 0.5 * A.scale;
+  auto prefetch_rows = [&](const double2* __restrict__ Qbase, long long r0) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const double2* src = Qbase + (r0 + rr) * A.Kzp_in;
+      double2* row = inw + rr * in_len;
+      for (int k = lane; k < Kz_in; k += 32) {
+        unsigned sa = (unsigned)__cvta_generic_to_shared(row + k);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  long long grp = (long long)blockIdx.x * WARPS + warp;
+  if (grp < ngroups) prefetch_rows(A.Q, grp * 2);
+  for (; grp < ngroups; grp += gstep) {
+    const long long row = grp * 2 + rho;
+    const double* __restrict__ wrow = A.wmap + row * g.nz + 2 * b;
+    // the weights of this row pair are needed after the inverse transform of every plane: pull them towards L2 now
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + lane * 16));
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + 512 + lane * 16));
+    for (int fb = 0; fb < nfb; ++fb) {
+      double2 u[16];
+      // ---- inverse: Hermitian pre-processing of the staged row -> stage 0 (radix 16, no twiddles)
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        u[r] = make_double2(0.0, 0.0);
+        if (16 * r < Kz_in || 241 - 16 * r < Kz_in) {   // warp-uniform: some k or H-k of this block is kept
+          const int k = b + 16 * r, hk = H - k;
+          if (k < Kz_in || hk < Kz_in) {
+            double2 zk = (k < Kz_in) ? inb[k] : make_double2(0.0, 0.0);
+            double2 zh = (hk < Kz_in) ? inb[hk] : make_double2(0.0, 0.0);
+            if (k == 0) {
+              zk.y = 0.0;
+              zh.y = 0.0;
+            }
+            const double2 a = make_double2(zk.x + zh.x, zk.y - zh.y);
+            const double2 d = make_double2(zk.x - zh.x, zk.y + zh.y);
+            double2 w = twn[k];
+            w.y = -w.y;
+            const double2 bb = c_mul(d, w);
+            u[r] = make_double2(a.x - bb.y, a.y + bb.x);
+          }
+        }
+      }
+      __syncwarp();
+      {
+        // the staging buffer is free again: start the copy of the next plane of this warp
+        const bool wrap = fb + 1 >= nfb;
+        const long long ngrp = wrap ? grp + gstep : grp;
+        if (ngrp < ngroups) prefetch_rows(A.Q + (wrap ? 0LL : (long long)(fb + 1) * A.q_stride), ngrp * 2);
+      }
+      dft16<-1>(u);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+      twiddle16<-1>(u, w1, w2, w4, w8);
+      dft16<-1>(u);
+      // ---- real-space step: x[2m], x[2m+1] at m = b + 16 r, times the weight map
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 wv = *reinterpret_cast<const double2*>(wrow + 32 * r);
+        u[r].x *= wv.x;
+        u[r].y *= wv.y;
+      }
+      // ---- forward: stage 0 from the same registers, one exchange, stage 1
+      dft16<1>(u);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+      twiddle16<1>(u, w1, w2, w4, w8);
+      dft16<1>(u);
+      // ---- r2c post-processing: T[k] = 1/2 (V[k] + conj V[H-k]) - i/2 e^{-2 pi i k/nz} (V[k] - conj V[H-k])
+      double2* __restrict__ dst = A.R + (long long)fb * A.r_stride + row * A.Kzp_out;
+      const int src_lane = (rho << 4) | ((16 - b) & 15);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        double2 v2;
+        v2.x = __shfl_sync(0xffffffffu, u[15 - r].x, src_lane);
+        v2.y = __shfl_sync(0xffffffffu, u[15 - r].y, src_lane);
+        if (b == 0) v2 = u[(16 - r) & 15];
+        const int k = b + 16 * r;
+        if (16 * r < Kz_out && k < Kz_out) {
+          const double2 v1 = u[r];
+          const double2 ev = make_double2(half * (v1.x + v2.x), half * (v1.y - v2.y));
+          const double2 dv = make_double2(half * (v1.x - v2.x), half * (v1.y + v2.y));
+          const double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);
+          dst[k] = make_double2(ev.x + od.x, ev.y + od.y);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct Sm100State {
@@ -1360,12 +1536,34 @@ static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
   return 0;
 }
 
+// two-exchange fused z pass (nz = 512, outputs below nz/4): see pass_z16_fused_kernel
+static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 8;
+  const int in_len = up8(A.Kz_in);
+  const size_t smem = (size_t)(Z16_H + 8 + WARPS * 2 * Z16_ROW + WARPS * 2 * in_len) * sizeof(double2);
+  const long long ngroups = (long long)c->g.nx * c->g.ny / 2;
+  const long long ctas = (ngroups + WARPS - 1) / WARPS;
+  const int per_sm = smem + 1024 <= (227 * 1024) / 2 ? 2 : 1;
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm);
+  SWW_TRY(set_smem(pass_z16_fused_kernel<WARPS, 2>, smem));
+  pass_z16_fused_kernel<WARPS, 2><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, in_len);
+  return 0;
+}
+
 static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   SWW_PROF(c, inv && fwd ? "fft.Z c2r*w*r2c fused" : (inv ? "fft.Z c2r" : "fft.Z r2c"));
   A.ymaps = c->ylm_maps;
   A.N = c->g.N;
   const int H = c->g.nz / 2;
   const bool ylm = A.lm >= 0;
+  const bool no_z16 = getenv("SWW_NO_Z16") != nullptr;   // A/B switch (tests, profiling)
+  if (inv && fwd && !ylm && H == Z16_H && A.wmap && A.Kz_out <= 128 && A.Kz_in <= Z16_H + 1 && !no_z16 &&
+      (c->g.nx * (long long)c->g.ny) % 2 == 0) {
+    SWW_TRY(launch_z16(c, s, A));
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define M(HH)                                                      \
   if (inv && fwd) {                                                \
     SWW_REQUIRE(!ylm, "fused z pass has no Y_lm variant");        \

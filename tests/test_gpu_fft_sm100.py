@@ -130,3 +130,32 @@ def test_fused_chains_agree_with_cufft_backend(eng, shape):
     assert relerr(F1.cpu().numpy(), F0) < 1e-11
     assert relerr(q1.cpu().numpy(), q0) < 1e-11
     ctx.close()
+
+
+def test_fused_z_pass_nz512_two_exchange_kernel(eng):
+    """nz = 512 takes the two-exchange fused z pass (pass_z16_fused_kernel): it must agree with the generic
+    warp-per-row kernel (SWW_NO_Z16=1) and with the cuFFT backend to round-off, and be deterministic."""
+    import os
+    from spectra_without_windows_b200 import synthetic as syn
+    grid, box, bc = (64, 64, 512), (1280.0, 1408.0, 5120.0), (1700.0, 60.0, -45.0)
+    mesh = eng.Mesh(box, grid, bc, 0.0, 0.12, 0.02, 4)
+    ctx = eng.Context(mesh, 0, ("ops", "pk_fisher"))
+    ctx.set_fft_backend(1)
+    nbar_r = syn.survey_nbar(box, grid, bc, n0=6e-3)
+    nbar_A = ctx.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)
+    a = np.random.default_rng(7).normal(size=grid) * np.sqrt(nbar_A)
+    F1, q1 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+    F1b, _ = ctx.pk_fisher(a)
+    assert np.array_equal(F1, F1b.cpu().numpy())
+    own0, _ = ctx.launch_counts()
+    os.environ["SWW_NO_Z16"] = "1"
+    try:
+        F2, q2 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+    finally:
+        del os.environ["SWW_NO_Z16"]
+    ctx.set_fft_backend(0)
+    F0, q0 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+    assert np.all(np.isfinite(F1)) and np.max(np.abs(F1)) > 0
+    assert relerr(F1, F2) < 1e-12 and relerr(q1, q2) < 1e-12
+    assert relerr(F1, F0) < 1e-11 and relerr(q1, q0) < 1e-11
+    ctx.close()
