@@ -1088,7 +1088,7 @@ __device__ __forceinline__ void twiddle16(double2* u, double2 w1, double2 w2, do
 #define Z16_H 256
 #define Z16_ROW 272   // 256 + one pad slot per 16
 
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, bool WREG>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g, int in_len) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1127,8 +1127,16 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
     const long long row = grp * 2 + rho;
     const double* __restrict__ wrow = A.wmap + row * g.nz + 2 * b;
     // the weights of this row pair are needed after the inverse transform of every plane: pull them towards L2 now
-    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + lane * 16));
-    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + 512 + lane * 16));
+    // WREG: the weights of the row pair sit in registers for all planes of the group (loaded here, consumed after
+    // the first inverse transform); otherwise they are pulled towards L2 now and loaded at the point of use
+    double2 wreg[WREG ? 16 : 1];
+    if (WREG) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) wreg[WREG ? r : 0] = *reinterpret_cast<const double2*>(wrow + 32 * r);
+    } else {
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + lane * 16));
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + 512 + lane * 16));
+    }
     for (int fb = 0; fb < nfb; ++fb) {
       double2 u[16];
       // ---- inverse: Hermitian pre-processing of the staged row -> stage 0 (radix 16, no twiddles)
@@ -1173,7 +1181,7 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
       // ---- real-space step: x[2m], x[2m+1] at m = b + 16 r, times the weight map
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const double2 wv = *reinterpret_cast<const double2*>(wrow + 32 * r);
+        const double2 wv = WREG ? wreg[WREG ? r : 0] : *reinterpret_cast<const double2*>(wrow + 32 * r);
         u[r].x *= wv.x;
         u[r].y *= wv.y;
       }
@@ -1537,17 +1545,31 @@ static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
 }
 
 // two-exchange fused z pass (nz = 512, outputs below nz/4): see pass_z16_fused_kernel
-static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
-  constexpr int WARPS = 8;
+template <int WARPS, int MINB, bool WREG>
+static int launch_z16_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   const int in_len = up8(A.Kz_in);
   const size_t smem = (size_t)(Z16_H + 8 + WARPS * 2 * Z16_ROW + WARPS * 2 * in_len) * sizeof(double2);
   const long long ngroups = (long long)c->g.nx * c->g.ny / 2;
   const long long ctas = (ngroups + WARPS - 1) / WARPS;
-  const int per_sm = smem + 1024 <= (227 * 1024) / 2 ? 2 : 1;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > MINB) per_sm = MINB;
+  if (per_sm < 1) per_sm = 1;
   const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm);
-  SWW_TRY(set_smem(pass_z16_fused_kernel<WARPS, 2>, smem));
-  pass_z16_fused_kernel<WARPS, 2><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, in_len);
+  SWW_TRY((set_smem(pass_z16_fused_kernel<WARPS, MINB, WREG>, smem)));
+  pass_z16_fused_kernel<WARPS, MINB, WREG><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, in_len);
   return 0;
+}
+
+static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
+  const char* e = getenv("SWW_Z16_VARIANT");
+  const int v = e ? atoi(e) : 0;
+  switch (v) {
+    case 1: return launch_z16_v<8, 2, false>(c, s, A);   // 16 warps/SM, weights loaded at the point of use (exposed latency)
+    case 2: return launch_z16_v<4, 3, true>(c, s, A);    // 12 warps/SM, weights in registers (small spills)
+    case 3: return launch_z16_v<4, 4, false>(c, s, A);   // 16 warps/SM in 4-warp CTAs
+    case 4: return launch_z16_v<4, 2, true>(c, s, A);    // 8 warps/SM in 4-warp CTAs, weights in registers
+    default: return launch_z16_v<8, 1, true>(c, s, A);   // 8 warps/SM, 246 registers: the weights of a row pair stay in registers for all planes (measured fastest)
+  }
 }
 
 static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
