@@ -243,6 +243,96 @@ def pk_solve(fish, q, qbar):
     return np.inner(np.linalg.inv(fish), q - qbar)
 
 
+# ----------------------------------------------------------------------------- ML weights
+def pk_map_from_table(S: Setup, table):
+    """Fiducial multipoles on the mesh (pk/compute_pk_randoms.py:188-193): linear interpolation of the columns
+    P_0, P_2, P_4 of the `fiducial_pk` table at |k| (scipy interp1d, default kind = linear)."""
+    t = np.asarray(table, float)
+    return np.asarray([np.interp(S.k_norm, t[:, 0], t[:, 1 + i]) for i in range(S.n_l)])
+
+
+def applyS(S: Setup, x, pk_map):
+    """Signal covariance S x (src/covariances_pk.py:45-95), complex128 throughout."""
+    tmp = ift(ft(x) / S.MAS) * S.nbar if S.include_pix else x * S.nbar                 # :76-79
+    f = 0.0
+    for l_i in range(len(pk_map)):
+        f = f + 4.0 * np.pi / (4.0 * l_i + 1.0) * S.ylm_sum(tmp, l_i) * pk_map[l_i]     # :82-89
+    if S.include_pix:
+        return ift(ft(S.nbar * ift(f)) / S.MAS) / S.v_cell                             # :92-93
+    return S.nbar * ift(f) / S.v_cell
+
+
+def applyC(S: Setup, x, pk_map):
+    """C = S + N (src/covariances_pk.py:10-43)."""
+    return applyS(S, x, pk_map) + applyN(x, S.nbar, S.v_cell, S.shot_fac, MAS=S.pix)
+
+
+def applyCinv(S: Setup, pix, pk_map, max_it=100, abs_tol=1e-8, rel_tol=None, P_fkp=1e4, info=None):
+    """Preconditioned conjugate gradients for C x = pix with the FKP inverse as first guess and preconditioner
+    (src/covariances_pk.py:222-327).  The products are complex and bilinear (np.sum(r*pre_r), no conjugation), the
+    stall test runs every 10 iterations, the relative test compares sqrt(new_sum/init_sum) with rel_tol."""
+    pre = lambda m: applyCinv_fkp(m, S.nbar_weight, S.v_cell, S.shot_fac, P_fkp=P_fkp, MAS=S.pix)
+    x = pre(pix)
+    r = pix - applyC(S, x, pk_map)
+    p = pre(r)
+    C_p = applyC(S, p, pk_map)
+    pre_r = pre(r)
+    old_sum = np.sum(r * pre_r)
+    init_sum = old_sum.copy()
+    alpha = old_sum / np.sum(p * C_p)
+    save_sum = old_sum.copy()
+    n_it = 0
+    for i in range(max_it):
+        if i % 10 == 0 and i > 0:
+            if np.abs((save_sum - old_sum) / old_sum) < 0.05:
+                break
+            save_sum = old_sum
+        x = x + alpha * p
+        r = r - alpha * C_p
+        pre_r = pre(r)
+        new_sum = np.sum(r * pre_r)
+        p = pre_r + (new_sum / old_sum) * p
+        n_it = i + 1
+        if rel_tol is not None:
+            if np.sqrt(new_sum / init_sum) < rel_tol:
+                break
+        elif np.sqrt(new_sum) < abs_tol:
+            break
+        old_sum = new_sum
+        C_p = applyC(S, p, pk_map)
+        alpha = old_sum / np.sum(p * C_p)
+    if info is not None:
+        info["iterations"] = n_it
+    return x
+
+
+def pk_data_q_ml(S: Setup, diff, pk_map):
+    """q_alpha with ML weights (pk/compute_pk_data.py:194-206)."""
+    Cinv_d = applyCinv(S, diff, pk_map, rel_tol=1e-6, max_it=30)
+    C_a = S.applyC_alpha(Cinv_d, data=True)
+    return np.asarray([np.real(np.sum(Cinv_d * c)) / 2.0 for c in C_a])
+
+
+def pk_fisher_realisation_ml(S: Setup, a, pk_map):
+    """q-bar_alpha and F_ab with ML weights: pk/compute_pk_randoms.py:205-281 along its non-low_mem branch
+    (:229-241, :247-281).  The reference script itself cannot run this configuration (undefined name at :261,
+    double `del` at :278), so the golden values come from its own functions composed the same way."""
+    Cinv_a = np.real(applyCinv(S, a, pk_map, rel_tol=1e-6, max_it=30))
+    Ainv_a = a / S.nbar_A
+    N_Ainv_a = applyN(Ainv_a, S.nbar, S.v_cell, S.shot_fac, MAS=S.pix)
+    C_a_Cinv = S.applyC_alpha(Cinv_a)
+    C_a_Ainv = S.applyC_alpha(Ainv_a)
+    nb = len(C_a_Cinv)
+    fish = np.zeros((nb, nb))
+    qbar = np.zeros(nb)
+    V = np.asarray([v.ravel() for v in C_a_Ainv])
+    for i in range(nb):
+        U = applyCinv(S, C_a_Cinv[i], pk_map, rel_tol=1e-6, max_it=30)
+        qbar[i] = 0.5 * np.real(np.sum(U * N_Ainv_a))
+        fish[i] = 0.5 * np.real(V @ U.ravel())
+    return qbar, 0.5 * (fish + fish.T)
+
+
 # ----------------------------------------------------------------------------- painting
 def tsc_paint(pos, w, box, grid, box_center):
     """TSC deposit without compensation/interlacing; restates FKPCatalog.to_mesh(window='tsc')

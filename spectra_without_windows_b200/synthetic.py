@@ -194,23 +194,40 @@ monte_carlo = {mc}
 output = {out}
 
 [settings]
-weights = FKP
+weights = {weights}
 N_mc = {nmc}
 include_pix = {include_pix}
 rand_nbar = {rand_nbar}
-fiducial_pk = None
+fiducial_pk = {fiducial_pk}
 use_qbar = {use_qbar}
 nbar_unif = 1e-3
 low_mem = True
 """
 
 
-def write_world_files(w: World, root: str, use_qbar=True, N_mc=None, include_pix=False, rand_nbar=False):
+def fiducial_pk_table(k_top, n=257):
+    """Synthetic fiducial multipoles for the ML weights: columns k, P_0, P_2, P_4 like the `fiducial_pk` text file
+    of the reference (pk/compute_pk_randoms.py:188-193).  Amplitude comparable to the shot noise of the toy
+    worlds, so that the conjugate-gradient inversion of C = S + N takes several iterations."""
+    k = np.linspace(0.0, float(k_top), n)
+    P0 = 3.0e4 / (1.0 + (k / 0.02) ** 2) ** 0.6
+    P2 = 0.5 * P0 * k / (k + 0.05)
+    P4 = 0.1 * P0 * (k / (k + 0.1)) ** 2
+    return np.stack([k, P0, P2, P4], axis=1)
+
+
+def write_world_files(w: World, root: str, use_qbar=True, N_mc=None, include_pix=False, rand_nbar=False,
+                      weights="FKP"):
     """Write the .param file, the nbar map and .npz Cartesian catalogues under `root`.
     Returns the param-file path."""
     out, mc, tmp = root + "/out/", root + "/mc/", root + "/tmp/"
     for d in (out, mc, tmp):
         os.makedirs(d, exist_ok=True)
+    fid = "None"
+    if weights == "ML":
+        fid = root + "/fiducial_pk.txt"
+        k_top = 1.01 * float(np.sqrt(np.sum((np.pi * np.asarray(w.grid) / np.asarray(w.box, float)) ** 2)))
+        np.savetxt(fid, fiducial_pk_table(k_top))
     np.save(w.nbar_file(out), w.nbar_r)
     dfile, rfile = root + "/data_%d.npz", root + "/randoms.npz"
     np.savez(dfile % 1, pos=w.data["pos"], w=w.data["w"], box_center=np.asarray(w.box_center, float))
@@ -221,5 +238,6 @@ def write_world_files(w: World, root: str, use_qbar=True, N_mc=None, include_pix
                                       bk=w.bk_bins, g=w.grid, type=w.type, zmin=w.zmin, zmax=w.zmax,
                                       b=w.box, h=w.h_fid, om=w.OmegaM_fid, tmp=tmp + w.type, mc=mc, out=out,
                                       nmc=(w.N_mc if N_mc is None else N_mc), use_qbar=use_qbar,
-                                      include_pix=include_pix, rand_nbar=rand_nbar))
+                                      include_pix=include_pix, rand_nbar=rand_nbar, weights=weights,
+                                      fiducial_pk=fid))
     return pfile

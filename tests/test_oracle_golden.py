@@ -113,3 +113,50 @@ def test_param_booleans_match_reference_scripts(variant, world, golden):
     qb = orc.bk_data_q(Sb, diff, mc_maps=[(gA, tgA), (gB, tgB)], N_mc=2)
     pb = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qb)
     assert relerr(pb, g["bk_p"][:, 3:].T.ravel()) < 2e-8
+
+
+# ---- maximum-likelihood weights (src/covariances_pk.py:10-95, 222-327): restatement vs reference functions
+def _planes(m):
+    nz = m.shape[2]
+    return {"p3": m[:, :, 3], "pny": m[:, :, nz // 2], "sums": np.asarray([m.sum(), (m * m).sum(), np.abs(m).max()])}
+
+
+def _check_planes(m, g, key, tol):
+    for kk, v in _planes(np.asarray(m, dtype=np.complex128)).items():
+        assert relerr(v, g[key + "_" + kk]) < tol, (key, kk)
+
+
+@pytest.mark.parametrize("pix", [False, True])
+def test_ml_operators_match_reference_functions(pix, world, golden):
+    w, g = world("toyA"), golden("toyA_ml")
+    kmin, kmax, dk, lmax = w.pk_bins
+    S = orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax, include_pix=pix)
+    pk_map = orc.pk_map_from_table(S, g["ml_pk_table"])
+    tag = "pix" if pix else "nopix"
+    x = np.random.default_rng(5).normal(size=tuple(w.grid))
+    _check_planes(orc.applyS(S, x, pk_map), g, "ml_S_" + tag, 1e-12)
+    _check_planes(orc.applyC(S, x, pk_map), g, "ml_C_" + tag, 1e-12)
+    diff, _ = orc.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box, w.grid, w.box_center)
+    info = {}
+    Ci = orc.applyCinv(S, diff, pk_map, rel_tol=1e-6, max_it=30, info=info)
+    assert "after %d iterations" % info["iterations"] in str(g["ml_cg_log_" + tag])
+    _check_planes(Ci, g, "ml_Cinv_d_" + tag, 1e-10)
+    _check_planes(orc.applyCinv(S, diff, pk_map, abs_tol=1e-3, max_it=4), g, "ml_Cinv_d_it4_" + tag, 1e-11)
+    if not pix:
+        assert relerr(orc.pk_data_q_ml(S, diff, pk_map), g["ml_pk_q"]) < 1e-10
+
+
+def test_ml_fisher_and_spectrum(world, golden):
+    w, g = world("toyA"), golden("toyA_ml")
+    kmin, kmax, dk, lmax = w.pk_bins
+    S = orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax)
+    pk_map = orc.pk_map_from_table(S, g["ml_pk_table"])
+    qbar, F = orc.pk_fisher_realisation_ml(S, S.grf(1), pk_map)
+    assert relerr(F, g["ml_pk_fish_1"]) < 1e-10
+    assert relerr(qbar, g["ml_pk_qbar_1"]) < 1e-10
+    # the unmodified pk/compute_pk_data.py run with weights = ML on those Fisher / bias files
+    fish = 0.5 * (g["ml_pk_fish_1"] + g["ml_pk_fish_2"])
+    bias = 0.5 * (g["ml_pk_qbar_1"] + g["ml_pk_qbar_2"])
+    p = orc.pk_solve(fish, g["ml_pk_q"], bias)
+    assert relerr(p, g["ml_pk_p"][:, 1:].T.ravel()) < 2e-8
+    assert "_ML_" in str(g["ml_pk_txt_name"])
