@@ -51,7 +51,7 @@ typedef struct {
 } sww_geometry;
 
 /* workspace selectors for sww_workspace_bytes */
-enum { SWW_WS_OPS = 0, SWW_WS_PK_FISHER = 1, SWW_WS_PK_DATA = 2, SWW_WS_BK_FISHER = 3, SWW_WS_BK_DATA = 4 };
+enum { SWW_WS_OPS = 0, SWW_WS_PK_FISHER = 1, SWW_WS_PK_DATA = 2, SWW_WS_BK_FISHER = 3, SWW_WS_BK_DATA = 4, SWW_WS_PK_ML = 5 };
 
 const char* sww_last_error(void);
 int sww_abi_version(void);
@@ -129,6 +129,31 @@ int sww_grf_legacy(sww_ctx* c, uint32_t seed, sww_devptr sigma, sww_devptr out, 
 int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a, sww_devptr fish_out, sww_devptr qbar_out);
 /* q_alpha [n_b] of a painted (n_g - alpha n_r)/V_cell map.  Replaces pk/compute_pk_data.py:191-206. */
 int sww_pk_data_q(sww_ctx* c, sww_devptr diff, sww_devptr q_out);
+
+/* ---- maximum-likelihood weights (`weights = ML`; workspace selector SWW_WS_PK_ML) ----
+ * These operators work on FULL COMPLEX maps double2[nx][ny][nz], like the reference's complex128 arrays: on the
+ * Nyquist planes Y_lm(k^) P_l(k) is not Hermitian, and the imaginary parts feed back through the bilinear
+ * conjugate-gradient products, so a half-spectrum formulation would not reproduce the reference to 1e-9.
+ * Fiducial multipoles P_l(|k|) interpolated on the mesh (pk/compute_pk_randoms.py:188-193): borrowed device
+ * pointer, double[n_l][nx][ny][nz]. */
+int sww_set_fiducial_pk(sww_ctx* c, sww_devptr pk_maps);
+/* out = Op x on complex maps (x != out); include_pix as set by sww_set_include_pix.
+ *   op 0: applyS (src/covariances_pk.py:45-95)   op 1: applyN (:97-124)
+ *   op 2: applyC = S + N (:10-43)                op 3: applyCinv_fkp / applyCinv_approx / preconditioner (:126-220) */
+int sww_ml_apply(sww_ctx* c, int op, sww_devptr x, sww_devptr out);
+/* applyCinv (src/covariances_pk.py:222-327): preconditioned conjugate gradients for C x = pix, FKP inverse as
+ * first guess and preconditioner, stall test every 10 iterations.  rel_tol < 0 means rel_tol = None (the
+ * absolute test sqrt(new_sum) < abs_tol applies).  stop_reason: 1 tolerance met, 2 stalled, 0 max_it reached. */
+int sww_ml_apply_cinv(sww_ctx* c, sww_devptr pix, int max_it, double abs_tol, double rel_tol, sww_devptr out,
+                      int32_t* iterations, int32_t* stop_reason);
+/* q_alpha = 1/2 sum_x z C_,alpha z of an already C^-1-weighted REAL map z (pk/compute_pk_data.py:198-206);
+ * for the complex C^-1 d of the ML weights the caller forms q[Re z] - q[Im z] (the products are bilinear). */
+int sww_pk_q_from_cinv(sww_ctx* c, sww_devptr z, sww_devptr q_out);
+/* One realisation with ML weights -> q-bar_alpha and symmetrised F_ab: pk/compute_pk_randoms.py:205-281 along
+ * its non-low_mem branch (n_b + 1 conjugate-gradient solves with rel_tol, max_it as at :211,:240).  The reference
+ * script cannot run this configuration itself (undefined name at :261, double `del` at :278). */
+int sww_pk_fisher_realisation_ml(sww_ctx* c, sww_devptr a, int max_it, double rel_tol, sww_devptr fish_out,
+                                 sww_devptr qbar_out, int32_t* total_iterations);
 
 /* ---- B_l(k1,k2,k3) pipelines ---- */
 /* triangle list (a<=b<=c) set by the host from test_bin (bk/compute_bk_randoms.py:186-211) */

@@ -52,6 +52,11 @@ SIGNATURES = {
     "sww_grf_legacy": [ctxp, C.c_uint32, u64, u64, u64, u64],
     "sww_pk_fisher_realisation": [ctxp, u64, u64, u64],
     "sww_pk_data_q": [ctxp, u64, u64],
+    "sww_set_fiducial_pk": [ctxp, u64],
+    "sww_ml_apply": [ctxp, C.c_int, u64, u64],
+    "sww_ml_apply_cinv": [ctxp, u64, C.c_int, f64, f64, u64, C.POINTER(i32), C.POINTER(i32)],
+    "sww_pk_q_from_cinv": [ctxp, u64, u64],
+    "sww_pk_fisher_realisation_ml": [ctxp, u64, C.c_int, f64, u64, u64, C.POINTER(i32)],
     "sww_bk_set_triangles": [ctxp, C.POINTER(i32), i32],
     "sww_bk_gmaps": [ctxp, u64, C.c_int, u64, u64],
     "sww_bk_fisher_pair": [ctxp, u64, u64, u64, u64, u64, u64, u64, u64],
@@ -61,7 +66,7 @@ SIGNATURES = {
     "sww_gram_f64": [ctxp, u64, u64, i32, i32, u64, C.c_int, u64],
 }
 
-WS_OPS, WS_PK_FISHER, WS_PK_DATA, WS_BK_FISHER, WS_BK_DATA = range(5)
+WS_OPS, WS_PK_FISHER, WS_PK_DATA, WS_BK_FISHER, WS_BK_DATA, WS_PK_ML = range(6)
 
 _lib = None
 

@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "libsww.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
-SOURCES = ["ctx.cu", "kernels.cu", "fft.cu", "fft_sm100.cu", "pipelines.cu", "bk.cu", "gram.cu", "rng.cu"]
+SOURCES = ["ctx.cu", "kernels.cu", "fft.cu", "fft_sm100.cu", "pipelines.cu", "bk.cu", "gram.cu", "rng.cu", "ml.cu"]
 
 
 def _stamp(paths):

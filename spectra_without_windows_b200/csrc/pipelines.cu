@@ -122,6 +122,7 @@ static void ops_layout(sww_ctx* c, Arena& ar, OpsBufs& b) {
 }
 
 size_t sww_bk_pipeline_bytes(sww_ctx* c, int what);  // bk.cu
+size_t sww_ml_pipeline_bytes(sww_ctx* c);           // ml.cu
 
 size_t sww_pipeline_bytes(sww_ctx* c, int what) {
   Arena dry;
@@ -141,6 +142,8 @@ size_t sww_pipeline_bytes(sww_ctx* c, int what) {
     OpsBufs b;
     ops_layout(c, dry, b);
     r = dry.peak;
+  } else if (what == SWW_WS_PK_ML) {
+    r = sww_ml_pipeline_bytes(c);
   } else {
     r = sww_bk_pipeline_bytes(c, what);
   }

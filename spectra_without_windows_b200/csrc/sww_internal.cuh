@@ -110,6 +110,7 @@ struct sww_ctx {
   bool have_z2z = false;
   int fft_backend = 0;
   bool include_pix = false;
+  const double* pk_fid = nullptr;   // borrowed: fiducial P_l(|k|) on the full mesh, double[n_l][nx][ny][nz] (ML weights)
   bool tight_ws = false;   // SWW_TIGHT_WS=1: size the workspace for the selected FFT backend only
   // bk
   std::vector<int> tris;

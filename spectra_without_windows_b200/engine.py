@@ -97,7 +97,7 @@ class Mesh:
 
 
 PIPELINES = {"ops": _lib.WS_OPS, "pk_fisher": _lib.WS_PK_FISHER, "pk_data": _lib.WS_PK_DATA,
-             "bk_fisher": _lib.WS_BK_FISHER, "bk_data": _lib.WS_BK_DATA}
+             "bk_fisher": _lib.WS_BK_FISHER, "bk_data": _lib.WS_BK_DATA, "pk_ml": _lib.WS_PK_ML}
 
 
 class Context:
@@ -294,6 +294,72 @@ class Context:
         q = self.empty((self.n_b,))
         _lib.check(self.lib.sww_pk_data_q(self._h, d.data_ptr(), q.data_ptr()))
         return q
+
+    # -- maximum-likelihood weights (context created with the "pk_ml" pipeline)
+    def set_fiducial_pk(self, table):
+        """Fiducial multipoles on the mesh from the `fiducial_pk` table (columns k, P_0, P_2, ...):
+        `interp1d(pk_input[:,0], pk_input[:,1:].T)(k_norm)[:lmax//2+1]`, pk/compute_pk_randoms.py:188-193
+        (linear interpolation; a |k| outside the table raises like interp1d does)."""
+        tab = np.asarray(table, dtype=np.float64)
+        m = self.mesh
+        kn = np.sqrt(m.kax[0][:, None, None] ** 2.0 + m.kax[1][None, :, None] ** 2.0 + m.kax[2][None, None, :] ** 2.0)
+        if kn.max() > tab[-1, 0] or kn.min() < tab[0, 0]:
+            raise ValueError("A value in x_new is outside the interpolation range.")
+        if tab.shape[1] - 1 < m.n_l:
+            raise Exception("fiducial_pk table has fewer multipoles than lmax//2+1")
+        pk = np.stack([np.interp(kn, tab[:, 0], tab[:, 1 + i]) for i in range(m.n_l)])
+        self._pk_fid = self.dev(pk)
+        _lib.check(self.lib.sww_set_fiducial_pk(self._h, self._pk_fid.data_ptr()))
+
+    def _cdev(self, x):
+        t = torch()
+        return self.dev(x, t.complex128)
+
+    def ml_apply(self, op, x):
+        """applyS / applyN / applyC / applyCinv_fkp on a complex map (src/covariances_pk.py:10-164)."""
+        t = torch()
+        x = self._cdev(x)
+        out = t.empty_like(x)
+        _lib.check(self.lib.sww_ml_apply(self._h, {"S": 0, "N": 1, "C": 2, "Cinv_fkp": 3}[op], x.data_ptr(), out.data_ptr()))
+        return out
+
+    def ml_apply_cinv(self, pix, max_it=100, abs_tol=1e-8, rel_tol=None):
+        """applyCinv (src/covariances_pk.py:222-327) -> (complex map, iterations, stop reason)."""
+        t = torch()
+        pix = self._cdev(pix)
+        out = t.empty_like(pix)
+        it, why = _lib.i32(0), _lib.i32(0)
+        _lib.check(self.lib.sww_ml_apply_cinv(self._h, pix.data_ptr(), int(max_it), float(abs_tol),
+                                              -1.0 if rel_tol is None else float(rel_tol), out.data_ptr(),
+                                              C.byref(it), C.byref(why)))
+        return out, it.value, why.value
+
+    def pk_q_from_cinv(self, z):
+        """q_alpha = 1/2 sum z C_,alpha z for a C^-1-weighted map; complex z: q[Re z] - q[Im z]."""
+        t = torch()
+        z = z if isinstance(z, t.Tensor) else t.from_numpy(np.ascontiguousarray(z)).to(self.device)
+        parts = [z.real.contiguous(), z.imag.contiguous()] if z.is_complex() else [z.to(t.float64).contiguous()]
+        q = None
+        for i, p in enumerate(parts):
+            qi = self.empty((self.n_b,))
+            _lib.check(self.lib.sww_pk_q_from_cinv(self._h, p.data_ptr(), qi.data_ptr()))
+            q = qi if q is None else q - qi
+        return q
+
+    def pk_data_q_ml(self, diff, max_it=30, rel_tol=1e-6):
+        """q_alpha with ML weights (pk/compute_pk_data.py:194-206) -> (q, CG iterations)."""
+        z, it, _ = self.ml_apply_cinv(diff, max_it=max_it, rel_tol=rel_tol)
+        return self.pk_q_from_cinv(z), it
+
+    def pk_fisher_ml(self, a, max_it=30, rel_tol=1e-6, fish_out=None, qbar_out=None):
+        """One realisation with ML weights -> (F, qbar, total CG iterations)."""
+        a = self.dev(a)
+        F = fish_out if fish_out is not None else self.empty((self.n_b, self.n_b))
+        q = qbar_out if qbar_out is not None else self.empty((self.n_b,))
+        its = _lib.i32(0)
+        _lib.check(self.lib.sww_pk_fisher_realisation_ml(self._h, a.data_ptr(), int(max_it), float(rel_tol), F.data_ptr(),
+                                                         q.data_ptr(), C.byref(its)))
+        return F, q, its.value
 
     # -- painting
     def paint(self, pos, w, box_center, scheme="TSC", scale=1.0, out=None):

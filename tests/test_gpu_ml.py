@@ -1,0 +1,114 @@
+"""Maximum-likelihood weights on the CUDA path (csrc/ml.cu) against golden vectors produced by the reference's
+own functions (oracle/make_golden.py toyA+ml) and against the CPU oracle on the power-of-two world."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from spectra_without_windows_b200 import engine
+    return engine
+
+
+def _planes(m):
+    m = np.asarray(m)
+    nz = m.shape[2]
+    return {"p3": m[:, :, 3], "pny": m[:, :, nz // 2], "sums": np.asarray([m.sum(), (m * m).sum(), np.abs(m).max()])}
+
+
+def _check(m, g, key, tol=TOL):
+    for kk, v in _planes(m.cpu().numpy()).items():
+        assert relerr(v, g[key + "_" + kk]) < tol, (key, kk)
+
+
+def make_ctx(eng, w, table, pix=False):
+    mesh = eng.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    ctx = eng.Context(mesh, 0, ("ops", "pk_ml"))
+    ctx.set_fields_from_randoms_density(w.nbar_r, w.alpha, w.shot_fac)
+    ctx.set_include_pix(pix)
+    ctx.set_fiducial_pk(table)
+    return mesh, ctx
+
+
+@pytest.mark.parametrize("pix", [False, True])
+def test_ml_operators_against_reference_functions(eng, world, golden, pix):
+    w, g = world("toyA"), golden("toyA_ml")
+    mesh, ctx = make_ctx(eng, w, g["ml_pk_table"], pix)
+    tag = "pix" if pix else "nopix"
+    x = np.random.default_rng(5).normal(size=tuple(w.grid))
+    _check(ctx.ml_apply("S", x), g, "ml_S_" + tag)
+    _check(ctx.ml_apply("C", x), g, "ml_C_" + tag)
+    diff = ctx.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box_center)
+    z, it, why = ctx.ml_apply_cinv(diff, max_it=30, rel_tol=1e-6)
+    assert why == 1 and "after %d iterations" % it in str(g["ml_cg_log_" + tag])
+    _check(z, g, "ml_Cinv_d_" + tag)
+    z4, it4, why4 = ctx.ml_apply_cinv(diff, max_it=4, abs_tol=1e-3)
+    assert it4 == 4 and why4 == 0
+    _check(z4, g, "ml_Cinv_d_it4_" + tag)
+    if not pix:
+        q = ctx.pk_q_from_cinv(z).cpu().numpy()
+        assert relerr(q, g["ml_pk_q"]) < TOL
+    ctx.close()
+
+
+def test_ml_fisher_realisation(eng, world, golden):
+    from oracle import sww_oracle as orc
+    w, g = world("toyA"), golden("toyA_ml")
+    mesh, ctx = make_ctx(eng, w, g["ml_pk_table"])
+    kmin, kmax, dk, lmax = w.pk_bins
+    S = orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax)
+    for r in (1, 2):
+        F, qbar, its = ctx.pk_fisher_ml(S.grf(r))
+        assert its > mesh.n_k * mesh.n_l
+        assert relerr(F.cpu().numpy(), g["ml_pk_fish_%d" % r]) < TOL
+        assert relerr(qbar.cpu().numpy(), g["ml_pk_qbar_%d" % r]) < TOL
+    with pytest.raises(Exception, match="include_pix"):
+        ctx.set_include_pix(True)
+        ctx.pk_fisher_ml(S.grf(1))
+    ctx.close()
+
+
+def test_ml_on_power_of_two_mesh_against_oracle(eng, world, golden):
+    """64 x 64 x 128: real transforms run on the hand-written passes, the complex ones on the C2C plan."""
+    from oracle import sww_oracle as orc
+    w = world("toyD")
+    table = golden("toyA_ml")["ml_pk_table"]
+    table = np.concatenate([table, [[10.0, table[-1, 1], table[-1, 2], table[-1, 3]]]])   # cover this mesh's |k|
+    mesh, ctx = make_ctx(eng, w, table)
+    assert ctx.fft_backend == 1
+    kmin, kmax, dk, lmax = w.pk_bins
+    S = orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax)
+    pk_map = orc.pk_map_from_table(S, table)
+    diff = ctx.grid_data(w.data["pos"], w.data["w"], w.randoms["pos"], w.randoms["w"], w.box_center)
+    d = diff.cpu().numpy()
+    info = {}
+    z_o = orc.applyCinv(S, d, pk_map, rel_tol=1e-6, max_it=30, info=info)
+    z, it, _ = ctx.ml_apply_cinv(diff, max_it=30, rel_tol=1e-6)
+    assert it == info["iterations"]
+    assert relerr(z.cpu().numpy(), z_o) < TOL
+    q, _ = ctx.pk_data_q_ml(diff)
+    C_a = S.applyC_alpha(z_o, data=True)
+    q_o = np.asarray([np.real(np.sum(z_o * c)) / 2.0 for c in C_a])
+    assert relerr(q.cpu().numpy(), q_o) < TOL
+    ctx.close()
+
+
+def test_ml_loud_errors(eng, world, golden):
+    w = world("toyA")
+    mesh = eng.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    ctx = eng.Context(mesh, 0, ("ops", "pk_ml"))
+    ctx.set_fields_from_randoms_density(w.nbar_r, w.alpha, w.shot_fac)
+    with pytest.raises(Exception, match="fiducial"):
+        ctx.ml_apply("S", np.ones(tuple(w.grid)))
+    with pytest.raises(ValueError, match="interpolation range"):
+        ctx.set_fiducial_pk(np.asarray([[0.0, 1.0, 1.0, 1.0], [0.01, 1.0, 1.0, 1.0]]))
+    small = eng.Context(mesh, 0, ("ops",))
+    small.set_fields_from_randoms_density(w.nbar_r, w.alpha, w.shot_fac)
+    small.set_fiducial_pk(golden("toyA_ml")["ml_pk_table"])
+    with pytest.raises(Exception, match="workspace too small"):
+        small.ml_apply("S", np.ones(tuple(w.grid)))
