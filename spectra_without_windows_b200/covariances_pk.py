@@ -1,8 +1,8 @@
 """Drop-in mirror of the reference's src/covariances_pk.py FKP operators, backed by libsww.so.
 
-Same names, argument order and meaning as the reference; ndarray in -> ndarray out.  FKP weights, both values of `include_pix`;
-`include_pix=True` is composed from the same kernels plus the k-space MAS filter; ML weights raise
-(SURVEY.md section 8f row N1 -- not yet built, never a CPU fallback).
+Same names, argument order and meaning as the reference; ndarray in -> ndarray out.  FKP and ML weights, both values of
+`include_pix` (`include_pix=True` is composed from the same kernels plus the k-space MAS filter).  The ML operators
+(applyS, applyC, applyCinv) keep full complex128 maps like the reference -- see csrc/ml.cu.  Never a CPU fallback.
 """
 from __future__ import annotations
 
@@ -96,9 +96,69 @@ def applyC_alpha(input_map, nbar, MAS_mat, Y_lms, k_grids, r_grids, v_cell, k_fi
     return out
 
 
-def applyCinv(*a, **k):
-    raise Exception("ML weights (preconditioned-CG applyCinv) are not implemented on the B200 path yet "
-                    "(SURVEY.md section 8f row N1); use weights = FKP")
+def _ml_context(input_map, nbar, pk_map, Y_lms, k_grids, r_grids, v_cell, shot_fac, P_fkp, include_pix):
+    """Context with the "pk_ml" workspace for the caller's mesh; n(r), shot factor and the fiducial P_l(k) maps are
+    (re)bound on every call because the reference passes them as arguments."""
+    info = _info(k_grids, r_grids)
+    lmax = 2 * (len(Y_lms) - 1)
+    # the binning of the context is irrelevant for these operators: any valid one below the Nyquist frequency
+    kny = float(np.min(np.pi * np.asarray(info["grid"]) / np.asarray(info["box"], float)))
+    mesh = engine.Mesh(info["box"], info["grid"], info["box_center"], 0.0, 0.5 * kny, 0.25 * kny, lmax)
+    ctx = engine.get_context(mesh, 0, ("ops", "pk_ml"))
+    ctx.set_fields(nbar, nbar, np.where(np.asarray(nbar) > 0, nbar, 1.0), float(shot_fac), float(P_fkp))
+    ctx.set_include_pix(include_pix)
+    if pk_map is not None:
+        pk = np.ascontiguousarray(np.real(pk_map), dtype=np.float64)
+        if pk.shape != (mesh.n_l,) + mesh.shape:
+            raise Exception("pk_map must hold lmax//2+1 multipoles on the mesh")
+        ctx._pk_fid = ctx.dev(pk)
+        engine._lib.check(ctx.lib.sww_set_fiducial_pk(ctx._h, ctx._pk_fid.data_ptr()))
+    if abs(ctx.mesh.v_cell - float(v_cell)) > 1e-12 * abs(float(v_cell)):
+        raise Exception("v_cell does not match the mesh of k_grids/r_grids")
+    return ctx
 
 
-applyC = applyS = applyCinv_approx = apply_inv_preconditoner = applyCinv
+def applyS(input_map, nbar, MAS_mat, pk_map, Y_lms, k_grids, r_grids, v_cell, include_pix=True):
+    """src/covariances_pk.py:45-95: signal covariance S x with the fiducial multipoles `pk_map`; complex128 out."""
+    ctx = _ml_context(input_map, nbar, pk_map, Y_lms, k_grids, r_grids, v_cell, 1.0, 1e4, include_pix)
+    return ctx.ml_apply("S", input_map).cpu().numpy()
+
+
+def applyC(input_map, nbar, MAS_mat, pk_map, Y_lms, k_grids, r_grids, v_cell, shot_fac, include_pix=True):
+    """src/covariances_pk.py:10-43: C x = S x + N x; complex128 out."""
+    ctx = _ml_context(input_map, nbar, pk_map, Y_lms, k_grids, r_grids, v_cell, shot_fac, 1e4, include_pix)
+    return ctx.ml_apply("C", input_map).cpu().numpy()
+
+
+def applyCinv_approx(input_map, nbar, MAS_mat, v_cell, shot_fac, P_fkp=1e4, include_pix=True):
+    """src/covariances_pk.py:166-192: the FKP form, used as first guess of the conjugate-gradient inversion."""
+    return applyCinv_fkp(input_map, nbar, MAS_mat, v_cell, shot_fac, P_fkp=P_fkp, include_pix=include_pix)
+
+
+def apply_inv_preconditoner(pix, nbar, MAS_mat, v_cell, shot_fac, P_fkp=1e4, include_pix=True):
+    """src/covariances_pk.py:194-220 (sic): the preconditioner of the conjugate-gradient inversion."""
+    return applyCinv_approx(pix, nbar, MAS_mat, v_cell, shot_fac, P_fkp=P_fkp, include_pix=include_pix)
+
+
+def applyCinv(pix, nbar, MAS_mat, P3D, Y_lms, k_grids, r_grids, v_cell, shot_fac, applyC=applyC, applyCinv_approx=applyCinv_approx,
+              max_it=100, abs_tol=1e-8, rel_tol=None, verb=1, apply_inv_preconditoner=apply_inv_preconditoner, P_fkp=1e4,
+              include_pix=True):
+    """src/covariances_pk.py:222-327: x = C^-1 pix by preconditioned conjugate gradients, on the device.  Same
+    stopping rules and messages; the operator hooks must be this module's own (a custom applyC cannot run on the GPU)."""
+    import time
+    g = globals()
+    if applyC is not g["applyC"] or applyCinv_approx is not g["applyCinv_approx"] or apply_inv_preconditoner is not g["apply_inv_preconditoner"]:
+        raise Exception("custom applyC / applyCinv_approx / apply_inv_preconditoner hooks are not supported on the B200 path")
+    start = time.time()
+    ctx = _ml_context(pix, nbar, P3D, Y_lms, k_grids, r_grids, v_cell, shot_fac, P_fkp, include_pix)
+    assert max_it < np.asarray(pix).size
+    x, it, why = ctx.ml_apply_cinv(pix, max_it=max_it, abs_tol=abs_tol, rel_tol=rel_tol)
+    if why == 2 and verb:
+        print("Inversion stalled after step %d; exiting" % (it + 1))
+    if why == 1 and verb:
+        print("Inversion stopped early after %d iterations" % it)
+    if why == 0 and it == max_it:
+        print("CGD did not stop early: is this converged?")
+    if verb:
+        print("\nInversion took %d seconds" % (time.time() - start))
+    return x.cpu().numpy()

@@ -55,10 +55,19 @@ class Params:
         self.rand_nbar = config.getboolean("settings", "rand_nbar")
         self.use_qbar = config.getboolean("settings", "use_qbar", fallback=True)
         self.spec = spec
+        if self.wtype == 1:
+            # Fiducial power spectrum input (for ML weights), pk/compute_pk_randoms.py:69-71
+            self.pk_input_file = str(config["settings"]["fiducial_pk"])
 
     def unsupported(self):
-        if self.wtype == 1:
-            raise Exception("weights = ML is not implemented on the B200 path yet (SURVEY.md section 8f row N1)")
+        """ML weights are built for the P_l(k) scripts; the bispectrum scripts' ML branch
+        (bk/compute_bk_randoms.py:229,408, bk/compute_bk_data.py:264) is not on the B200 path yet and fails loudly."""
+        if self.wtype == 1 and self.spec != "pk":
+            raise Exception("weights = ML is not implemented for the bispectrum scripts on the B200 path yet; use weights = FKP")
+
+    def load_fiducial_pk(self, ctx):
+        """pk/compute_pk_randoms.py:188-193: table k | P_0 | P_2 | ... -> P_l(|k|) maps on the device."""
+        ctx.set_fiducial_pk(np.loadtxt(self.pk_input_file))
 
     def ktag(self):
         return "k%.3f_%.3f_%.3f_l%d" % (self.k_min, self.k_max, self.dk, self.lmax)
@@ -143,13 +152,20 @@ def pk_randoms_main(argv):
     P.unsupported()
     print("\n## Loading %s random iteration %d with %s weights" % (P.string, rand_it, P.weight_type))
     print("\nLoading data")
-    ctx, mesh, nbar_A, alpha_ran, shot_fac, _ = _setup(P, 1, ("pk_fisher",), paint_data=False)
+    ctx, mesh, nbar_A, alpha_ran, shot_fac, _ = _setup(P, 1, ("pk_fisher",) if P.wtype == 0 else ("pk_ml",), paint_data=False)
     print("Data-to-random ratio: %.3f, shot-noise factor: %.3f" % (alpha_ran, shot_fac))
     # Gaussian sample (numpy legacy stream, pk/compute_pk_randoms.py:139-140)
     np.random.seed(rand_it)
     a = np.random.normal(loc=0.0, scale=np.sqrt(nbar_A), size=nbar_A.shape)
     print("\n## Computing Fisher and bias term on the GPU (%d bins)" % ctx.n_b)
-    F, qbar = ctx.pk_fisher(a)
+    if P.wtype == 0:
+        F, qbar = ctx.pk_fisher(a)
+    else:
+        # ML weights: C^-1 by preconditioned conjugate gradients on every derivative map
+        # (pk/compute_pk_randoms.py:211,240 -- rel_tol=1e-6, max_it=30)
+        P.load_fiducial_pk(ctx)
+        F, qbar, its = ctx.pk_fisher_ml(a, max_it=30, rel_tol=1e-6)
+        print("%d conjugate-gradient solves, %d iterations in total" % (ctx.n_b + 1, its))
     np.save(bias_file_name, qbar.cpu().numpy())
     np.save(fish_file_name, F.cpu().numpy())
     duration = time.time() - init
@@ -188,10 +204,16 @@ def pk_data_main(argv):
         print("\n## Analyzing %s simulation %d with %s weights" % (P.string, sim_no, P.weight_type))
     else:
         print("\n## Analyzing %s with %s weights" % (P.string, P.weight_type))
-    ctx, mesh, nbar_A, alpha_ran, shot_fac, diff = _setup(P, sim_no, ("pk_data",), paint_data=True)
+    ctx, mesh, nbar_A, alpha_ran, shot_fac, diff = _setup(P, sim_no, ("pk_data",) if P.wtype == 0 else ("pk_ml",), paint_data=True)
     print("alpha = %.3f, shot_factor: %.3f" % (alpha_ran, shot_fac))
     print("\n## Computing C-inverse of data and associated computations assuming %s weightings\n" % P.weight_type)
-    q_alpha = ctx.pk_data_q(diff).cpu().numpy()
+    if P.wtype == 0:
+        q_alpha = ctx.pk_data_q(diff).cpu().numpy()
+    else:   # pk/compute_pk_data.py:194 -- applyCinv(..., rel_tol=1e-6, verb=1, max_it=30)
+        P.load_fiducial_pk(ctx)
+        q, it = ctx.pk_data_q_ml(diff, max_it=30, rel_tol=1e-6)
+        print("Inversion stopped after %d iterations" % it)
+        q_alpha = q.cpu().numpy()
     try:
         bias = np.load(combined_bias)
         fish = np.load(combined_fish)

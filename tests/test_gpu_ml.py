@@ -112,3 +112,74 @@ def test_ml_loud_errors(eng, world, golden):
     small.set_fiducial_pk(golden("toyA_ml")["ml_pk_table"])
     with pytest.raises(Exception, match="workspace too small"):
         small.ml_apply("S", np.ones(tuple(w.grid)))
+
+
+def test_ml_mirrors_keep_the_reference_call_surface(world, golden):
+    """covariances_pk.applyS / applyC / applyCinv with the reference's positional arguments (src/covariances_pk.py:10,45,222)."""
+    from scipy.interpolate import interp1d
+    from spectra_without_windows_b200 import covariances_pk as cp
+    from spectra_without_windows_b200 import opt_utilities as ou
+    w, g = world("toyA"), golden("toyA_ml")
+    box, grid = np.asarray(w.box), np.asarray(w.grid)
+    kmin, kmax, dk, lmax = w.pk_bins
+    data = ou.Catalog(w.data["pos"], w.data["w"], box_center=w.box_center)
+    rand = ou.Catalog(w.randoms["pos"], w.randoms["w"], box_center=w.box_center)
+    diff, density = ou.grid_data(data, rand, box, grid, MAS="TSC", return_randoms=False)
+    k_grids, r_grids = ou.load_coord_grids(box, grid, density)
+    k_norm = np.sqrt(np.sum(k_grids ** 2.0, axis=0))
+    k_grids /= (1e-12 + k_norm)
+    r_grids /= (1e-12 + np.sqrt(np.sum(r_grids ** 2.0, axis=0)))
+    MAS = ou.load_MAS(box, grid)
+    Y = ou.compute_spherical_harmonic_functions(lmax)
+    nbar = w.nbar_r * w.alpha
+    v_cell = 1.0 * box.prod() / (1.0 * grid.prod())
+    table = g["ml_pk_table"]
+    pk_map = interp1d(table[:, 0], table[:, 1:].T)(np.asarray(k_norm))[:lmax // 2 + 1]   # pk/compute_pk_randoms.py:192-193
+    x = np.random.default_rng(5).normal(size=tuple(grid))
+    Sx = cp.applyS(x, nbar, MAS, pk_map, Y, k_grids, r_grids, v_cell, include_pix=False)
+    assert Sx.dtype == np.complex128
+    for kk, v in _planes(Sx).items():
+        assert relerr(v, g["ml_S_nopix_" + kk]) < TOL
+    Cx = cp.applyC(x, nbar, MAS, pk_map, Y, k_grids, r_grids, v_cell, w.shot_fac, include_pix=True)
+    for kk, v in _planes(Cx).items():
+        assert relerr(v, g["ml_C_pix_" + kk]) < TOL
+    Ci = cp.applyCinv(diff, nbar, MAS, pk_map, Y, k_grids, r_grids, v_cell, w.shot_fac, rel_tol=1e-6, verb=0, max_it=30,
+                      include_pix=False)
+    for kk, v in _planes(Ci).items():
+        assert relerr(v, g["ml_Cinv_d_nopix_" + kk]) < TOL
+    with pytest.raises(Exception, match="hooks"):
+        cp.applyCinv(diff, nbar, MAS, pk_map, Y, k_grids, r_grids, v_cell, w.shot_fac, applyC=lambda *a, **k: 0)
+
+
+def test_ml_scripts_end_to_end(world, golden, tmp_path):
+    """weights = ML through the drop-in CLIs: per-seed Fisher / bias files, then the P_l(k) text, against the files the
+    reference's own functions + its unmodified pk/compute_pk_data.py produce."""
+    import glob
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from spectra_without_windows_b200 import synthetic as syn
+    w, g = world("toyA"), golden("toyA_ml")
+    p = syn.write_world_files(w, str(tmp_path), weights="ML")
+    mc, od = str(tmp_path) + "/mc/", str(tmp_path) + "/out/"
+
+    def run(script, arg):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, script), str(arg), p], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return r.stdout
+
+    for r in (1, 2):
+        out = run("pk/compute_pk_randoms.py", r)
+        assert "conjugate-gradient solves" in out
+        F = np.load(glob.glob(mc + "*%d_ML_pk_fish_a_*.npy" % r)[0])
+        qb = np.load(glob.glob(mc + "*%d_ML_pk_q-bar_a_*.npy" % r)[0])
+        assert relerr(F, g["ml_pk_fish_%d" % r]) < TOL and relerr(qb, g["ml_pk_qbar_%d" % r]) < TOL
+    run("pk/compute_pk_data.py", 1)
+    f = glob.glob(od + "pk_*.txt")[0]
+    assert os.path.basename(f) == str(g["ml_pk_txt_name"])
+    assert open(f).read().split("\n")[:15] == str(g["ml_pk_txt"]).split("\n")[:15]
+    assert relerr(np.loadtxt(f), g["ml_pk_p"]) < 2e-8
+    # the bispectrum scripts refuse ML weights loudly
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bk/compute_bk_randoms.py"), "1", p], capture_output=True, text=True)
+    assert r.returncode != 0 and "ML" in r.stderr
