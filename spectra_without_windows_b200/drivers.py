@@ -60,8 +60,9 @@ class Params:
             self.pk_input_file = str(config["settings"]["fiducial_pk"])
 
     def unsupported(self):
-        """ML weights are built for the P_l(k) scripts; the bispectrum scripts' ML branch
-        (bk/compute_bk_randoms.py:229,408, bk/compute_bk_data.py:264) is not on the B200 path yet and fails loudly."""
+        """ML weights are built for the P_l(k) scripts.  The bispectrum scripts' ML branch cannot run in the reference
+        either (`np.maximum([lmax_pk,lmax])` raises TypeError at bk/compute_bk_randoms.py:173 and
+        bk/compute_bk_data.py:170), so there is nothing to be in parity with: fail loudly."""
         if self.wtype == 1 and self.spec != "pk":
             raise Exception("weights = ML is not implemented for the bispectrum scripts on the B200 path yet; use weights = FKP")
 
