@@ -122,6 +122,13 @@ int sww_paint(sww_ctx* c, sww_devptr pos, sww_devptr w, uint64_t n, const double
  * are bit-exact; the Gaussian values agree with numpy's to <= 2 ulp.  Synchronous on `stream` only: the
  * generator uses one SM, so on a side stream it overlaps with the pipelines of the context stream. */
 int sww_grf_legacy(sww_ctx* c, uint32_t seed, sww_devptr sigma, sww_devptr out, uint64_t n, sww_stream stream /* 0: context stream */);
+/* The same for up to 8 seeds at once (outs[s] = field of seeds[s], all scaled by the same sigma): the MT19937
+ * recurrences are sequential but independent, one CTA each, so a batch costs the time of one field.
+ * With stream != 0 the call only enqueues (no host synchronisation); sww_grf_check() afterwards reports the
+ * (probability ~1e-15) case of a field left short of accepted polar pairs. */
+int sww_grf_legacy_batch(sww_ctx* c, const uint32_t* seeds, int nseeds, sww_devptr sigma, const sww_devptr* outs, uint64_t n,
+                         sww_stream stream);
+int sww_grf_check(sww_ctx* c);
 
 /* ---- P_l(k) pipelines ---- */
 /* One Gaussian realisation `a` (double[N], device) -> q-bar_alpha [n_b] and the symmetrised

@@ -50,6 +50,8 @@ SIGNATURES = {
     "sww_get_binmap": [ctxp, u64],
     "sww_paint": [ctxp, u64, u64, u64, pd, C.c_int, f64, u64],
     "sww_grf_legacy": [ctxp, C.c_uint32, u64, u64, u64, u64],
+    "sww_grf_check": [ctxp],
+    "sww_grf_legacy_batch": [ctxp, C.POINTER(C.c_uint32), C.c_int, u64, C.POINTER(u64), u64, u64],
     "sww_pk_fisher_realisation": [ctxp, u64, u64, u64],
     "sww_pk_data_q": [ctxp, u64, u64],
     "sww_set_fiducial_pk": [ctxp, u64],

@@ -30,10 +30,14 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y) {
   return y;
 }
 
-// state: 624 words in global memory (updated in place); writes nblocks*624 tempered words
-__global__ void __launch_bounds__(256) mt_words_kernel(unsigned* __restrict__ state, unsigned* __restrict__ out, long long nblocks) {
+// state: 624 words in global memory (updated in place); writes nblocks*624 tempered words.
+// One CTA per stream of a batch (blockIdx.x): independent seeds advance side by side on separate SMs.
+__global__ void __launch_bounds__(256) mt_words_kernel(unsigned* __restrict__ state, unsigned* __restrict__ out, long long nblocks,
+                                                       long long word_stride) {
   __shared__ unsigned mt[MT_N];
   const int t = threadIdx.x;
+  state += (long long)blockIdx.x * MT_N;
+  out += (long long)blockIdx.x * word_stride;
   for (int i = t; i < MT_N; i += 256) mt[i] = state[i];
   __syncthreads();
   for (long long b = 0; b < nblocks; ++b) {
@@ -76,8 +80,11 @@ __device__ __forceinline__ bool polar_attempt(const unsigned* __restrict__ w, lo
 #define PA_BLOCK 1024
 // pass 1: accepted attempts per block of 1024 attempts
 __global__ void __launch_bounds__(PA_BLOCK) polar_count_kernel(const unsigned* __restrict__ w, long long nattempts,
-                                                                unsigned* __restrict__ block_counts) {
+                                                                unsigned* __restrict__ block_counts, long long word_stride,
+                                                                long long count_stride) {
   __shared__ unsigned wc[PA_BLOCK / 32];
+  w += (long long)blockIdx.y * word_stride;
+  block_counts += (long long)blockIdx.y * count_stride;
   const long long i = (long long)blockIdx.x * PA_BLOCK + threadIdx.x;
   double x1, x2, r2;
   bool ok = (i < nattempts) && polar_attempt(w, i, x1, x2, r2);
@@ -95,9 +102,13 @@ __global__ void __launch_bounds__(PA_BLOCK) polar_count_kernel(const unsigned* _
 // offsets[nblocks] = accepted pairs of this chunk; *running = pairs emitted by earlier chunks (read by the emit
 // pass through offsets[nblocks+1], then advanced)
 __global__ void __launch_bounds__(1024) scan_counts_kernel(unsigned* __restrict__ counts, long long* __restrict__ offsets, int nblocks,
-                                                            long long* __restrict__ running) {
+                                                            long long* __restrict__ running, long long count_stride,
+                                                            long long offset_stride) {
   __shared__ long long part[1024];
   const int t = threadIdx.x;
+  counts += (long long)blockIdx.x * count_stride;
+  offsets += (long long)blockIdx.x * offset_stride;
+  running += blockIdx.x;
   const int per = (nblocks + 1023) / 1024;
   long long s = 0;
   for (int k = 0; k < per; ++k) {
@@ -129,11 +140,18 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(unsigned* __restrict_
 }
 
 // pass 3: accepted attempt with stream rank j writes out[2j] = sigma*f*x2, out[2j+1] = sigma*f*x1
+#define RNG_MAX_BATCH 8
+struct RngOuts {
+  double* p[RNG_MAX_BATCH];
+};
 __global__ void __launch_bounds__(PA_BLOCK) polar_emit_kernel(const unsigned* __restrict__ w, long long nattempts,
                                                                const long long* __restrict__ offsets, int nblocks,
-                                                               const double* __restrict__ sigma, double* __restrict__ out,
-                                                               long long nout) {
+                                                               const double* __restrict__ sigma, RngOuts outs, long long nout,
+                                                               long long word_stride, long long offset_stride) {
   __shared__ unsigned wc[PA_BLOCK / 32];
+  w += (long long)blockIdx.y * word_stride;
+  offsets += (long long)blockIdx.y * offset_stride;
+  double* __restrict__ out = outs.p[blockIdx.y];
   const long long i = (long long)blockIdx.x * PA_BLOCK + threadIdx.x;
   double x1 = 0, x2 = 0, r2 = 1;
   bool ok = (i < nattempts) && polar_attempt(w, i, x1, x2, r2);
@@ -151,40 +169,58 @@ __global__ void __launch_bounds__(PA_BLOCK) polar_emit_kernel(const unsigned* __
   if (o + 1 < nout) out[o + 1] = 0.0 + sigma[o + 1] * (f * x1);
 }
 
+// asynchronous shortfall guard: sticky device flag, read by sww_grf_check
+__global__ void rng_guard_kernel(const long long* __restrict__ running, long long need_pairs, int nseeds, int* __restrict__ flag) {
+  if (threadIdx.x < nseeds && running[threadIdx.x] < need_pairs) *flag = 1;
+}
+
 struct RngScratch {
+  int* flag = nullptr;
   unsigned* state = nullptr;
   unsigned* words = nullptr;
   unsigned* counts = nullptr;
   long long* offsets = nullptr;
   long long* running = nullptr;
   long long cap_attempts = 0;
+  int cap_batch = 0;
+  long long word_stride = 0, count_stride = 0, offset_stride = 0;
 };
 static RngScratch g_rng;
 
-static int rng_reserve(long long attempts) {
-  if (attempts <= g_rng.cap_attempts) return 0;
+static int rng_reserve(long long attempts, int batch) {
+  if (attempts <= g_rng.cap_attempts && batch <= g_rng.cap_batch) return 0;
   if (g_rng.words) {
     cudaFree(g_rng.words);
     cudaFree(g_rng.counts);
     cudaFree(g_rng.offsets);
   }
   if (!g_rng.state) {
-    SWW_CUDA(cudaMalloc(&g_rng.state, MT_N * sizeof(unsigned)));
-    SWW_CUDA(cudaMalloc(&g_rng.running, sizeof(long long)));
+    SWW_CUDA(cudaMalloc(&g_rng.state, RNG_MAX_BATCH * MT_N * sizeof(unsigned)));
+    SWW_CUDA(cudaMalloc(&g_rng.running, RNG_MAX_BATCH * sizeof(long long)));
+    SWW_CUDA(cudaMalloc(&g_rng.flag, sizeof(int)));
+    SWW_CUDA(cudaMemset(g_rng.flag, 0, sizeof(int)));
   }
+  if (batch < g_rng.cap_batch) batch = g_rng.cap_batch;
   long long nb = (attempts + PA_BLOCK - 1) / PA_BLOCK;
-  SWW_CUDA(cudaMalloc(&g_rng.words, (size_t)(attempts * 4 + MT_N) * sizeof(unsigned)));
-  SWW_CUDA(cudaMalloc(&g_rng.counts, (size_t)(nb + 1) * sizeof(unsigned)));
-  SWW_CUDA(cudaMalloc(&g_rng.offsets, (size_t)(nb + 2) * sizeof(long long)));
+  g_rng.word_stride = attempts * 4 + MT_N;
+  g_rng.count_stride = nb + 1;
+  g_rng.offset_stride = nb + 2;
+  SWW_CUDA(cudaMalloc(&g_rng.words, (size_t)g_rng.word_stride * batch * sizeof(unsigned)));
+  SWW_CUDA(cudaMalloc(&g_rng.counts, (size_t)g_rng.count_stride * batch * sizeof(unsigned)));
+  SWW_CUDA(cudaMalloc(&g_rng.offsets, (size_t)g_rng.offset_stride * batch * sizeof(long long)));
   g_rng.cap_attempts = attempts;
+  g_rng.cap_batch = batch;
   return 0;
 }
 
-// out[i] = sigma[i] * gauss_i, i < n, with the numpy legacy stream of `seed`
-extern "C" int sww_grf_legacy(sww_ctx* c, uint32_t seed, sww_devptr sigma_, sww_devptr out_, uint64_t n, sww_stream stream_) {
-  SWW_REQUIRE(c && sigma_ && out_ && n > 0, "null argument");
-  // runs on `stream_` (0: the context stream) and returns when the field is complete on that stream; the
-  // generator occupies a single SM, so a side stream overlaps it with the Fisher kernels of another field
+// outs[s][i] = sigma[i] * gauss_i(seed s), i < n, with the numpy legacy streams of `seeds`; the nseeds recurrences
+// (one CTA each, inherently sequential) advance side by side, so a batch costs the time of one field
+extern "C" int sww_grf_legacy_batch(sww_ctx* c, const uint32_t* seeds, int nseeds, sww_devptr sigma_, const sww_devptr* outs_,
+                                    uint64_t n, sww_stream stream_) {
+  SWW_REQUIRE(c && seeds && sigma_ && outs_ && n > 0, "null argument");
+  SWW_REQUIRE(nseeds >= 1 && nseeds <= RNG_MAX_BATCH, "grf batch of %d seeds (1..%d)", nseeds, RNG_MAX_BATCH);
+  // runs on `stream_` (0: the context stream) and returns when the fields are complete on that stream; the
+  // generator occupies one SM per seed, so a side stream overlaps it with the Fisher kernels of another field
   struct StreamSwap {
     sww_ctx* c;
     cudaStream_t old;
@@ -193,39 +229,74 @@ extern "C" int sww_grf_legacy(sww_ctx* c, uint32_t seed, sww_devptr sigma_, sww_
   } swap_(c, (cudaStream_t)stream_);
   SWW_PROF(c, "rng.legacy gaussian field");
   const double* sigma = (const double*)sigma_;
-  double* out = (double*)out_;
+  RngOuts outs = {};
+  for (int b = 0; b < nseeds; ++b) {
+    SWW_REQUIRE(outs_[b], "null output pointer");
+    outs.p[b] = (double*)outs_[b];
+  }
   // chunks of 624*2^14 words = 2.56 M attempts (a whole number of MT blocks)
   const long long blocks_per_chunk = 4LL << 14;                 // x624 words, divisible by 4 words per attempt
   const long long att_per_chunk = blocks_per_chunk * MT_N / 4;
-  SWW_TRY(rng_reserve(att_per_chunk));
+  SWW_TRY(rng_reserve(att_per_chunk, nseeds));
   // init_genrand seeding (numpy mt19937_seed)
-  unsigned h[MT_N];
-  unsigned s = seed;
-  for (int pos = 0; pos < MT_N; ++pos) {
-    h[pos] = s;
-    s = 1812433253u * (s ^ (s >> 30)) + (unsigned)pos + 1u;
+  static unsigned h[RNG_MAX_BATCH * MT_N];
+  for (int b = 0; b < nseeds; ++b) {
+    unsigned s = seeds[b];
+    for (int pos = 0; pos < MT_N; ++pos) {
+      h[b * MT_N + pos] = s;
+      s = 1812433253u * (s ^ (s >> 30)) + (unsigned)pos + 1u;
+    }
   }
-  SWW_CUDA(cudaMemcpyAsync(g_rng.state, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));   // pageable source: staged before return
-  SWW_CUDA(cudaMemsetAsync(g_rng.running, 0, sizeof(long long), c->stream));
+  SWW_CUDA(cudaMemcpyAsync(g_rng.state, h, sizeof(unsigned) * MT_N * nseeds, cudaMemcpyHostToDevice, c->stream));   // pageable source: staged before return
+  SWW_CUDA(cudaMemsetAsync(g_rng.running, 0, sizeof(long long) * RNG_MAX_BATCH, c->stream));
   const long long need_pairs = ((long long)n + 1) / 2;
   const int nb = (int)((att_per_chunk + PA_BLOCK - 1) / PA_BLOCK);
   // accepted pairs per chunk ~ Binomial(A, pi/4): plan the chunk count 8 sigma on the safe side, no read-back per chunk
   const double p = 0.78539816339744831, sd = sqrt((double)att_per_chunk * p * (1.0 - p));
   long long chunks = (long long)ceil((double)need_pairs / ((double)att_per_chunk * p - 8.0 * sd));
   long long done_pairs = 0;
+  const bool async = stream_ != 0;   // side stream: no host synchronisation, the shortfall guard is a device flag (sww_grf_check)
   while (done_pairs < need_pairs) {
     for (long long k = 0; k < chunks; ++k) {
-      mt_words_kernel<<<1, 256, 0, c->stream>>>(g_rng.state, g_rng.words, blocks_per_chunk);
-      polar_count_kernel<<<nb, PA_BLOCK, 0, c->stream>>>(g_rng.words, att_per_chunk, g_rng.counts);
-      scan_counts_kernel<<<1, 1024, 0, c->stream>>>(g_rng.counts, g_rng.offsets, nb, g_rng.running);
-      polar_emit_kernel<<<nb, PA_BLOCK, 0, c->stream>>>(g_rng.words, att_per_chunk, g_rng.offsets, nb, sigma, out, (long long)n);
+      mt_words_kernel<<<nseeds, 256, 0, c->stream>>>(g_rng.state, g_rng.words, blocks_per_chunk, g_rng.word_stride);
+      polar_count_kernel<<<dim3(nb, nseeds), PA_BLOCK, 0, c->stream>>>(g_rng.words, att_per_chunk, g_rng.counts, g_rng.word_stride,
+                                                                        g_rng.count_stride);
+      scan_counts_kernel<<<nseeds, 1024, 0, c->stream>>>(g_rng.counts, g_rng.offsets, nb, g_rng.running, g_rng.count_stride,
+                                                          g_rng.offset_stride);
+      polar_emit_kernel<<<dim3(nb, nseeds), PA_BLOCK, 0, c->stream>>>(g_rng.words, att_per_chunk, g_rng.offsets, nb, sigma, outs,
+                                                                       (long long)n, g_rng.word_stride, g_rng.offset_stride);
       c->n_own += 4;
     }
     SWW_CUDA(cudaGetLastError());
-    // one read-back at the end guards the (astronomically unlikely) shortfall
-    SWW_CUDA(cudaMemcpyAsync(&done_pairs, g_rng.running, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (async) {
+      rng_guard_kernel<<<1, 32, 0, c->stream>>>(g_rng.running, need_pairs, nseeds, g_rng.flag);
+      c->n_own++;
+      break;
+    }
+    // one read-back at the end guards the (astronomically unlikely) shortfall: the slowest stream decides
+    long long run[RNG_MAX_BATCH];
+    SWW_CUDA(cudaMemcpyAsync(run, g_rng.running, sizeof(long long) * nseeds, cudaMemcpyDeviceToHost, c->stream));
     SWW_CUDA(cudaStreamSynchronize(c->stream));
+    done_pairs = run[0];
+    for (int b = 1; b < nseeds; ++b) done_pairs = run[b] < done_pairs ? run[b] : done_pairs;
     chunks = 1;
   }
   return 0;
+}
+
+// synchronises the device and reports whether any asynchronous batch fell short of accepted pairs (probability ~1e-15
+// per field with the 8-sigma chunk plan; the caller would regenerate on the context stream)
+extern "C" int sww_grf_check(sww_ctx* c) {
+  SWW_REQUIRE(c, "null context");
+  if (!g_rng.flag) return 0;
+  int f = 0;
+  SWW_CUDA(cudaDeviceSynchronize());
+  SWW_CUDA(cudaMemcpy(&f, g_rng.flag, sizeof(int), cudaMemcpyDeviceToHost));
+  SWW_REQUIRE(f == 0, "device RNG: a field was left incomplete (too few accepted polar pairs); regenerate it synchronously");
+  return 0;
+}
+
+extern "C" int sww_grf_legacy(sww_ctx* c, uint32_t seed, sww_devptr sigma_, sww_devptr out_, uint64_t n, sww_stream stream_) {
+  SWW_REQUIRE(out_, "null argument");
+  return sww_grf_legacy_batch(c, &seed, 1, sigma_, &out_, n, stream_);
 }

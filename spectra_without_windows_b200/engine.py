@@ -251,34 +251,55 @@ class Context:
                                            0 if stream is None else stream.cuda_stream))
         return out
 
-    def field_pipeline(self, seeds, sigma):
-        """Iterate device-generated legacy fields, generating field i+1 on a side stream while the caller's
-        work on field i runs on the context stream.  Yields (seed, field tensor)."""
+    def grf_legacy_batch(self, seeds, sigma, outs=None, stream=None):
+        """Fields of up to 8 seeds at once (independent MT19937 recurrences side by side: the cost of one field)."""
+        sigma = self.dev(sigma)
+        seeds = [int(s) & 0xFFFFFFFF for s in seeds]
+        if outs is None:
+            outs = [self.empty(tuple(sigma.shape)) for _ in seeds]
+        arr = (C.c_uint32 * len(seeds))(*seeds)
+        ptrs = (_lib.u64 * len(seeds))(*[o.data_ptr() for o in outs[:len(seeds)]])
+        _lib.check(self.lib.sww_grf_legacy_batch(self._h, arr, len(seeds), sigma.data_ptr(), ptrs, int(sigma.numel()),
+                                                 0 if stream is None else stream.cuda_stream))
+        return outs[:len(seeds)]
+
+    def field_pipeline(self, seeds, sigma, batch=None):
+        """Iterate device-generated legacy fields.  Batch j+1 (`batch` seeds, generated side by side) is produced on a
+        side stream while the caller's work on the fields of batch j runs on the context stream.  Yields (seed, field)."""
         t = torch()
         sigma = self.dev(sigma)
         seeds = list(seeds)
         if not seeds:
             return
+        if batch is None:
+            # two sets of `batch` fields stay resident: keep them below ~8 % of the device memory
+            total = t.cuda.get_device_properties(self.device).total_memory
+            batch = int(max(1, min(4, (0.08 * total) // (2 * 8 * sigma.numel()))))
+        batch = max(1, min(int(batch), 8, len(seeds)))
+        groups = [seeds[i:i + batch] for i in range(0, len(seeds), batch)]
         side = t.cuda.Stream(device=self.device)
-        bufs = [self.empty(tuple(sigma.shape)) for _ in range(2)]
+        bufs = [[self.empty(tuple(sigma.shape)) for _ in range(batch)] for _ in range(2)]
         main = self.stream
         side.wait_stream(main)
-        self.grf_legacy(seeds[0], sigma, bufs[0], stream=side)
+        self.grf_legacy_batch(groups[0], sigma, bufs[0], stream=side)
         done = t.cuda.Event()
         done.record(side)
-        used = []                       # used[i]: the caller's work on field i has been enqueued up to here
-        for i, s in enumerate(seeds):
+        used = []                       # used[j]: the caller's work on batch j has been enqueued up to here
+        for j, grp in enumerate(groups):
             main.wait_event(done)
-            yield s, bufs[i % 2]
+            if j + 1 < len(groups):
+                if j >= 1:
+                    side.wait_event(used[j - 1])    # buffer set (j+1)%2 was last read by the work on batch j-1
+                # enqueue-only on the side stream: overlaps the caller's work on batch j
+                self.grf_legacy_batch(groups[j + 1], sigma, bufs[(j + 1) % 2], stream=side)
+                done = t.cuda.Event()
+                done.record(side)
+            for i, s in enumerate(grp):
+                yield s, bufs[j % 2][i]
             ev = t.cuda.Event()
             ev.record(main)
             used.append(ev)
-            if i + 1 < len(seeds):
-                if i >= 1:
-                    side.wait_event(used[i - 1])    # buffer (i+1)%2 was last read by the work on field i-1
-                self.grf_legacy(seeds[i + 1], sigma, bufs[(i + 1) % 2], stream=side)   # overlaps the work on field i
-                done = t.cuda.Event()
-                done.record(side)
+        _lib.check(self.lib.sww_grf_check(self._h))
 
     # -- P_l(k)
     def pk_fisher(self, a, fish_out=None, qbar_out=None):

@@ -37,3 +37,31 @@ def test_fisher_from_device_field_matches_host_field(world):
     e = float((F1 - F0).abs().max() / F0.abs().max())
     assert e < 1e-12
     ctx.close()
+
+
+def test_batched_fields_and_pipeline_match_numpy(world):
+    """Up to 8 independent legacy streams advance side by side; the overlapped pipeline hands out the same fields."""
+    from spectra_without_windows_b200 import engine
+    w = world("toyD")
+    mesh = engine.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    ctx = engine.Context(mesh, 0, ("pk_fisher",))
+    sigma = np.random.default_rng(1).random(tuple(w.grid)) + 0.5
+    seeds = [5, 6, 7, 4000000000, 9, 10, 11]
+
+    def ref(s):
+        np.random.seed(s)
+        return np.random.normal(loc=0.0, scale=sigma, size=sigma.shape)
+
+    outs = ctx.grf_legacy_batch(seeds, sigma)
+    for s, o in zip(seeds, outs):
+        assert np.max(np.abs(o.cpu().numpy() - ref(s)) / np.maximum(np.abs(ref(s)), 1e-300)) < 1e-14, s
+    with pytest.raises(Exception, match="batch"):
+        ctx.grf_legacy_batch(list(range(9)), sigma)
+    for batch in (1, 3):
+        got = {}
+        for s, a in ctx.field_pipeline(seeds, sigma, batch=batch):
+            got[s] = a.clone()          # the buffer is recycled two batches later
+        assert sorted(got) == sorted(seeds)
+        for s in seeds:
+            assert np.max(np.abs(got[s].cpu().numpy() - ref(s)) / np.maximum(np.abs(ref(s)), 1e-300)) < 1e-14, (batch, s)
+    ctx.close()
