@@ -556,12 +556,12 @@ def main():
             roof["traffic"] = traffic
             roof["dominant_kernel"] = {
                 "name": "%s (fused z pass: c2r * nW * r2c of the %d Fisher rows of one k bin)"
-                        % ("pass_z16_fused_kernel<8,1,true>" if nz == 512 and kz_out <= 128 else "pass_zw_kernel<H,1,1,0>", rows_per_launch),
+                        % ("pass_z16_fused_kernel<4,3,true>" if nz == 512 and kz_out <= 128 else "pass_zw_kernel<H,1,1,0>", rows_per_launch),
                 "launches_per_realisation": prof[zkey]["launches"], "avg_launch_ms": dur * 1e3,
                 "share_of_step": prof[zkey]["ms"] / (ms / args.steps),
                 "algorithmic_bytes_per_launch": bytes_launch, "achieved_gbs": bytes_launch / dur / 1e9,
                 "frac_of_hbm_peak": bytes_launch / dur / 1e9 / peak, "dram_traffic_bytes_per_launch_ncu": traffic,
-                "note": "FP64-pipe bound (ncu: 56 % of the pipe, 64 DFMA/clk/SM; two half-length complex FFTs per row), so its HBM fraction is below the step's; see profiles/r1c for the ncu capture",
+                "note": "FP64-pipe bound (ncu: 56 % of the pipe, 64 DFMA/clk/SM; two half-length complex FFTs per row), so its HBM fraction is below the step's; see profiles/r1d for the ncu capture",
                 "timing": "CUDA events on the launching stream around every launch of one extra realisation after the timed region"}
         line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -1085,6 +1085,17 @@ __device__ __forceinline__ void twiddle16(double2* u, double2 w1, double2 w2, do
   }
 }
 
+// the same from a shared-memory table tab[r * 16 + b] = W_256^(b r): 15 conflict-free loads instead of 11 complex products
+template <int DIR>
+__device__ __forceinline__ void twiddle16_tab(double2* u, const double2* __restrict__ tab, int b) {
+#pragma unroll
+  for (int r = 1; r < 16; ++r) {
+    double2 w = tab[r * 16 + b];
+    if (DIR < 0) w.y = -w.y;
+    u[r] = c_mul(u[r], w);
+  }
+}
+
 #define Z16_H 256
 #define Z16_ROW 272   // 256 + one pad slot per 16
 
@@ -1094,7 +1105,8 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int H = Z16_H, ROW = Z16_ROW;
   double2* twn = reinterpret_cast<double2*>(smem_raw);   // [H + 8]  exp(-2 pi i j / nz), j <= H
-  double2* bufs = twn + (H + 8);                         // [WARPS][2 * ROW] exchange buffers
+  double2* tab = twn + (H + 8);                          // [16][16] inter-stage twiddles W_256^(b r) at [r * 16 + b]
+  double2* bufs = tab + 256;                             // [WARPS][2 * ROW] exchange buffers
   double2* inbs = bufs + WARPS * 2 * ROW;                // [WARPS][2 * in_len] staged input rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rho = lane >> 4, b = lane & 15;
@@ -1102,13 +1114,13 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
   double2* inw = inbs + warp * 2 * in_len;
   const double2* inb = inw + rho * in_len;
   for (int i = tid; i <= H; i += WARPS * 32) twn[i] = twn_g[i];
-  const double2 w1 = twh_g[b], w2 = twh_g[2 * b], w4 = twh_g[4 * b], w8 = twh_g[(8 * b) & (H - 1)];
+  for (int i = tid; i < 256; i += WARPS * 32) tab[i] = twh_g[((i >> 4) * (i & 15)) & (H - 1)];
   __syncthreads();
   const long long ngroups = (long long)g.nx * g.ny / 2;
   const long long gstep = (long long)gridDim.x * WARPS;
   const int nfb = A.nb > 1 ? A.nb : 1;
   const int Kz_in = A.Kz_in, Kz_out = A.Kz_out;
-  const double half = 0.5 * A.scale;
+  const double half = 0.5 * A.scale;   // 1/2 of the r2c post-processing and the caller's scale, folded into the weights
   auto prefetch_rows = [&](const double2* __restrict__ Qbase, long long r0) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
@@ -1132,7 +1144,10 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
     double2 wreg[WREG ? 16 : 1];
     if (WREG) {
 #pragma unroll
-      for (int r = 0; r < 16; ++r) wreg[WREG ? r : 0] = *reinterpret_cast<const double2*>(wrow + 32 * r);
+      for (int r = 0; r < 16; ++r) {
+        const double2 wv = *reinterpret_cast<const double2*>(wrow + 32 * r);
+        wreg[WREG ? r : 0] = make_double2(wv.x * half, wv.y * half);
+      }
     } else {
       asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + lane * 16));
       asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.wmap + grp * 2 * g.nz + 512 + lane * 16));
@@ -1176,12 +1191,13 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
       __syncwarp();
 #pragma unroll
       for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
-      twiddle16<-1>(u, w1, w2, w4, w8);
+      twiddle16_tab<-1>(u, tab, b);
       dft16<-1>(u);
       // ---- real-space step: x[2m], x[2m+1] at m = b + 16 r, times the weight map
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const double2 wv = WREG ? wreg[WREG ? r : 0] : *reinterpret_cast<const double2*>(wrow + 32 * r);
+        double2 wv = WREG ? wreg[WREG ? r : 0] : *reinterpret_cast<const double2*>(wrow + 32 * r);
+        if (!WREG) wv = make_double2(wv.x * half, wv.y * half);
         u[r].x *= wv.x;
         u[r].y *= wv.y;
       }
@@ -1193,7 +1209,7 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
       __syncwarp();
 #pragma unroll
       for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
-      twiddle16<1>(u, w1, w2, w4, w8);
+      twiddle16_tab<1>(u, tab, b);
       dft16<1>(u);
       // ---- r2c post-processing: T[k] = 1/2 (V[k] + conj V[H-k]) - i/2 e^{-2 pi i k/nz} (V[k] - conj V[H-k])
       double2* __restrict__ dst = A.R + (long long)fb * A.r_stride + row * A.Kzp_out;
@@ -1207,8 +1223,8 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
         const int k = b + 16 * r;
         if (16 * r < Kz_out && k < Kz_out) {
           const double2 v1 = u[r];
-          const double2 ev = make_double2(half * (v1.x + v2.x), half * (v1.y - v2.y));
-          const double2 dv = make_double2(half * (v1.x - v2.x), half * (v1.y + v2.y));
+          const double2 ev = make_double2(v1.x + v2.x, v1.y - v2.y);
+          const double2 dv = make_double2(v1.x - v2.x, v1.y + v2.y);
           const double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);
           dst[k] = make_double2(ev.x + od.x, ev.y + od.y);
         }
@@ -1548,7 +1564,7 @@ static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
 template <int WARPS, int MINB, bool WREG>
 static int launch_z16_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   const int in_len = up8(A.Kz_in);
-  const size_t smem = (size_t)(Z16_H + 8 + WARPS * 2 * Z16_ROW + WARPS * 2 * in_len) * sizeof(double2);
+  const size_t smem = (size_t)(Z16_H + 8 + 256 + WARPS * 2 * Z16_ROW + WARPS * 2 * in_len) * sizeof(double2);
   const long long ngroups = (long long)c->g.nx * c->g.ny / 2;
   const long long ctas = (ngroups + WARPS - 1) / WARPS;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -1565,10 +1581,12 @@ static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
   const int v = e ? atoi(e) : 0;
   switch (v) {
     case 1: return launch_z16_v<8, 2, false>(c, s, A);   // 16 warps/SM, weights loaded at the point of use (exposed latency)
-    case 2: return launch_z16_v<4, 3, true>(c, s, A);    // 12 warps/SM, weights in registers (small spills)
+    case 2: return launch_z16_v<8, 1, true>(c, s, A);    // 8 warps/SM, 224 registers
     case 3: return launch_z16_v<4, 4, false>(c, s, A);   // 16 warps/SM in 4-warp CTAs
     case 4: return launch_z16_v<4, 2, true>(c, s, A);    // 8 warps/SM in 4-warp CTAs, weights in registers
-    default: return launch_z16_v<8, 1, true>(c, s, A);   // 8 warps/SM, 246 registers: the weights of a row pair stay in registers for all planes (measured fastest)
+    // 12 warps/SM (3 CTAs of 4 warps, 168 registers, no spills): the weights of a row pair stay in registers for all
+    // planes of the group -- measured fastest (100.5 ms per C2 realisation vs 101.2 / 111.3 / 113.4 for cases 1 / 2 / 4)
+    default: return launch_z16_v<4, 3, true>(c, s, A);
   }
 }
 
