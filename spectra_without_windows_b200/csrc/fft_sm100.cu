@@ -701,8 +701,11 @@ __device__ __forceinline__ void w_mid_stages(double2* buf, const double2* tw, in
   if constexpr (WPlan<H>::NS == 3) w_mid_stage<H, DIR, REV, 1>(buf, tw, lane);
 }
 
+#ifndef ZW_INV_ONE_CTA
+#define ZW_INV_ONE_CTA 0   // 1: inverse-only variants at 255 registers / 8 warps per SM -- measured slower (the kernel is latency bound)
+#endif
 template <int H, bool INV, bool FWD, bool YLM>
-__global__ void __launch_bounds__(256, ((H >= 512 && INV) ? 1 : 2))
+__global__ void __launch_bounds__(256, ((H >= 512 && INV) || (INV && !FWD && ZW_INV_ONE_CTA)) ? 1 : 2)
 pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = 8;
@@ -717,9 +720,9 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
   double2* bufs = tabf + TF;                             // [WARPS][RW*ROWLEN (+8)]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double2* buf = bufs + warp * (RW * ROWLEN + 8);
-  // fused variant: the complex input rows of the NEXT plane stream into a second per-warp buffer (cp.async)
+  // inverse variants: the complex input rows of the NEXT plane stream into a second per-warp buffer (cp.async)
   // while the current plane is transformed, so no row waits on a DRAM round trip
-  constexpr bool PREF = INV && FWD;
+  constexpr bool PREF = INV;
   double2* inb = PREF ? bufs + WARPS * (RW * ROWLEN + 8) + warp * (RW * ROWLEN + 8) : buf;
   for (int i = tid; i <= H; i += 256) twn[i] = twn_g[i];
   w_fill_tab<H, false, 0>(tabi, twh_g, tid, 256);
@@ -742,7 +745,8 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
   }
   for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * WARPS) {
     const long long row0 = grp * RW;
-    const int nfb_all = (INV && FWD && A.nb > 1) ? A.nb : 1;
+    const int nfb_all = (INV && FWD && A.nb > 1) ? A.nb : 1;   // planes transformed one after the other (fused variant)
+    const int npl = (INV && A.nb > 1) ? A.nb : 1;                // planes of one row group in prefetch order
     int cur_fb = 0;
     double2 u[IPS][SE];
     // early prefetch of the weights only where the registers allow it: not with 16 values per lane
@@ -825,7 +829,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         __syncwarp();
         if (PREF) {
           // the staging buffer is free again: start the copy of the next plane of this warp
-          const bool wrap = cur_fb + 1 >= nfb_all;
+          const bool wrap = cur_fb + 1 >= npl;
           const long long ngrp = wrap ? grp + (long long)gridDim.x * WARPS : grp;
           if (ngrp < ngroups) prefetch_rows(A.Q + (wrap ? 0LL : (long long)(cur_fb + 1) * A.q_stride), ngrp * RW);
         }
@@ -863,6 +867,7 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 #pragma unroll
           for (int r = 0; r < SE; ++r) acc[s][r] = make_double2(0.0, 0.0);
         for (int bq = 0; bq < A.nb; ++bq) {
+          cur_fb = bq;
           do_inverse(A.Q + (long long)bq * A.q_stride);
           const int lmb = A.lms[bq];
           if (lmb >= 1 && A.ymaps) {
@@ -1551,7 +1556,7 @@ template <int H, bool INV, bool FWD, bool YLM>
 static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
   constexpr int WARPS = 8;
   size_t smem = (size_t)(H + 8 + WTabSize<H, false>::value + WTabSize<H, true>::value) * 16 +
-                (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16 * ((INV && FWD) ? 2 : 1);
+                (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16 * (INV ? 2 : 1);
   long long ngroups = (long long)c->g.nx * c->g.ny / WGeo<H>::RW;
   long long ctas = (ngroups + WARPS - 1) / WARPS;
   int grid = (int)(ctas < SMS * 2 ? ctas : SMS * 2);
