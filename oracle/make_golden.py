@@ -221,6 +221,10 @@ def run_ml(name):
             kk = (kmin, kmax, dk, lmax)
             np.save(mc + "%s%d_ML_pk_q-bar_a_k%.3f_%.3f_%.3f_l%d.npy" % ((w.type, r) + kk), qb)   # :116-117
             np.save(mc + "%s%d_ML_pk_fish_a_k%.3f_%.3f_%.3f_l%d.npy" % ((w.type, r) + kk), fish)
+        # include_pix = True, one seed (function level only)
+        np.random.seed(1)
+        a = np.random.normal(loc=0.0, scale=np.sqrt(nbar_A), size=nbar_A.shape)
+        out["ml_pk_qbar_pix_1"], out["ml_pk_fish_pix_1"] = ml_fisher_function_level(cp, a, dict(S, include_pix=True))
         rh.run_script("pk/compute_pk_data.py", 1, p)
         f = glob.glob(od + "pk_*_ML_*.txt")[0]
         out["ml_pk_txt_name"] = np.asarray(os.path.basename(f))

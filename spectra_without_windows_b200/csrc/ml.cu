@@ -481,7 +481,9 @@ extern "C" int sww_pk_fisher_realisation_ml(sww_ctx* c, sww_devptr a_, int max_i
                                             sww_devptr qbar_out, int32_t* total_iterations) {
   ML_READY(c);
   SWW_REQUIRE(a_ && fish_out && qbar_out, "null device pointer");
-  SWW_REQUIRE(!c->include_pix, "ML Fisher matrix: include_pix = True is not supported yet");
+  // include_pix = True: C_,alpha = M^-1 n IFT[...] n M^-1 / v (src/covariances_pk.py:371-372,396-397), N = M^-1 n M^-1,
+  // and M^-1 (a real, even filter) is self-adjoint, so it is moved onto the map each product is taken with
+  const bool pix = c->include_pix;
   MlBufs b;
   ml_layout(c, c->ar, b, true);
   ML_ARENA(c);
@@ -497,11 +499,20 @@ extern "C" int sww_pk_fisher_realisation_ml(sww_ctx* c, sww_devptr a_, int max_i
   LAUNCHED(c);
   SWW_TRY(ml_cg(c, b, b.cin, max_it, 1e-8, rel_tol, &it, nullptr));
   its += it;
-  c_part_kernel<<<ew_grid(), 256, 0, c->stream>>>(Nl, b.cx, 0, c->nbar, b.nCa);      // n * Re C^-1 a
+  c_part_kernel<<<ew_grid(), 256, 0, c->stream>>>(Nl, b.cx, 0, pix ? nullptr : c->nbar, b.nCa);   // [n *] Re C^-1 a
   LAUNCHED(c);
   SWW_TRY(k_div(c, a, c->nbar_A, b.tmp));                                            // A^-1 a
-  SWW_TRY(k_mul(c, b.tmp, c->nbar, 1.0, b.nAa));                                     // n A^-1 a
-  SWW_TRY(k_mul(c, b.tmp, c->nbar, c->shot / c->v_cell, b.NAa));                     // N A^-1 a
+  if (pix) {
+    SWW_TRY(sww_mas_filter_internal(c, b.nCa, -1, b.X, b.u));
+    SWW_TRY(k_mul(c, b.u, c->nbar, 1.0, b.nCa));                                     // n M^-1 Re C^-1 a
+    SWW_TRY(sww_mas_filter_internal(c, b.tmp, -1, b.X, b.u));
+    SWW_TRY(k_mul(c, b.u, c->nbar, 1.0, b.nAa));                                     // n M^-1 A^-1 a
+    SWW_TRY(sww_mas_filter_internal(c, b.nAa, -1, b.X, b.NAa));
+    SWW_TRY(k_mul(c, b.NAa, nullptr, c->shot / c->v_cell, b.NAa));                   // N A^-1 a = s M^-1 n M^-1 A^-1 a / v
+  } else {
+    SWW_TRY(k_mul(c, b.tmp, c->nbar, 1.0, b.nAa));                                   // n A^-1 a
+    SWW_TRY(k_mul(c, b.tmp, c->nbar, c->shot / c->v_cell, b.NAa));                   // N A^-1 a
+  }
   SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
   SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
   for (int alpha = 0; alpha < n_b; ++alpha) {
@@ -515,6 +526,10 @@ extern "C" int sww_pk_fisher_realisation_ml(sww_ctx* c, sww_devptr a_, int max_i
       SWW_TRY(sww_c2r(c, b.X, b.u));
       SWW_TRY(k_mul(c, b.u, c->nbar, 1.0 / (N * c->v_cell), b.u));
     }
+    if (pix) {
+      SWW_TRY(sww_mas_filter_internal(c, b.u, -1, b.X, b.tmp));
+      SWW_TRY(k_mul(c, b.tmp, nullptr, 1.0, b.u));
+    }
     // U_alpha = C^-1 [C_,alpha C^-1 a]
     c_from_real_kernel<<<ew_grid(), 256, 0, c->stream>>>(Nl, b.u, b.cin);
     LAUNCHED(c);
@@ -527,8 +542,15 @@ extern "C" int sww_pk_fisher_realisation_ml(sww_ctx* c, sww_devptr a_, int max_i
     SWW_CUDA(cudaMemcpyAsync(qbar + alpha, &qb, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SWW_CUDA(cudaStreamSynchronize(c->stream));
     // F_alpha,beta = 1/2 sum Re(U_alpha) n IFT[Theta_b G_l'] / v_cell, binned in Fourier space
-    c_part_kernel<<<ew_grid(), 256, 0, c->stream>>>(Nl, b.cx, 0, c->nbar, b.u);
-    LAUNCHED(c);
+    if (pix) {
+      c_part_kernel<<<ew_grid(), 256, 0, c->stream>>>(Nl, b.cx, 0, nullptr, b.tmp);
+      LAUNCHED(c);
+      SWW_TRY(sww_mas_filter_internal(c, b.tmp, -1, b.X, b.u));
+      SWW_TRY(k_mul(c, b.u, c->nbar, 1.0, b.u));
+    } else {
+      c_part_kernel<<<ew_grid(), 256, 0, c->stream>>>(Nl, b.cx, 0, c->nbar, b.u);
+      LAUNCHED(c);
+    }
     SWW_TRY(bin_against(c, b, b.u, b.G, 0.5 / (N * c->v_cell), F + (size_t)alpha * n_b));
   }
   SWW_TRY(k_symmetrise(c, F, n_b));

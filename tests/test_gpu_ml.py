@@ -67,9 +67,10 @@ def test_ml_fisher_realisation(eng, world, golden):
         assert its > mesh.n_k * mesh.n_l
         assert relerr(F.cpu().numpy(), g["ml_pk_fish_%d" % r]) < TOL
         assert relerr(qbar.cpu().numpy(), g["ml_pk_qbar_%d" % r]) < TOL
-    with pytest.raises(Exception, match="include_pix"):
-        ctx.set_include_pix(True)
-        ctx.pk_fisher_ml(S.grf(1))
+    ctx.set_include_pix(True)          # MAS forward-modelled in S, N, the preconditioner and C_,alpha
+    F, qbar, _ = ctx.pk_fisher_ml(S.grf(1))
+    assert relerr(F.cpu().numpy(), g["ml_pk_fish_pix_1"]) < TOL
+    assert relerr(qbar.cpu().numpy(), g["ml_pk_qbar_pix_1"]) < TOL
     ctx.close()
 
 

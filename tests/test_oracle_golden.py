@@ -154,6 +154,9 @@ def test_ml_fisher_and_spectrum(world, golden):
     qbar, F = orc.pk_fisher_realisation_ml(S, S.grf(1), pk_map)
     assert relerr(F, g["ml_pk_fish_1"]) < 1e-10
     assert relerr(qbar, g["ml_pk_qbar_1"]) < 1e-10
+    Sp = orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax, include_pix=True)
+    qbar, F = orc.pk_fisher_realisation_ml(Sp, Sp.grf(1), pk_map)
+    assert relerr(F, g["ml_pk_fish_pix_1"]) < 1e-10 and relerr(qbar, g["ml_pk_qbar_pix_1"]) < 1e-10
     # the unmodified pk/compute_pk_data.py run with weights = ML on those Fisher / bias files
     fish = 0.5 * (g["ml_pk_fish_1"] + g["ml_pk_fish_2"])
     bias = 0.5 * (g["ml_pk_qbar_1"] + g["ml_pk_qbar_2"])
