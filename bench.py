@@ -341,6 +341,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--fft", type=int, default=-1, help="FFT backend: 0 cuFFT, 1 hand-written sm_100a passes (default: auto = 1 on power-of-two meshes)")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="independent realisations in flight per GPU (one context + stream each): the tail of one "
+                         "realisation's kernels overlaps the next one's; 1 = strictly one after the other")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="after the timed region, one extra realisation with CUDA-event profiling per kernel family")
@@ -397,10 +400,31 @@ def main():
         del sig
         sig = None
         args.no_e2e = True
-    F_acc = torch.zeros((n_b, n_b), dtype=torch.float64, device=dev)
-    q_acc = torch.zeros((n_b,), dtype=torch.float64, device=dev)
-    F_i = torch.empty_like(F_acc)
-    q_i = torch.empty_like(q_acc)
+    # K independent realisations in flight: context k works on stream k (realisations are independent; their sums are
+    # combined at the end), so the tails of one realisation's kernels overlap the next one's
+    K = 1 if big else max(1, min(int(args.inflight), 4))
+    # every extra context brings its own workspace and Y_lm cache: only as many as the device memory holds, leaving
+    # room for the end-to-end buffers
+    torch.cuda.synchronize()
+    footprint = torch.cuda.memory_allocated(dev)
+    free_b, _total_b = torch.cuda.mem_get_info(dev)
+    K = max(1, min(K, 1 + int((free_b - (12 << 30)) // max(1, footprint))))
+    main_stream = torch.cuda.current_stream(dev)
+    ctxs, streams = [ctx], [main_stream]
+    for k in range(1, K):
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            ck = engine.Context(mesh, local, ("pk_fisher",))
+            if args.fft >= 0:
+                ck.set_fft_backend(args.fft)
+            ck.set_fields(nbar, nbar, nbar_A, SHOT)
+        ctxs.append(ck)
+        streams.append(st)
+    torch.cuda.synchronize()
+    F_acc = [torch.zeros((n_b, n_b), dtype=torch.float64, device=dev) for _ in range(K)]
+    q_acc = [torch.zeros((n_b,), dtype=torch.float64, device=dev) for _ in range(K)]
+    F_i = [torch.empty_like(F_acc[0]) for _ in range(K)]
+    q_i = [torch.empty_like(q_acc[0]) for _ in range(K)]
     flush = None
     if mesh.N * 8 <= 2 * 126e6:
         flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -411,37 +435,57 @@ def main():
         torch.cuda.synchronize()
 
     def step(i):
-        ctx.pk_fisher(a_dev[i % nbuf], F_i, q_i)
-        F_acc.add_(F_i)
-        q_acc.add_(q_i)
-        if flush is not None:
-            flush.fill_(i & 255)
+        k = i % K
+        with torch.cuda.stream(streams[k]):
+            ctxs[k].pk_fisher(a_dev[i % nbuf], F_i[k], q_i[k])
+            F_acc[k].add_(F_i[k])
+            q_acc[k].add_(q_i[k])
+            if flush is not None:
+                flush.fill_(i & 255)
+
+    def fork(ev):
+        ev.record(main_stream)
+        for st in streams[1:]:
+            st.wait_event(ev)
+
+    def join():
+        for st in streams[1:]:
+            main_stream.wait_stream(st)
 
     for i in range(args.warmup):
         step(i)
     barrier()
-    own0, fft0 = ctx.launch_counts()
+    counts0 = [c_.launch_counts() for c_ in ctxs]
     sampler = ClockSampler(local) if rank == 0 else None
-    F_acc.zero_()
-    q_acc.zero_()
+    for k in range(K):
+        F_acc[k].zero_()
+        q_acc[k].zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    fork(e0)
     for i in range(args.steps):
         step(i)
+    join()
+    for k in range(1, K):
+        F_acc[0].add_(F_acc[k])
+        q_acc[0].add_(q_acc[k])
     if world > 1:   # the only exchange of the path: partial Fisher / bias sums (pk/compute_pk_data.py:227-233)
-        dist.all_reduce(F_acc)
-        dist.all_reduce(q_acc)
-    e1.record()
+        dist.all_reduce(F_acc[0])
+        dist.all_reduce(q_acc[0])
+    e1.record(main_stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
-    own1, fft1 = ctx.launch_counts()
+    counts1 = [c_.launch_counts() for c_ in ctxs]
+    own0, fft0 = (sum(c_[j] for c_ in counts0) for j in (0, 1))
+    own1, fft1 = (sum(c_[j] for c_ in counts1) for j in (0, 1))
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
     value = world * args.steps / (ms * 1e-3)
+    F_iK, q_iK = F_i, q_i
+    F_i, q_i = F_iK[0], q_iK[0]
 
     # ---- end-to-end through the public API with HOST buffers (pinned): H2D of the field, D2H of F and q-bar
     e2e = None
@@ -449,32 +493,40 @@ def main():
         a_host = [torch.empty(mesh.shape, dtype=torch.float64).pin_memory() for _ in range(2)]
         for h, d in zip(a_host, a_dev):
             h.copy_(d)
-        F_host = torch.empty((n_b, n_b), dtype=torch.float64).pin_memory()
-        q_host = torch.empty((n_b,), dtype=torch.float64).pin_memory()
+        F_host = [torch.empty((n_b, n_b), dtype=torch.float64).pin_memory() for _ in range(K)]
+        q_host = [torch.empty((n_b,), dtype=torch.float64).pin_memory() for _ in range(K)]
         copy_stream = torch.cuda.Stream(device=dev)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
-        main_stream = torch.cuda.current_stream(dev)
+        B = 2 * K                                  # device field buffers: K in use, K being filled
+        a_e2e = list(a_dev) + [torch.empty_like(a_dev[0]) for _ in range(B - len(a_dev))]
+        ready = [torch.cuda.Event() for _ in range(B)]
+        freed = [torch.cuda.Event() for _ in range(B)]
 
         def e2e_run(n):
-            for j in range(2):
+            """Every realisation: H2D of its field from pinned memory (copy stream, K ahead), the Fisher realisation on
+            context i % K, D2H of F and q-bar."""
+            for j in range(B):
                 freed[j].record(main_stream)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[0])
-                a_dev[0].copy_(a_host[0], non_blocking=True)
-                ready[0].record(copy_stream)
+
+            def issue_copy(i):
+                j = i % B
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[j])
+                    a_e2e[j].copy_(a_host[i % 2], non_blocking=True)
+                    ready[j].record(copy_stream)
+
+            for i in range(min(K, n)):
+                issue_copy(i)
             for i in range(n):
-                j = i % 2
-                if i + 1 < n:
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(freed[1 - j])
-                        a_dev[1 - j].copy_(a_host[1 - j], non_blocking=True)
-                        ready[1 - j].record(copy_stream)
-                main_stream.wait_event(ready[j])
-                ctx.pk_fisher(a_dev[j], F_i, q_i)
-                freed[j].record(main_stream)
-                F_host.copy_(F_i, non_blocking=True)
-                q_host.copy_(q_i, non_blocking=True)
+                j, k = i % B, i % K
+                if i + K < n:
+                    issue_copy(i + K)
+                st = streams[k]
+                st.wait_event(ready[j])
+                with torch.cuda.stream(st):
+                    ctxs[k].pk_fisher(a_e2e[j], F_iK[k], q_iK[k])
+                    freed[j].record(st)
+                    F_host[k].copy_(F_iK[k], non_blocking=True)
+                    q_host[k].copy_(q_iK[k], non_blocking=True)
             torch.cuda.synchronize()
 
         e2e_run(1)
@@ -491,8 +543,8 @@ def main():
         t0 = time.perf_counter()
         for seed, a_f in ctx.field_pipeline([1000 * rank + i + 1 for i in range(args.steps)], sig):
             ctx.pk_fisher(a_f, F_i, q_i)
-            F_host.copy_(F_i, non_blocking=True)
-            q_host.copy_(q_i, non_blocking=True)
+            F_host[0].copy_(F_i, non_blocking=True)
+            q_host[0].copy_(q_i, non_blocking=True)
         torch.cuda.synchronize()
         dt_rng = time.perf_counter() - t0
         trng = torch.tensor([dt_rng], dtype=torch.float64, device=dev)
@@ -503,7 +555,7 @@ def main():
                "with_device_legacy_rng": {"value": world * args.steps / dt_rng, "unit": "realisations/s",
                                           "note": "numpy-legacy Gaussian field generated on the device (sww_grf_legacy, on a side stream, overlapped) + Fisher realisation; "
                                                   "the reference draws it on the host at ~5.4 s per 512^3 field per core"},
-               "d2h_bytes_per_step": int((n_b * n_b + n_b) * 8), "note": "field H2D from pinned memory (double-buffered on a copy stream), F and q-bar D2H; host RNG not included"}
+               "d2h_bytes_per_step": int((n_b * n_b + n_b) * 8), "note": "field H2D from pinned memory (copy stream, %d realisations ahead), F and q-bar D2H every step; host RNG not included" % K}
 
     prof = None
     if rank == 0 and (args.profile or ctx.fft_backend == 1):
@@ -566,7 +618,7 @@ def main():
         line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args.workload, mesh),
+                "config": dict(workload_config(args.workload, mesh), realisations_in_flight=K),
                 "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
                 "gpu_launches": int((own1 - own0) + (fft1 - fft0)) if ctx.fft_backend == 0 else int(own1 - own0),
                 "own_kernel_launches": int(own1 - own0), "library_fft_calls": int(fft1 - fft0) if ctx.fft_backend == 0 else 0,

@@ -120,6 +120,7 @@ extern "C" int sww_ctx_destroy(sww_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   sww_fft_destroy(c);
+  sww_rng_destroy(c);
   cudaFree(c->d_tables);
   cudaFree(c->d_binmap);
   cudaFree(c->d_partial);

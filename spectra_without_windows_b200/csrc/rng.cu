@@ -183,11 +183,29 @@ struct RngScratch {
   long long* running = nullptr;
   long long cap_attempts = 0;
   int cap_batch = 0;
+  unsigned h_state[8 * MT_N];   // host copy of the seeded states (source of an asynchronous upload)
   long long word_stride = 0, count_stride = 0, offset_stride = 0;
 };
-static RngScratch g_rng;
 
-static int rng_reserve(long long attempts, int batch) {
+static RngScratch& rng_of(sww_ctx* c) {
+  if (!c->rng) c->rng = new RngScratch();
+  return *(RngScratch*)c->rng;
+}
+
+void sww_rng_destroy(sww_ctx* c) {
+  RngScratch* r = (RngScratch*)c->rng;
+  if (!r) return;
+  cudaFree(r->flag);
+  cudaFree(r->state);
+  cudaFree(r->words);
+  cudaFree(r->counts);
+  cudaFree(r->offsets);
+  cudaFree(r->running);
+  delete r;
+  c->rng = nullptr;
+}
+
+static int rng_reserve(RngScratch& g_rng, long long attempts, int batch) {
   if (attempts <= g_rng.cap_attempts && batch <= g_rng.cap_batch) return 0;
   if (g_rng.words) {
     cudaFree(g_rng.words);
@@ -237,9 +255,10 @@ extern "C" int sww_grf_legacy_batch(sww_ctx* c, const uint32_t* seeds, int nseed
   // chunks of 624*2^14 words = 2.56 M attempts (a whole number of MT blocks)
   const long long blocks_per_chunk = 4LL << 14;                 // x624 words, divisible by 4 words per attempt
   const long long att_per_chunk = blocks_per_chunk * MT_N / 4;
-  SWW_TRY(rng_reserve(att_per_chunk, nseeds));
+  RngScratch& g_rng = rng_of(c);
+  SWW_TRY(rng_reserve(g_rng, att_per_chunk, nseeds));
   // init_genrand seeding (numpy mt19937_seed)
-  static unsigned h[RNG_MAX_BATCH * MT_N];
+  unsigned* h = g_rng.h_state;
   for (int b = 0; b < nseeds; ++b) {
     unsigned s = seeds[b];
     for (int pos = 0; pos < MT_N; ++pos) {
@@ -288,6 +307,8 @@ extern "C" int sww_grf_legacy_batch(sww_ctx* c, const uint32_t* seeds, int nseed
 // per field with the 8-sigma chunk plan; the caller would regenerate on the context stream)
 extern "C" int sww_grf_check(sww_ctx* c) {
   SWW_REQUIRE(c, "null context");
+  if (!c->rng) return 0;
+  RngScratch& g_rng = rng_of(c);
   if (!g_rng.flag) return 0;
   int f = 0;
   SWW_CUDA(cudaDeviceSynchronize());

@@ -104,6 +104,7 @@ struct sww_ctx {
   size_t fft_work_bytes = 0;   // bytes reserved for FFT scratch (cuFFT work area or the sm_100a pass buffers)
   size_t fft_work_cap = 0;
   void* sm100 = nullptr;       // Sm100State (fft_sm100.cu)
+  void* rng = nullptr;         // RngScratch (rng.cu)
   const double* ylm_maps = nullptr;   // optional cache [n_lm-1][N] of Y_lm(r^), lm >= 1
   // cuFFT
   cufftHandle plan_d2z = 0, plan_z2d = 0, plan_z2z = 0;
@@ -160,6 +161,7 @@ int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out);
 int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out);
 size_t sww_fft_sm100_work_bytes(const sww_ctx* c);
 void sww_fft_sm100_destroy(sww_ctx* c);
+void sww_rng_destroy(sww_ctx* c);   // rng.cu
 struct F3Args {
   double2* dst;
   int lm, first, mas_power;
