@@ -282,36 +282,71 @@ def run_bk(args, wl, mesh, rank, world, local, dev):
     aB = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig
     n_b = ctx.n_b_bk
     ctx.bk_delta()
-    F_acc = torch.zeros((n_b, n_b), dtype=torch.float64, device=dev)
-    maps = None
+    # K independent pairs in flight (context + stream each): the tensor-pipe-bound Gram of one pair overlaps the
+    # HBM-bound passes of the other at the kernel tails
+    K = max(1, min(int(args.inflight), 2))
+    torch.cuda.synchronize()
+    footprint = torch.cuda.memory_allocated(dev)      # at C4 the phi maps of one pair take ~150 GB: one pair at a time
+    free_b, _total_b = torch.cuda.mem_get_info(dev)
+    K = max(1, min(K, 1 + int((free_b - (24 << 30)) // max(1, footprint))))
+    main_stream = torch.cuda.current_stream(dev)
+    ctxs, streams = [ctx], [main_stream]
+    for k in range(1, K):
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            ck = engine.Context(mesh, local, ("bk_fisher",))
+            if args.fft >= 0:
+                ck.set_fft_backend(args.fft)
+            ck.set_fields(nbar, nbar, nbar_A, SHOT)
+            ck.bk_delta()
+        ctxs.append(ck)
+        streams.append(st)
+    torch.cuda.synchronize()
+    F_acc = [torch.zeros((n_b, n_b), dtype=torch.float64, device=dev) for _ in range(K)]
+    maps = [None] * K
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        F, maps = ctx.bk_fisher_pair(aA, aB, maps)
+    def step(i):
+        k = i % K
+        with torch.cuda.stream(streams[k]):
+            F, maps[k] = ctxs[k].bk_fisher_pair(aA, aB, maps[k])
+            F_acc[k].add_(F)
+
+    for i in range(max(args.warmup, K)):
+        step(i)
     barrier()
-    own0, fft0 = ctx.launch_counts()
+    counts0 = [c_.launch_counts() for c_ in ctxs]
     sampler = ClockSampler(local) if rank == 0 else None
+    for k in range(K):
+        F_acc[k].zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
-    for _ in range(args.steps):
-        F, maps = ctx.bk_fisher_pair(aA, aB, maps)
-        F_acc.add_(F)
+    e0.record(main_stream)
+    for st in streams[1:]:
+        st.wait_event(e0)
+    for i in range(args.steps):
+        step(i)
+    for st in streams[1:]:
+        main_stream.wait_stream(st)
+    for k in range(1, K):
+        F_acc[0].add_(F_acc[k])
     if world > 1:
-        dist.all_reduce(F_acc)
-    e1.record()
+        dist.all_reduce(F_acc[0])
+    e1.record(main_stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
-    own1, fft1 = ctx.launch_counts()
+    counts1 = [c_.launch_counts() for c_ in ctxs]
+    own0, own1 = sum(c_[0] for c_ in counts0), sum(c_[0] for c_ in counts1)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
+    maps = maps[0]
     prof = None
     if rank == 0:
         ctx.profile(True)
@@ -324,7 +359,7 @@ def run_bk(args, wl, mesh, rank, world, local, dev):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s: compute_bk_randoms Fisher pair (2 realisations per step), mesh %s, k in [%.3f,%.3f] dk=%.3f lmax=%d, %d triangles, n_b=%d"
                            % (args.workload, "x".join(str(int(g)) for g in mesh.grid), mesh.k_min, mesh.k_max, mesh.dk, mesh.lmax, ctx.n_tri, n_b),
-                           "l2": "inputs>L2"},
+                           "l2": "inputs>L2", "pairs_in_flight": K},
                 "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
                 "gpu_launches": int(own1 - own0), "clocks": clocks, "profile_one_pair": prof,
                 "gram_flop_per_pair": 2.0 * n_b * n_b * mesh.N}
