@@ -39,13 +39,24 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// chunk length of the plain Gram: 16 keeps a 3-stage tile set at 90 KB, so two CTAs (16 warps) share an SM and one
+// CTA's DMMAs cover the other's barrier / fragment-load bubbles
+#ifndef KCG
+#define KCG 32
+#endif
+#ifndef GRAM_CTAS
+#define GRAM_CTAS 2
+#endif
+#ifndef STAGES_G
+#define STAGES_G 2
+#endif
 struct GramSmem {
-  double A[STAGES][TM][KC + KPAD];
-  double B[STAGES][TN][KC + KPAD];
+  double A[STAGES_G][TM][KCG + KPAD];
+  double B[STAGES_G][TN][KCG + KPAD];
 };
 
 template <bool VEC16>
-__global__ void __launch_bounds__(GTHREADS, 1)
+__global__ void __launch_bounds__(GTHREADS, GRAM_CTAS)
 gram_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, int m, int n, long long K,
                  long long chunks_per_split, double* __restrict__ partial, int Mpad, int Npad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -53,7 +64,7 @@ gram_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, int
   const int mt = blockIdx.x, nt = blockIdx.y, ks = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps, warp tile 32 x 32
-  const long long total_chunks = (K + KC - 1) / KC;
+  const long long total_chunks = (K + KCG - 1) / KCG;
   long long c_begin = (long long)ks * chunks_per_split;
   long long c_end = c_begin + chunks_per_split;
   if (c_end > total_chunks) c_end = total_chunks;
@@ -66,11 +77,11 @@ gram_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, int
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   auto load_stage = [&](int stage, long long chunk) {
-    const long long k0 = chunk * KC;
+    const long long k0 = chunk * KCG;
     if (VEC16) {
       // 16-byte pieces: (TM+TN) rows x KC/2 pieces
-      for (int p = tid; p < (TM + TN) * (KC / 2); p += GTHREADS) {
-        int r = p / (KC / 2), q = p - r * (KC / 2);
+      for (int p = tid; p < (TM + TN) * (KCG / 2); p += GTHREADS) {
+        int r = p / (KCG / 2), q = p - r * (KCG / 2);
         long long k = k0 + 2 * q;
         if (r < TM) {
           int gi = row0 + r;
@@ -85,8 +96,8 @@ gram_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, int
         }
       }
     } else {
-      for (int p = tid; p < (TM + TN) * KC; p += GTHREADS) {
-        int r = p / KC, q = p - r * KC;
+      for (int p = tid; p < (TM + TN) * KCG; p += GTHREADS) {
+        int r = p / KCG, q = p - r * KCG;
         long long k = k0 + q;
         if (r < TM) {
           int gi = row0 + r;
@@ -104,23 +115,23 @@ gram_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, int
   const long long nchunks = c_end > c_begin ? c_end - c_begin : 0;
   // prologue
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
+  for (int s = 0; s < STAGES_G - 1; ++s) {
     if (s < nchunks) load_stage(s, c_begin + s);
     cp_async_commit();
   }
   for (long long it = 0; it < nchunks; ++it) {
-    cp_async_wait<STAGES - 2>();
+    cp_async_wait<STAGES_G - 2>();
     __syncthreads();
     // prefetch chunk it + STAGES-1 into the stage consumed at iteration it-1
     {
-      long long nx = it + STAGES - 1;
-      if (nx < nchunks) load_stage((int)(nx % STAGES), c_begin + nx);
+      long long nx = it + STAGES_G - 1;
+      if (nx < nchunks) load_stage((int)(nx % STAGES_G), c_begin + nx);
       cp_async_commit();
     }
-    const int st = (int)(it % STAGES);
+    const int st = (int)(it % STAGES_G);
     const int ar = wm * 32 + (lane >> 2), br = wn * 32 + (lane >> 2), kk = lane & 3;
 #pragma unroll
-    for (int k4 = 0; k4 < KC; k4 += 4) {
+    for (int k4 = 0; k4 < KCG; k4 += 4) {
       double a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = S.A[st][ar + 8 * i][k4 + kk];
@@ -325,8 +336,8 @@ static int gram_run(sww_ctx* c, const double* A, const double* B, int m, int n, 
   SWW_PROF(c, "gram.dmma f64");
   int mtiles = (m + TM - 1) / TM, ntiles = (n + TN - 1) / TN;
   int Mpad = mtiles * TM, Npad = ntiles * TN;
-  long long total_chunks = (K + KC - 1) / KC;
-  int ksplit = (148 * 2 + mtiles * ntiles - 1) / (mtiles * ntiles);
+  long long total_chunks = (K + KCG - 1) / KCG;
+  int ksplit = (148 * 2 * GRAM_CTAS + mtiles * ntiles - 1) / (mtiles * ntiles);   // two waves of resident CTAs
   if (ksplit > total_chunks) ksplit = (int)total_chunks;
   if (ksplit < 1) ksplit = 1;
   long long cps = (total_chunks + ksplit - 1) / ksplit;
