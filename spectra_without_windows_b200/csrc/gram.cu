@@ -190,8 +190,11 @@ struct Gram3Smem {
 // Tile: 128 (i,j) rows x 8 NJ columns.  Warps 0-3 and 4-7 cover the same four 32-row slabs and split each
 // K chunk in halves (the column count is small, so the second warp column of the plain Gram would idle);
 // the two halves are summed through shared memory at the end.
+#ifndef GRAM3_CTAS
+#define GRAM3_CTAS 2
+#endif
 template <int NJ>
-__global__ void __launch_bounds__(GTHREADS, 1)
+__global__ void __launch_bounds__(GTHREADS, GRAM3_CTAS)
 gram3_dmma_kernel(const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z, int ni, int nj,
                   int nz, long long K, long long chunks_per_split, double* __restrict__ partial, int Mpad, int Npad) {
   constexpr int TN3 = 8 * NJ;
@@ -386,7 +389,7 @@ static int gram3_launch(sww_ctx* c, const double* X, const double* Y, const doub
   int mtiles = (m + TM - 1) / TM, ntiles = (nz + TN3 - 1) / TN3;
   int Mpad = mtiles * TM, Npad = ntiles * TN3;
   long long total_chunks = (K + KC - 1) / KC;
-  int ksplit = (148 * 2 + mtiles * ntiles - 1) / (mtiles * ntiles);
+  int ksplit = (148 * 2 * GRAM3_CTAS + mtiles * ntiles - 1) / (mtiles * ntiles);
   if (ksplit > total_chunks) ksplit = (int)total_chunks;
   if (ksplit < 1) ksplit = 1;
   long long cps = (total_chunks + ksplit - 1) / ksplit;
