@@ -9,6 +9,6 @@ cap() {
   ncu -i gpurun_out/prof_c4_$1.ncu-rep --page source --csv > gpurun_out/source_c4_$1.csv 2>/dev/null
   rm -f gpurun_out/prof_c4_$1.ncu-rep
 }
-cap zinv 'pass_zw_kernel' 1500
+cap zinv 'pass_zw_kernel' ${ZSKIP:-1500}
 cap gram 'gram_dmma_kernel' 3
 ls -la gpurun_out | head -30
