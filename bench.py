@@ -359,7 +359,7 @@ def run_bk(args, wl, mesh, rank, world, local, dev):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s: compute_bk_randoms Fisher pair (2 realisations per step), mesh %s, k in [%.3f,%.3f] dk=%.3f lmax=%d, %d triangles, n_b=%d"
                            % (args.workload, "x".join(str(int(g)) for g in mesh.grid), mesh.k_min, mesh.k_max, mesh.dk, mesh.lmax, ctx.n_tri, n_b),
-                           "l2": "inputs>L2", "pairs_in_flight": K},
+                           "l2": "inputs>L2"}, "pairs_in_flight": K,
                 "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
                 "gpu_launches": int(own1 - own0), "clocks": clocks, "profile_one_pair": prof,
                 "gram_flop_per_pair": 2.0 * n_b * n_b * mesh.N}
@@ -653,7 +653,7 @@ def main():
         line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(workload_config(args.workload, mesh), realisations_in_flight=K),
+                "config": workload_config(args.workload, mesh), "realisations_in_flight": K,
                 "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
                 "gpu_launches": int((own1 - own0) + (fft1 - fft0)) if ctx.fft_backend == 0 else int(own1 - own0),
                 "own_kernel_launches": int(own1 - own0), "library_fft_calls": int(fft1 - fft0) if ctx.fft_backend == 0 else 0,
