@@ -263,9 +263,10 @@ class Context:
                                                  0 if stream is None else stream.cuda_stream))
         return outs[:len(seeds)]
 
-    def field_pipeline(self, seeds, sigma, batch=None):
+    def field_pipeline(self, seeds, sigma, batch=None, consumers=None):
         """Iterate device-generated legacy fields.  Batch j+1 (`batch` seeds, generated side by side) is produced on a
-        side stream while the caller's work on the fields of batch j runs on the context stream.  Yields (seed, field)."""
+        side stream while the caller's work on the fields of batch j runs on the `consumers` streams (default: the
+        context stream; several when realisations are kept in flight on several contexts).  Yields (seed, field)."""
         t = torch()
         sigma = self.dev(sigma)
         seeds = list(seeds)
@@ -277,29 +278,51 @@ class Context:
             batch = int(max(1, min(4, (0.08 * total) // (2 * 8 * sigma.numel()))))
         batch = max(1, min(int(batch), 8, len(seeds)))
         groups = [seeds[i:i + batch] for i in range(0, len(seeds), batch)]
+        consumers = list(consumers) if consumers else [self.stream]
         side = t.cuda.Stream(device=self.device)
         bufs = [[self.empty(tuple(sigma.shape)) for _ in range(batch)] for _ in range(2)]
-        main = self.stream
-        side.wait_stream(main)
+        for st in consumers:
+            side.wait_stream(st)
         self.grf_legacy_batch(groups[0], sigma, bufs[0], stream=side)
         done = t.cuda.Event()
         done.record(side)
-        used = []                       # used[j]: the caller's work on batch j has been enqueued up to here
+        used = []                       # used[j]: the consumers' work on batch j has been enqueued up to these events
         for j, grp in enumerate(groups):
-            main.wait_event(done)
+            for st in consumers:
+                st.wait_event(done)
             if j + 1 < len(groups):
                 if j >= 1:
-                    side.wait_event(used[j - 1])    # buffer set (j+1)%2 was last read by the work on batch j-1
-                # enqueue-only on the side stream: overlaps the caller's work on batch j
+                    for ev in used[j - 1]:
+                        side.wait_event(ev)     # buffer set (j+1)%2 was last read by the work on batch j-1
+                # enqueue-only on the side stream: overlaps the consumers' work on batch j
                 self.grf_legacy_batch(groups[j + 1], sigma, bufs[(j + 1) % 2], stream=side)
                 done = t.cuda.Event()
                 done.record(side)
             for i, s in enumerate(grp):
                 yield s, bufs[j % 2][i]
-            ev = t.cuda.Event()
-            ev.record(main)
-            used.append(ev)
+            evs = []
+            for st in consumers:
+                ev = t.cuda.Event()
+                ev.record(st)
+                evs.append(ev)
+            used.append(evs)
         _lib.check(self.lib.sww_grf_check(self._h))
+
+    def clone_for_stream(self, stream, pipelines=("pk_fisher",)):
+        """A second context on the same mesh, fields and settings that works on `stream`: independent realisations can
+        then be kept in flight side by side (the tails of one realisation's kernels overlap the other's)."""
+        t = torch()
+        with t.cuda.stream(stream):
+            c = Context(self.mesh, self.device.index, pipelines)
+            if c.fft_backend != self.fft_backend:
+                c.set_fft_backend(self.fft_backend)
+            n, nw, nA = self._fields
+            c.set_fields(n, nw, nA, self.shot_fac, self.P_fkp)
+            c.set_include_pix(getattr(self, "include_pix", False))
+            if getattr(self, "_pk_fid", None) is not None:      # ML weights: share the fiducial P_l(k) maps
+                c._pk_fid = self._pk_fid
+                _lib.check(c.lib.sww_set_fiducial_pk(c._h, c._pk_fid.data_ptr()))
+        return c
 
     # -- P_l(k)
     def pk_fisher(self, a, fish_out=None, qbar_out=None):

@@ -9,6 +9,8 @@ data-path collective: realisations are independent.
 
     torchrun --nproc-per-node 8 -m spectra_without_windows_b200.mc_driver pk <paramfile> [--per-seed]
 
+`--inflight K` (default 2, P_l(k) with device-generated fields): K realisations are kept in flight per GPU, each on
+its own context and stream, as far as the device memory holds K workspaces.
 `--per-seed` also writes the reference's per-seed checkpoint files, and seeds whose files already
 exist are skipped (the reference's idempotent re-entry, pk/compute_pk_randoms.py:121-127).
 The Gaussian fields follow numpy's legacy stream with the reference's seeds
@@ -81,6 +83,7 @@ def main(argv):
     spec, paramfile = argv[1], argv[2]
     per_seed = "--per-seed" in argv
     host_rng = "--host-rng" in argv
+    inflight = int(argv[argv.index("--inflight") + 1]) if "--inflight" in argv else 2
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -91,10 +94,16 @@ def main(argv):
     for d in (P.outdir, P.mcdir):
         os.makedirs(d, exist_ok=True)
     tag = P.ktag()
-    ctx, mesh, nbar_A, alpha_ran, shot_fac, _ = drivers._setup(P, 1, ("pk_fisher",) if spec == "pk" else ("bk_fisher",), paint_data=False)
+    pipe = (("pk_fisher",) if P.wtype == 0 else ("pk_ml",)) if spec == "pk" else ("bk_fisher",)
+    ctx, mesh, nbar_A, alpha_ran, shot_fac, _ = drivers._setup(P, 1, pipe, paint_data=False)
+    if P.wtype == 1:
+        P.load_fiducial_pk(ctx)
     sig = np.sqrt(nbar_A)
 
     sig_dev = None if host_rng else ctx.dev(sig)
+    import time
+    torch.cuda.synchronize()
+    t_loop = time.time()
 
     def grf(seed):
         # numpy's legacy global stream is not thread-safe: a private RandomState gives the same values
@@ -106,10 +115,14 @@ def main(argv):
         fish_name = lambda r: P.mcdir + "%s%d_%s_pk_fish_a_%s.npy" % (P.string, r, P.weight_type, tag)
         bias_name = lambda r: P.mcdir + "%s%d_%s_pk_q-bar_a_%s.npy" % (P.string, r, P.weight_type, tag)
 
-        def one(seed, a):
+        def one(seed, a, c=None):
+            c = c or ctx
             if per_seed and os.path.exists(fish_name(seed)) and os.path.exists(bias_name(seed)):
-                return ctx.dev(np.load(fish_name(seed))), ctx.dev(np.load(bias_name(seed)))
-            F, q = ctx.pk_fisher(a)
+                return c.dev(np.load(fish_name(seed))), c.dev(np.load(bias_name(seed)))
+            if P.wtype == 1:
+                F, q, _ = c.pk_fisher_ml(a, max_it=30, rel_tol=1e-6)
+            else:
+                F, q = c.pk_fisher(a)
             if per_seed:
                 np.save(fish_name(seed), F.cpu().numpy())
                 np.save(bias_name(seed), q.cpu().numpy())
@@ -119,12 +132,33 @@ def main(argv):
             (F, q), n = run_mc(range(1, P.N_mc + 1), one, lambda: (ctx.zeros((n_b, n_b)), ctx.zeros((n_b,))), rank, world,
                                dist if world > 1 else None, prefetch_fn=grf)
         else:
-            # device RNG: field i+1 is generated on a side stream while the Fisher kernels of field i run
-            F, q = ctx.zeros((n_b, n_b)), ctx.zeros((n_b,))
-            for seed, a in ctx.field_pipeline(shard(range(1, P.N_mc + 1), rank, world), sig_dev):
-                Fi, qi = one(seed, a)
-                F += Fi
-                q += qi
+            # device RNG: batch j+1 is generated on a side stream while the Fisher kernels of batch j run; K contexts
+            # on K streams keep K realisations in flight (as many as the device memory holds workspaces for)
+            torch.cuda.synchronize()
+            footprint = torch.cuda.memory_allocated()
+            free_b, _ = torch.cuda.mem_get_info()
+            K = max(1, min(inflight, 4, 1 + int((free_b - (12 << 30)) // max(1, footprint))))
+            if P.wtype == 1:
+                K = 1      # the conjugate-gradient solver synchronises with the host every iteration
+            ctxs, streams = [ctx], [ctx.stream]
+            for k in range(1, K):
+                st = torch.cuda.Stream()
+                ctxs.append(ctx.clone_for_stream(st, pipe))
+                streams.append(st)
+            Fk = [ctx.zeros((n_b, n_b)) for _ in range(K)]
+            qk = [ctx.zeros((n_b,)) for _ in range(K)]
+            torch.cuda.synchronize()
+            for i, (seed, a) in enumerate(ctx.field_pipeline(shard(range(1, P.N_mc + 1), rank, world), sig_dev, consumers=streams)):
+                k = i % K
+                with torch.cuda.stream(streams[k]):
+                    Fi, qi = one(seed, a, ctxs[k])
+                    Fk[k] += Fi
+                    qk[k] += qi
+            torch.cuda.synchronize()
+            F, q = Fk[0], qk[0]
+            for k in range(1, K):
+                F += Fk[k]
+                q += qk[k]
             reduce_sums([F, q], world > 1, dist if world > 1 else None)
         if rank == 0:
             np.save(P.outdir + "fisher-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (F / P.N_mc).cpu().numpy())
@@ -152,6 +186,11 @@ def main(argv):
                          prefetch_fn=(lambda p: (grf(2 * p), grf(2 * p + 1))) if host_rng else None, workers=1)
         if rank == 0:
             np.save(P.outdir + "fisher-bk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (F / (P.N_mc // 2)).cpu().numpy())
+    torch.cuda.synchronize()
+    if rank == 0:
+        dt = time.time() - t_loop
+        print("%s Monte-Carlo loop: %d realisations on %d GPU(s) in %.2f s (%.3f realisations/s, fields %s)"
+              % (spec, P.N_mc, world, dt, P.N_mc / dt, "from numpy on the host" if host_rng else "generated on the device"))
     if world > 1:
         dist.destroy_process_group()
 

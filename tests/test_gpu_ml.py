@@ -181,6 +181,16 @@ def test_ml_scripts_end_to_end(world, golden, tmp_path):
     assert os.path.basename(f) == str(g["ml_pk_txt_name"])
     assert open(f).read().split("\n")[:15] == str(g["ml_pk_txt"]).split("\n")[:15]
     assert relerr(np.loadtxt(f), g["ml_pk_p"]) < 2e-8
+    # the sharded Monte-Carlo driver produces the same combined Fisher / bias files from scratch
+    for f in glob.glob(od + "fisher-pk_*") + glob.glob(od + "bias-pk_*"):
+        os.remove(f)
+    r = subprocess.run([sys.executable, "-m", "spectra_without_windows_b200.mc_driver", "pk", p], capture_output=True, text=True,
+                       cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    fish = 0.5 * (g["ml_pk_fish_1"] + g["ml_pk_fish_2"])
+    bias = 0.5 * (g["ml_pk_qbar_1"] + g["ml_pk_qbar_2"])
+    assert relerr(np.load(glob.glob(od + "fisher-pk_*_ML_*.npy")[0]), fish) < TOL
+    assert relerr(np.load(glob.glob(od + "bias-pk_*_ML_*.npy")[0]), bias) < TOL
     # the bispectrum scripts refuse ML weights loudly
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bk/compute_bk_randoms.py"), "1", p], capture_output=True, text=True)
     assert r.returncode != 0 and "ML" in r.stderr
