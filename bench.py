@@ -576,10 +576,12 @@ def main():
         # the same loop with the field drawn ON THE DEVICE from numpy's legacy stream (no host RNG, no H2D)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for seed, a_f in ctx.field_pipeline([1000 * rank + i + 1 for i in range(args.steps)], sig):
-            ctx.pk_fisher(a_f, F_i, q_i)
-            F_host[0].copy_(F_i, non_blocking=True)
-            q_host[0].copy_(q_i, non_blocking=True)
+        for i, (seed, a_f) in enumerate(ctx.field_pipeline([1000 * rank + i + 1 for i in range(args.steps)], sig, consumers=streams)):
+            k = i % K
+            with torch.cuda.stream(streams[k]):
+                ctxs[k].pk_fisher(a_f, F_iK[k], q_iK[k])
+                F_host[k].copy_(F_iK[k], non_blocking=True)
+                q_host[k].copy_(q_iK[k], non_blocking=True)
         torch.cuda.synchronize()
         dt_rng = time.perf_counter() - t0
         trng = torch.tensor([dt_rng], dtype=torch.float64, device=dev)
@@ -588,8 +590,9 @@ def main():
         dt_rng = float(trng.item())
         e2e = {"value": world * args.steps / dt, "unit": "realisations/s", "h2d_bytes_per_step": int(mesh.N * 8),
                "with_device_legacy_rng": {"value": world * args.steps / dt_rng, "unit": "realisations/s",
-                                          "note": "numpy-legacy Gaussian field generated on the device (sww_grf_legacy, on a side stream, overlapped) + Fisher realisation; "
-                                                  "the reference draws it on the host at ~5.4 s per 512^3 field per core"},
+                                          "note": "numpy-legacy Gaussian fields generated on the device (sww_grf_legacy_batch, four seeds side by side on a side stream, "
+                                                  "overlapped) + Fisher realisations; short runs pay the first, un-overlapped batch (the N_mc = 100 product "
+                                                  "run reaches 4.1/s, DESIGN.md); the reference draws a field on the host in ~5.4 s per 512^3 per core"},
                "d2h_bytes_per_step": int((n_b * n_b + n_b) * 8), "note": "field H2D from pinned memory (copy stream, %d realisations ahead), F and q-bar D2H every step; host RNG not included" % K}
 
     prof = None
