@@ -330,8 +330,19 @@ gram3_dmma_kernel(const double* __restrict__ X, const double* __restrict__ Y, co
   }
 }
 
-static double* g_partial = nullptr;
-static size_t g_partial_bytes = 0;
+// split-K partial tiles: per-context scratch (two contexts may run Grams on two streams at the same time)
+static int gram_scratch(sww_ctx* c, size_t need, double** out) {
+  if (need > c->gram_partial_bytes) {
+    if (c->d_gram_partial) {
+      SWW_CUDA(cudaStreamSynchronize(c->stream));   // earlier launches of this context may still read the old buffer
+      cudaFree(c->d_gram_partial);
+    }
+    SWW_CUDA(cudaMalloc(&c->d_gram_partial, need));
+    c->gram_partial_bytes = need;
+  }
+  *out = c->d_gram_partial;
+  return 0;
+}
 
 static int gram_run(sww_ctx* c, const double* A, const double* B, int m, int n, long long K, int accumulate, double* C,
                     int ldc, int col0) {
@@ -346,11 +357,8 @@ static int gram_run(sww_ctx* c, const double* A, const double* B, int m, int n, 
   long long cps = (total_chunks + ksplit - 1) / ksplit;
   ksplit = (int)((total_chunks + cps - 1) / cps);
   size_t need = (size_t)ksplit * Mpad * Npad * sizeof(double);
-  if (need > g_partial_bytes) {
-    if (g_partial) cudaFree(g_partial);
-    SWW_CUDA(cudaMalloc(&g_partial, need));
-    g_partial_bytes = need;
-  }
+  double* g_partial = nullptr;
+  SWW_TRY(gram_scratch(c, need, &g_partial));
   size_t smem = sizeof(GramSmem);
   bool vec16 = (K % 2 == 0) && (((uintptr_t)A % 16) == 0) && (((uintptr_t)B % 16) == 0);
   dim3 grid(mtiles, ntiles, ksplit);
@@ -395,11 +403,8 @@ static int gram3_launch(sww_ctx* c, const double* X, const double* Y, const doub
   long long cps = (total_chunks + ksplit - 1) / ksplit;
   ksplit = (int)((total_chunks + cps - 1) / cps);
   size_t need = (size_t)ksplit * Mpad * Npad * sizeof(double);
-  if (need > g_partial_bytes) {
-    if (g_partial) cudaFree(g_partial);
-    SWW_CUDA(cudaMalloc(&g_partial, need));
-    g_partial_bytes = need;
-  }
+  double* g_partial = nullptr;
+  SWW_TRY(gram_scratch(c, need, &g_partial));
   size_t smem = sizeof(Gram3Smem);
   SWW_CUDA(cudaFuncSetAttribute(gram3_dmma_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(mtiles, ntiles, ksplit);

@@ -124,6 +124,8 @@ struct sww_ctx {
   size_t partial_elems = 0;
   unsigned int* d_counter = nullptr;
   int shell_rows = -1;   // rows of the shell-ordered store (-1: not decided yet)
+  double* d_gram_partial = nullptr;   // split-K partial tiles of the DMMA Grams (gram.cu)
+  size_t gram_partial_bytes = 0;
   double* d_q1_scratch = nullptr;
   size_t q1_scratch_elems = 0;
   // profiling
