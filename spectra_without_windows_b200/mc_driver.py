@@ -102,6 +102,8 @@ def main(argv):
 
     sig_dev = None if host_rng else ctx.dev(sig)
     import time
+    if world > 1:
+        dist.barrier()       # also builds the NCCL communicator now, not inside the final all-reduce
     torch.cuda.synchronize()
     t_loop = time.time()
 
@@ -148,6 +150,7 @@ def main(argv):
             Fk = [ctx.zeros((n_b, n_b)) for _ in range(K)]
             qk = [ctx.zeros((n_b,)) for _ in range(K)]
             torch.cuda.synchronize()
+            t_loop = time.time()      # the extra contexts are set-up, like the first one
             for i, (seed, a) in enumerate(ctx.field_pipeline(shard(range(1, P.N_mc + 1), rank, world), sig_dev, consumers=streams)):
                 k = i % K
                 with torch.cuda.stream(streams[k]):
