@@ -126,9 +126,10 @@ def _check_planes(m, g, key, tol):
         assert relerr(v, g[key + "_" + kk]) < tol, (key, kk)
 
 
+@pytest.mark.parametrize("name", ["toyA", "toyC"])     # toyC: odd mesh sizes (no Nyquist planes), k_min > 0, lmax = 2
 @pytest.mark.parametrize("pix", [False, True])
-def test_ml_operators_match_reference_functions(pix, world, golden):
-    w, g = world("toyA"), golden("toyA_ml")
+def test_ml_operators_match_reference_functions(pix, name, world, golden):
+    w, g = world(name), golden(name + "_ml")
     kmin, kmax, dk, lmax = w.pk_bins
     S = orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax, include_pix=pix)
     pk_map = orc.pk_map_from_table(S, g["ml_pk_table"])
