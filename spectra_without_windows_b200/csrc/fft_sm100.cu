@@ -14,8 +14,13 @@
 //             F3  x-axis  P -> epilogue: store into a spectrum, accumulate Y_lm(k^)-weighted, or bin
 //                         conj(T) G_l' straight into the k-shell histogram (no spectrum is written)
 //
-// The fused P_l Fisher row is I1 -> I2 -> Z(c2r * nW * r2c in shared memory) -> F2 -> F3(bin): the
-// real-space map u_alpha and its weighted transform never touch HBM.
+// The fused P_l Fisher rows of one k bin are I1 -> I2 -> Z(c2r * nW * r2c) -> F2 -> F3(shell-ordered store), batched over
+// the multipoles: the real-space map u_alpha and its weighted transform never touch HBM, and the k-shell reduction of
+// all rows is one launch of segmented dot products at the end (shell_dot_kernel).  Kernels of this file:
+//   pass_i1 / pass_i2 / pass_f2 / pass_f3   column passes (x or y axis), tiles of 8 z-columns in shared memory
+//   pass_zw_kernel                          z pass, one warp per row, generic in nz (inverse, forward or fused)
+//   pass_z16_fused_kernel                   the fused z pass for nz = 512: 256 = 16 x 16, two exchanges per row
+//   shell_sort_g / shell_dot / shell_dot_reduce   shell-ordered G maps and the segmented products
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
