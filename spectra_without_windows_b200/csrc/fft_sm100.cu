@@ -1244,6 +1244,165 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused z pass for nz = 1024 (H = 512 = 2 x 16 x 16), one row per warp.  EXPERIMENTAL: selected only with SWW_Z32=1
+// (written at the end of round 1 without GPU time left to validate it; its index algebra is pinned by the numpy model
+// tests/test_z32_model_cpu.py, the nz = 512 kernel above is its validated template).
+//   * the half-warps p = lane >> 4 run the even / odd 256-point transforms of the 512-point half-length FFT in the
+//     two-exchange layout of pass_z16_fused_kernel (lane b < 16 holds 16 complex values at n = b + 16 r);
+//   * inverse: decimation in frequency -- A[n] = Y[n] + Y[n+256] (p = 0), B[n] = (Y[n] - Y[n+256]) e^{+2 pi i n/512}
+//     (p = 1), both formed straight from the staged Hermitian row, so x_c[2q + p] comes out of half-warp p;
+//   * forward: decimation in time -- E, O from the same registers, joined by ONE xor-16 shuffle exchange:
+//     V[j] = E[j] + W^j O[j] (kept by p = 0), V[j + 256] = E[j] - W^j O[j] (kept by p = 1);
+//   * r2c post-processing on the p = 0 lanes: V[512 - k] sits in half-warp 1, lane 16 - b, register 15 - r.
+// ------------------------------------------------------------------------------------------
+#define Z32_H 512
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+pass_z32_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g, int in_len) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = Z32_H, ROW = Z16_ROW;
+  double2* twn = reinterpret_cast<double2*>(smem_raw);   // [H + 8]  exp(-2 pi i j / nz), j <= H
+  double2* tab = twn + (H + 8);                          // [16][16] inter-stage twiddles W_256^(b r) at [r * 16 + b]
+  double2* bufs = tab + 256;                             // [WARPS][2 * ROW] exchange buffers (one per half-warp)
+  double2* inbs = bufs + WARPS * 2 * ROW;                // [WARPS][in_len] staged input row
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p = lane >> 4, b = lane & 15;
+  double2* buf = bufs + warp * 2 * ROW + p * ROW;
+  double2* inb = inbs + warp * in_len;
+  for (int i = tid; i <= H; i += WARPS * 32) twn[i] = twn_g[i];
+  for (int i = tid; i < 256; i += WARPS * 32) tab[i] = twh_g[(2 * (i >> 4) * (i & 15)) & (H - 1)];   // W_512^(2 b r)
+  __syncthreads();
+  const long long nrows = (long long)g.nx * g.ny;
+  const long long gstep = (long long)gridDim.x * WARPS;
+  const int nfb = A.nb > 1 ? A.nb : 1;
+  const int Kz_in = A.Kz_in, Kz_out = A.Kz_out;
+  const double half = 0.5 * A.scale;
+  auto prefetch_row = [&](const double2* __restrict__ Qbase, long long r0) {
+    const double2* src = Qbase + r0 * A.Kzp_in;
+    for (int k = lane; k < Kz_in; k += 32) {
+      unsigned sa = (unsigned)__cvta_generic_to_shared(inb + k);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+    }
+  };
+  // Y[k] of the half-length sequence from the staged row (zero where neither k nor H - k is kept)
+  auto hermY = [&](int k) -> double2 {
+    const int hk = H - k;
+    if (!(k < Kz_in || hk < Kz_in)) return make_double2(0.0, 0.0);
+    double2 zk = (k < Kz_in) ? inb[k] : make_double2(0.0, 0.0);
+    double2 zh = (hk < Kz_in) ? inb[hk] : make_double2(0.0, 0.0);
+    if (k == 0) {
+      zk.y = 0.0;
+      zh.y = 0.0;
+    }
+    const double2 a = make_double2(zk.x + zh.x, zk.y - zh.y);
+    const double2 d = make_double2(zk.x - zh.x, zk.y + zh.y);
+    double2 w = twn[k];
+    w.y = -w.y;
+    const double2 bb = c_mul(d, w);
+    return make_double2(a.x - bb.y, a.y + bb.x);
+  };
+  long long row = (long long)blockIdx.x * WARPS + warp;
+  if (row < nrows) prefetch_row(A.Q, row);
+  asm volatile("cp.async.commit_group;\n" ::);
+  for (; row < nrows; row += gstep) {
+    const double* __restrict__ wrow = A.wmap + row * g.nz + 4 * b + 2 * p;
+    double2 wreg[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const double2 wv = *reinterpret_cast<const double2*>(wrow + 64 * r);
+      wreg[r] = make_double2(wv.x * half, wv.y * half);
+    }
+    for (int fb = 0; fb < nfb; ++fb) {
+      double2 u[16];
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncwarp();
+      // ---- inverse: pre-processing + radix-2 decimation in frequency, straight into stage 0 of the 256-point transforms
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        u[r] = make_double2(0.0, 0.0);
+        // warp-uniform: some n, 512 - n, n + 256 or 256 - n of this block of 16 is kept
+        if (16 * r < Kz_in || 497 - 16 * r < Kz_in || 16 * r + 256 < Kz_in || 241 - 16 * r < Kz_in) {
+          const int n = b + 16 * r;
+          const double2 y0 = hermY(n), y1 = hermY(n + 256);
+          if (p == 0) {
+            u[r] = make_double2(y0.x + y1.x, y0.y + y1.y);
+          } else {
+            double2 w = twn[2 * n];      // e^{-2 pi i n/512}; conjugate for the inverse
+            w.y = -w.y;
+            u[r] = c_mul(make_double2(y0.x - y1.x, y0.y - y1.y), w);
+          }
+        }
+      }
+      __syncwarp();
+      {
+        const bool wrap = fb + 1 >= nfb;
+        const long long nrow = wrap ? row + gstep : row;
+        if (nrow < nrows) prefetch_row(A.Q + (wrap ? 0LL : (long long)(fb + 1) * A.q_stride), nrow);
+        asm volatile("cp.async.commit_group;\n" ::);
+      }
+      dft16<-1>(u);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+      twiddle16_tab<-1>(u, tab, b);
+      dft16<-1>(u);
+      // ---- real-space step: u[r] = x_c[2 q + p] = (x[4q + 2p], x[4q + 2p + 1]) at q = b + 16 r
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        u[r].x *= wreg[r].x;
+        u[r].y *= wreg[r].y;
+      }
+      // ---- forward: E (p = 0) and O (p = 1) from the same registers
+      dft16<1>(u);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+      twiddle16_tab<1>(u, tab, b);
+      dft16<1>(u);
+      // ---- radix-2 join: V[j] = E[j] + W_512^j O[j] (p = 0),  V[j + 256] = E[j] - W_512^j O[j] (p = 1),  j = b + 16 r
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        double2 o;
+        o.x = __shfl_xor_sync(0xffffffffu, u[r].x, 16);
+        o.y = __shfl_xor_sync(0xffffffffu, u[r].y, 16);
+        const double2 e = p == 0 ? u[r] : o;           // E[j]
+        const double2 od = p == 0 ? o : u[r];          // O[j]
+        const double2 t = c_mul(od, twn[2 * (b + 16 * r)]);
+        u[r] = p == 0 ? make_double2(e.x + t.x, e.y + t.y) : make_double2(e.x - t.x, e.y - t.y);
+      }
+      // ---- r2c post-processing on the p = 0 lanes: T[k] = (V[k] + conj V[H-k]) - i e^{-2 pi i k/nz} (V[k] - conj V[H-k])
+      //      (the 1/2 is folded into the weights);  V[512 - k] = V[(256 - k) + 256]: half-warp 1, lane 16 - b, register
+      //      15 - r; for b = 0 lane 16 holds it in register 16 - r, so that lane offers that register instead
+      double2* __restrict__ dst = A.R + (long long)fb * A.r_stride + row * A.Kzp_out;
+      const int src_lane = 16 | ((16 - b) & 15);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        if (16 * r < Kz_out) {                          // warp-uniform
+          const double2 offer = (lane == 16) ? u[(16 - r) & 15] : u[15 - r];
+          double2 v2;
+          v2.x = __shfl_sync(0xffffffffu, offer.x, src_lane);
+          v2.y = __shfl_sync(0xffffffffu, offer.y, src_lane);
+          const int k = b + 16 * r;
+          if (k == 0) v2 = u[0];                        // V[512] = V[0]
+          if (p == 0 && k < Kz_out) {
+            const double2 v1 = u[r];
+            const double2 ev = make_double2(v1.x + v2.x, v1.y - v2.y);
+            const double2 dv = make_double2(v1.x - v2.x, v1.y + v2.y);
+            const double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);
+            dst[k] = make_double2(ev.x + od.x, ev.y + od.y);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct Sm100State {
@@ -1586,6 +1745,21 @@ static int launch_z16_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   return 0;
 }
 
+static int launch_z32(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 4, MINB = 3;
+  const int in_len = up8(A.Kz_in);
+  const size_t smem = (size_t)(Z32_H + 8 + 256 + WARPS * 2 * Z16_ROW + WARPS * in_len) * sizeof(double2);
+  const long long nrows = (long long)c->g.nx * c->g.ny;
+  const long long ctas = (nrows + WARPS - 1) / WARPS;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > MINB) per_sm = MINB;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm);
+  SWW_TRY((set_smem(pass_z32_fused_kernel<WARPS, MINB>, smem)));
+  pass_z32_fused_kernel<WARPS, MINB><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, in_len);
+  return 0;
+}
+
 static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
   const char* e = getenv("SWW_Z16_VARIANT");
   const int v = e ? atoi(e) : 0;
@@ -1607,6 +1781,13 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   const int H = c->g.nz / 2;
   const bool ylm = A.lm >= 0;
   const bool no_z16 = getenv("SWW_NO_Z16") != nullptr;   // A/B switch (tests, profiling)
+  if (inv && fwd && !ylm && H == Z32_H && A.wmap && A.Kz_out <= 256 && A.Kz_in <= Z32_H + 1 && getenv("SWW_Z32") != nullptr) {
+    // experimental (not yet validated on a GPU): opt-in only
+    SWW_TRY(launch_z32(c, s, A));
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (inv && fwd && !ylm && H == Z16_H && A.wmap && A.Kz_out <= 128 && A.Kz_in <= Z16_H + 1 && !no_z16 &&
       (c->g.nx * (long long)c->g.ny) % 2 == 0) {
     SWW_TRY(launch_z16(c, s, A));
