@@ -159,3 +159,30 @@ def test_fused_z_pass_nz512_two_exchange_kernel(eng):
     assert relerr(F1, F2) < 1e-12 and relerr(q1, q2) < 1e-12
     assert relerr(F1, F0) < 1e-11 and relerr(q1, q0) < 1e-11
     ctx.close()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SWW_TEST_Z32"), reason="experimental nz = 1024 kernel: opt-in (SWW_TEST_Z32=1)")
+def test_fused_z_pass_nz1024_experimental_kernel(eng):
+    """pass_z32_fused_kernel (SWW_Z32=1) against the generic fused z pass and the cuFFT backend on a 64 x 64 x 1024 mesh."""
+    import os
+    from spectra_without_windows_b200 import synthetic as syn
+    grid, box, bc = (64, 64, 1024), (1280.0, 1408.0, 10240.0), (1700.0, 60.0, -45.0)
+    mesh = eng.Mesh(box, grid, bc, 0.0, 0.12, 0.02, 4)
+    ctx = eng.Context(mesh, 0, ("ops", "pk_fisher"))
+    ctx.set_fft_backend(1)
+    nbar_r = syn.survey_nbar(box, grid, bc, n0=6e-3)
+    nbar_A = ctx.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)
+    a = np.random.default_rng(7).normal(size=grid) * np.sqrt(nbar_A)
+    F_ref, q_ref = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+    os.environ["SWW_Z32"] = "1"
+    try:
+        F1, q1 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+        F1b, _ = ctx.pk_fisher(a)
+    finally:
+        del os.environ["SWW_Z32"]
+    assert np.array_equal(F1, F1b.cpu().numpy())
+    assert relerr(F1, F_ref) < 1e-12 and relerr(q1, q_ref) < 1e-12
+    ctx.set_fft_backend(0)
+    F0, q0 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+    assert relerr(F1, F0) < 1e-11 and relerr(q1, q0) < 1e-11
+    ctx.close()
