@@ -26,6 +26,27 @@ def test_params_roundtrip(tmp_path, world):
         drivers.Params(str(tmp_path) + "/missing.param", "pk")
 
 
+def test_params_ml_weights(tmp_path, world):
+    """weights = ML: the fiducial_pk table is located like pk/compute_pk_randoms.py:69-71 and covers every |k| of the mesh;
+    the bispectrum scripts refuse ML loudly; anything but FKP / ML raises the reference's message."""
+    w = world("toyA")
+    p = synthetic.write_world_files(w, str(tmp_path), weights="ML")
+    P = drivers.Params(p, "pk")
+    assert P.wtype == 1 and P.weight_type == "ML" and os.path.exists(P.pk_input_file)
+    P.unsupported()                                     # P_l(k): supported
+    tab = np.loadtxt(P.pk_input_file)
+    assert tab.shape[1] == 4 and tab[0, 0] == 0.0
+    mesh = engine.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    k_top = np.sqrt(sum(np.max(np.abs(a)) ** 2 for a in mesh.kax))
+    assert tab[-1, 0] > k_top                           # interp1d would raise otherwise
+    with pytest.raises(Exception, match="ML"):
+        drivers.Params(p, "bk").unsupported()
+    bad = str(tmp_path) + "/bad.param"
+    open(bad, "w").write(open(p).read().replace("weights = ML", "weights = XYZ"))
+    with pytest.raises(Exception, match="weights must be 'FKP' or 'ML'"):
+        drivers.Params(bad, "pk")
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference paramfiles only exist in the build container")
 def test_reference_paramfiles_parse_unchanged():
     files = sorted(glob.glob(REF + "/*.param"))
