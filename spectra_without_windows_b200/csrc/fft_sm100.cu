@@ -1508,8 +1508,22 @@ static int set_smem(K kernel, size_t smem) {
   return 0;
 }
 
+// SWW_GRID_OVERSUB (default 1): the passes are persistent kernels with one static share of the work per resident CTA, so a
+// CTA slot taken by a co-running kernel (the single-CTA MT19937 recurrences of the device RNG, NCCL, another context)
+// delays a full share to the end of the launch.  A factor G > 1 launches G times more, G times shorter CTAs, so that a
+// missing slot costs 1/G of a launch instead.  Not yet evaluated on a GPU (added after the round's budget was spent).
+static long long grid_oversub() {
+  static long long v = 0;
+  if (v == 0) {
+    const char* e = getenv("SWW_GRID_OVERSUB");
+    v = e ? atoll(e) : 1;
+    if (v < 1 || v > 64) v = 1;
+  }
+  return v;
+}
+
 static inline int grid_for_items(long long items, int per_sm) {
-  long long g = (long long)SMS * per_sm;
+  long long g = (long long)SMS * per_sm * grid_oversub();
   return (int)(items < g ? items : g);
 }
 
@@ -1723,7 +1737,8 @@ static int launch_zw(sww_ctx* c, Sm100State* s, ZArgs A) {
                 (size_t)WARPS * (WGeo<H>::RW * WGeo<H>::ROWLEN + 8) * 16 * (INV ? 2 : 1);
   long long ngroups = (long long)c->g.nx * c->g.ny / WGeo<H>::RW;
   long long ctas = (ngroups + WARPS - 1) / WARPS;
-  int grid = (int)(ctas < SMS * 2 ? ctas : SMS * 2);
+  const long long slots = (long long)SMS * 2 * grid_oversub();
+  int grid = (int)(ctas < slots ? ctas : slots);
   SWW_TRY(set_smem(pass_zw_kernel<H, INV, FWD, YLM>, smem));
   pass_zw_kernel<H, INV, FWD, YLM><<<grid, 256, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n);
   return 0;
@@ -1739,7 +1754,7 @@ static int launch_z16_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm > MINB) per_sm = MINB;
   if (per_sm < 1) per_sm = 1;
-  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm);
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm * grid_oversub());
   SWW_TRY((set_smem(pass_z16_fused_kernel<WARPS, MINB, WREG>, smem)));
   pass_z16_fused_kernel<WARPS, MINB, WREG><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, in_len);
   return 0;
