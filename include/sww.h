@@ -70,6 +70,11 @@ int sww_profile_enable(sww_ctx* c, int enable);
 int sww_profile_report(sww_ctx* c, char* buf, uint64_t buf_bytes);
 /* choose the FFT backend: 0 = cuFFT, 1 = hand-written sm_100a passes (power-of-two meshes) */
 int sww_set_fft_backend(sww_ctx* c, int backend);
+/* Coarse row mesh of the P_l(k) Fisher rows (the n_b evaluations of applyC_alpha_single,
+ * src/covariances_pk.py:404-466, that pk/compute_pk_randoms.py:220-275 loops over): the band-limited products
+ * are evaluated exactly on the smallest power-of-two grid M_i >= 2 (2 b_i + 1), b_i = largest binned mode index.
+ * grid[3] receives M (zeros when the rows run on the full mesh; SWW_ROW_MESH=0 disables it). */
+int sww_row_mesh(sww_ctx* c, int32_t grid[3]);
 
 /* n(r) maps: nbar (load_nbar(...,alpha_ran) or painted randoms), nbar_weight, nbar_A
  * (pk/compute_pk_randoms.py:135-136,160,173-179).  Borrowed device pointers, double[N]. */

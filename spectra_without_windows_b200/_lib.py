@@ -33,6 +33,7 @@ SIGNATURES = {
     "sww_bind_workspace": [ctxp, u64, u64],
     "sww_launch_counts": [ctxp, C.POINTER(u64), C.POINTER(u64)],
     "sww_set_fft_backend": [ctxp, C.c_int],
+    "sww_row_mesh": [ctxp, C.POINTER(i32)],
     "sww_profile_enable": [ctxp, C.c_int],
     "sww_profile_report": [ctxp, C.c_char_p, u64],
     "sww_ylm_cache_bytes": [ctxp, C.POINTER(u64)],

@@ -19,10 +19,9 @@
 #include "sww_internal.cuh"
 #include "ylm_gen.cuh"
 
-#define SMS 148
 
 int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
-                             double2* spec, double2* const* out);
+                             double2* spec, double2* const* out, const sww_ctx* out_mesh = nullptr);
 size_t sww_sm100_qstack_bytes(const sww_ctx* c, int nb);
 int sww_gram3(sww_ctx* c, const double* X, const double* Y, const double* Z, int ni, int nj, int nz, long long K, double* C);
 int sww_gram_upper(sww_ctx* c, const double* A, const double* B, int m, int n, long long K, int row_limit,

@@ -29,18 +29,12 @@ static int max_abs_index_below(const double* kax, int n, double kmax) {
   return best;
 }
 
-extern "C" int sww_ctx_create(const sww_geometry* geo, sww_ctx** out) {
-  SWW_REQUIRE(geo && out, "null argument");
-  SWW_REQUIRE(geo->lmax >= 0 && geo->lmax % 2 == 0 && geo->lmax <= 2 * (SWW_MAX_L - 1),
-              "l-max must be even and <= %d", 2 * (SWW_MAX_L - 1));
-  SWW_REQUIRE(geo->n_k >= 1 && geo->n_k <= SWW_MAX_BINS, "n_k must be in [1,%d]", SWW_MAX_BINS);
-  for (int d = 0; d < 3; ++d) SWW_REQUIRE(geo->grid[d] >= 4, "grid too small");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  SWW_REQUIRE(e == cudaSuccess && ndev > 0, "no CUDA device: libsww has no CPU path (%s)", cudaGetErrorString(e));
-  SWW_CUDA(cudaSetDevice(geo->device));
-  sww_ctx* c = new sww_ctx();
+int sww_rowmesh_create(sww_ctx* c, const sww_geometry* geo);   // rowmesh.cu
+int sww_rowmesh_prepare(sww_ctx* c);                            // rowmesh.cu
+
+static int ctx_fill(sww_ctx* c, const sww_geometry* geo, bool child) {
   c->device = geo->device;
+  c->is_child = child;
   {
     const char* e = getenv("SWW_TIGHT_WS");
     c->tight_ws = e && e[0] == '1';
@@ -65,11 +59,7 @@ extern "C" int sww_ctx_create(const sww_geometry* geo, sww_ctx** out) {
   // Hermitian (R2C) evaluation requires every binned mode to lie strictly below Nyquist on every axis
   for (int d = 0; d < 3; ++d) {
     double kny = M_PI * geo->grid[d] / geo->box[d];
-    if (!(kmax < kny)) {
-      sww_set_error("k_max=%.6g is not below the Nyquist frequency %.6g of axis %d", kmax, kny, d);
-      delete c;
-      return -1;
-    }
+    SWW_REQUIRE(kmax < kny, "k_max=%.6g is not below the Nyquist frequency %.6g of axis %d", kmax, kny, d);
   }
   g.bx = max_abs_index_below(geo->kax[0], g.nx, kmax);
   g.by = max_abs_index_below(geo->kax[1], g.ny, kmax);
@@ -105,20 +95,50 @@ extern "C" int sww_ctx_create(const sww_geometry* geo, sww_ctx** out) {
   }
   SWW_CUDA(cudaMalloc(&c->d_binmap, (size_t)g.Nc));
   g.binmap = c->d_binmap;
-  c->partial_elems = (size_t)148 * 4 * SWW_MAX_L * SWW_MAX_BINS;
+  c->partial_elems = (size_t)SMS * 4 * SWW_MAX_L * SWW_MAX_BINS;
   SWW_CUDA(cudaMalloc(&c->d_partial, c->partial_elems * sizeof(double)));
   SWW_CUDA(cudaMalloc(&c->d_counter, 16 * sizeof(unsigned int)));
   SWW_CUDA(cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned int)));
   SWW_TRY(k_build_binmap(c));
-  SWW_TRY(sww_fft_init(c));
+  if (child) {
+    // the row mesh only ever runs the hand-written passes: no cuFFT plans
+    c->fft_work_bytes = sww_fft_sm100_work_bytes(c);
+    c->fft_backend = 1;
+  } else {
+    SWW_TRY(sww_fft_init(c));
+    SWW_TRY(sww_rowmesh_create(c, geo));
+  }
   SWW_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int sww_ctx_create_internal(const sww_geometry* geo, sww_ctx** out, bool child) {
+  SWW_REQUIRE(geo && out, "null argument");
+  SWW_REQUIRE(geo->lmax >= 0 && geo->lmax % 2 == 0 && geo->lmax <= 2 * (SWW_MAX_L - 1),
+              "l-max must be even and <= %d", 2 * (SWW_MAX_L - 1));
+  SWW_REQUIRE(geo->n_k >= 1 && geo->n_k <= SWW_MAX_BINS, "n_k must be in [1,%d]", SWW_MAX_BINS);
+  for (int d = 0; d < 3; ++d) SWW_REQUIRE(geo->grid[d] >= 4, "grid too small");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  SWW_REQUIRE(e == cudaSuccess && ndev > 0, "no CUDA device: libsww has no CPU path (%s)", cudaGetErrorString(e));
+  SWW_CUDA(cudaSetDevice(geo->device));
+  sww_ctx* c = new sww_ctx();
+  int r = ctx_fill(c, geo, child);
+  if (r != 0) {
+    sww_ctx_destroy(c);   // every failure path releases the tables, plans and the child context
+    return r;
+  }
   *out = c;
   return 0;
 }
 
+extern "C" int sww_ctx_create(const sww_geometry* geo, sww_ctx** out) { return sww_ctx_create_internal(geo, out, false); }
+
 extern "C" int sww_ctx_destroy(sww_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
+  if (c->rowc) sww_ctx_destroy(c->rowc);
+  c->rowc = nullptr;
   sww_fft_destroy(c);
   sww_rng_destroy(c);
   cudaFree(c->d_tables);
@@ -137,6 +157,7 @@ extern "C" int sww_ctx_set_stream(sww_ctx* c, sww_stream s) {
   SWW_REQUIRE(c, "null context");
   c->stream = (cudaStream_t)s;
   if (c->fft_work || c->fft_work_bytes == 0) SWW_TRY(sww_fft_bind_work(c));
+  if (c->rowc) SWW_TRY(sww_ctx_set_stream(c->rowc, s));
   return 0;
 }
 
@@ -151,16 +172,28 @@ extern "C" int sww_set_fft_backend(sww_ctx* c, int backend) {
   SWW_REQUIRE(c, "null context");
   SWW_REQUIRE(backend == 0 || backend == 1, "unknown FFT backend %d", backend);
   SWW_REQUIRE(!(c->tight_ws && c->ar.base && backend != c->fft_backend), "SWW_TIGHT_WS=1: the FFT backend is fixed once the workspace is bound");
-  if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes (nx,ny in [64,1024], nz in [128,2048])");
+  if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes (nx,ny in [64,1024], nz in [128,1024])");
   c->fft_backend = backend;
   return 0;
 }
 
-static size_t persist_layout(sww_ctx* c) {
+extern "C" int sww_row_mesh(sww_ctx* c, int32_t grid[3]) {
+  SWW_REQUIRE(c && grid, "null argument");
+  const bool on = c->rowc && c->fft_backend == 1;
+  grid[0] = on ? c->rowc->g.nx : 0;
+  grid[1] = on ? c->rowc->g.ny : 0;
+  grid[2] = on ? c->rowc->g.nz : 0;
+  return 0;
+}
+
+static size_t persist_own(sww_ctx* c) {
   size_t nW = ((size_t)c->g.N * sizeof(double) + 255) & ~size_t(255);
   size_t fw = (c->fft_work_bytes + 255) & ~size_t(255);
   return nW + fw;
 }
+
+// [nW map][FFT work area] of this context, then the same of the coarse row mesh
+static size_t persist_layout(sww_ctx* c) { return persist_own(c) + (c->rowc ? persist_own(c->rowc) : 0); }
 
 size_t sww_pipeline_bytes(sww_ctx* c, int what);  // pipelines.cu
 
@@ -183,6 +216,17 @@ extern "C" int sww_bind_workspace(sww_ctx* c, sww_devptr ws, uint64_t bytes) {
   c->fft_work_cap = c->fft_work_bytes;
   c->fields_dirty = true;
   SWW_TRY(sww_fft_bind_work(c));
+  if (c->rowc) {
+    sww_ctx* r = c->rowc;
+    char* rb = (char*)ws + persist_own(c);
+    r->ar.base = rb;
+    r->ar.cap = persist_own(r);
+    r->persist_bytes = r->ar.cap;
+    r->d_nW = (double*)rb;
+    r->fft_work = rb + (((size_t)r->g.N * sizeof(double) + 255) & ~size_t(255));
+    r->fft_work_cap = r->fft_work_bytes;
+    r->row_ready = false;
+  }
   return 0;
 }
 
@@ -197,6 +241,7 @@ extern "C" int sww_set_fields(sww_ctx* c, sww_devptr nbar, sww_devptr nbar_weigh
   c->P_fkp = P_fkp;
   SWW_TRY(k_prep_static(c));
   c->fields_dirty = false;
+  if (c->rowc) SWW_TRY(sww_rowmesh_prepare(c));
   return 0;
 }
 
@@ -220,7 +265,7 @@ extern "C" int sww_bk_set_triangles(sww_ctx* c, const int32_t* tris, int32_t n_t
 // ------------------------------------------------------------------------------------------
 // profiling
 // ------------------------------------------------------------------------------------------
-ProfScope::ProfScope(sww_ctx* c_, const char* name) : c(c_), slot(-1) {
+ProfScope::ProfScope(sww_ctx* c_, const char* name) : c(c_->parent ? c_->parent : c_), st(c_->stream), slot(-1) {
   if (!c->prof_on) return;
   int cat = -1;
   for (size_t i = 0; i < c->prof_names.size(); ++i)
@@ -236,11 +281,11 @@ ProfScope::ProfScope(sww_ctx* c_, const char* name) : c(c_), slot(-1) {
   c->prof_cat.push_back(cat);
   c->prof_ev.push_back(a);
   c->prof_ev.push_back(b);
-  cudaEventRecord(a, c->stream);
+  cudaEventRecord(a, st);
 }
 
 ProfScope::~ProfScope() {
-  if (slot >= 0) cudaEventRecord(c->prof_ev[2 * slot + 1], c->stream);
+  if (slot >= 0) cudaEventRecord(c->prof_ev[2 * slot + 1], st);
 }
 
 static void prof_clear(sww_ctx* c) {

@@ -41,6 +41,7 @@ void sww_fft_destroy(sww_ctx* c) {
 }
 
 int sww_fft_bind_work(sww_ctx* c) {
+  if (!c->plan_d2z) return 0;   // row-mesh child: hand-written passes only
   SWW_CUFFT(cufftSetWorkArea(c->plan_d2z, c->fft_work));
   SWW_CUFFT(cufftSetWorkArea(c->plan_z2d, c->fft_work));
   SWW_CUFFT(cufftSetStream(c->plan_d2z, c->stream));

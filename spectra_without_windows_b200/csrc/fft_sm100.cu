@@ -30,7 +30,6 @@
 #include "sww_internal.cuh"
 #include "ylm_gen.cuh"
 
-#define SMS 148
 
 static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
@@ -334,6 +333,15 @@ __device__ __forceinline__ double warp_sum_f(double v) {
   return v;
 }
 
+// cell of mode (ix, iy, iz) of this grid in a spectrum laid out for another grid [dnx][dny][dnzh] of the same box (the
+// coarse row mesh): negative frequencies keep their distance from the end of the axis.  dnx == 0: this grid.
+__device__ __forceinline__ long long remap_cell(const Geo& g, const F3Args& A, int ix, int iy, int iz) {
+  if (A.dnx == 0) return ((long long)ix * g.ny + iy) * g.nzh + iz;
+  const int jx = 2 * ix < g.nx ? ix : ix - g.nx + A.dnx;
+  const int jy = 2 * iy < g.ny ? iy : iy - g.ny + A.dny;
+  return ((long long)jx * A.dny + jy) * A.dnzh + iz;
+}
+
 template <int N, int AX, int MODE>
 __global__ void __launch_bounds__(N / 2, (N >= 512 ? (N >= 1024 ? 1 : 2) : 3))
 pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ P,
@@ -397,7 +405,7 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
           const int ia = bi + r * (N / RL);
           const bool inb = bA.has(ia) && iz < Kz;
           const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
-          const long long cell = ((long long)ix * g.ny + iy) * g.nzh + iz;
+          const long long cell = inb ? remap_cell(g, A, ix, iy, iz) : 0;
           const double2 t = u[s][r];
           if (MODE == 0) {
             if (inb) A.dst[cell] = t;
@@ -447,7 +455,7 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
       const int par = lane & 1, sub = lane >> 1;
       for (int q0 = warp; q0 < nitems; q0 += GRP * NW) { // uniform per warp (collectives below)
         int bq[GRP], jq[GRP], ccq[GRP];
-        long long cellp[GRP], cellm[GRP];
+        long long cellp[GRP], gcp[GRP], gcm[GRP];
         bool mir[GRP];
 #pragma unroll
         for (int j = 0; j < GRP; ++j) {
@@ -459,7 +467,11 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
           ccq[j] = cc;
           mir[j] = inb && ja > 0 && (!full || ja < N / 2);
           cellp[j] = row_of<AX>(jq[j], io, g.ny) * g.nzh + iz;
-          cellm[j] = row_of<AX>(mir[j] ? N - jq[j] : 0, io, g.ny) * g.nzh + iz;
+          {
+            const int jm = mir[j] ? N - jq[j] : 0;
+            gcp[j] = AX == 0 ? remap_cell(g, A, jq[j], io, iz) : remap_cell(g, A, io, jq[j], iz);
+            gcm[j] = AX == 0 ? remap_cell(g, A, jm, io, iz) : remap_cell(g, A, io, jm, iz);
+          }
           bq[j] = inb ? (int)g.binmap[cellp[j]] : SWW_NO_BIN;
         }
         double2 Gp[GRP][3], Gm[GRP][3];
@@ -468,8 +480,8 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
 #pragma unroll
           for (int q = 0; q < 3; ++q)
             if (q < A.n_g && bq[j] != SWW_NO_BIN) {
-              Gp[j][q] = A.G[q][cellp[j]];
-              if (mir[j]) Gm[j][q] = A.G[q][cellm[j]];
+              Gp[j][q] = A.G[q][gcp[j]];
+              if (mir[j]) Gm[j][q] = A.G[q][gcm[j]];
             }
 #pragma unroll
         for (int j = 0; j < GRP; ++j) {
@@ -1789,14 +1801,20 @@ static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
   }
 }
 
+// A/B switches (tests, profiling) are looked up per launch so that a test can flip them; only the value "1" enables one
+static inline bool env_on(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1' && e[1] == 0;
+}
+
 static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   SWW_PROF(c, inv && fwd ? "fft.Z c2r*w*r2c fused" : (inv ? "fft.Z c2r" : "fft.Z r2c"));
   A.ymaps = c->ylm_maps;
   A.N = c->g.N;
   const int H = c->g.nz / 2;
   const bool ylm = A.lm >= 0;
-  const bool no_z16 = getenv("SWW_NO_Z16") != nullptr;   // A/B switch (tests, profiling)
-  if (inv && fwd && !ylm && H == Z32_H && A.wmap && A.Kz_out <= 256 && A.Kz_in <= Z32_H + 1 && getenv("SWW_Z32") != nullptr) {
+  const bool no_z16 = env_on("SWW_NO_Z16");
+  if (inv && fwd && !ylm && H == Z32_H && A.wmap && A.Kz_out <= 256 && A.Kz_in <= Z32_H + 1 && env_on("SWW_Z32")) {
     // experimental (not yet validated on a GPU): opt-in only
     SWW_TRY(launch_z32(c, s, A));
     c->n_own++;

@@ -351,7 +351,7 @@ static int gram_run(sww_ctx* c, const double* A, const double* B, int m, int n, 
   int mtiles = (m + TM - 1) / TM, ntiles = (n + TN - 1) / TN;
   int Mpad = mtiles * TM, Npad = ntiles * TN;
   long long total_chunks = (K + KCG - 1) / KCG;
-  int ksplit = (148 * 2 * GRAM_CTAS + mtiles * ntiles - 1) / (mtiles * ntiles);   // two waves of resident CTAs
+  int ksplit = (SMS * 2 * GRAM_CTAS + mtiles * ntiles - 1) / (mtiles * ntiles);   // two waves of resident CTAs
   if (ksplit > total_chunks) ksplit = (int)total_chunks;
   if (ksplit < 1) ksplit = 1;
   long long cps = (total_chunks + ksplit - 1) / ksplit;
@@ -397,7 +397,7 @@ static int gram3_launch(sww_ctx* c, const double* X, const double* Y, const doub
   int mtiles = (m + TM - 1) / TM, ntiles = (nz + TN3 - 1) / TN3;
   int Mpad = mtiles * TM, Npad = ntiles * TN3;
   long long total_chunks = (K + KC - 1) / KC;
-  int ksplit = (148 * 2 * GRAM3_CTAS + mtiles * ntiles - 1) / (mtiles * ntiles);
+  int ksplit = (SMS * 2 * GRAM3_CTAS + mtiles * ntiles - 1) / (mtiles * ntiles);
   if (ksplit > total_chunks) ksplit = (int)total_chunks;
   if (ksplit < 1) ksplit = 1;
   long long cps = (total_chunks + ksplit - 1) / ksplit;

@@ -4,7 +4,6 @@
 #include "sww_internal.cuh"
 #include "ylm_gen.cuh"
 
-#define SMS 148
 
 // ------------------------------------------------------------------------------------------
 // helpers

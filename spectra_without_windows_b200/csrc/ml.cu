@@ -13,7 +13,6 @@
 #include "sww_internal.cuh"
 #include "ylm_gen.cuh"
 
-#define SMS 148
 typedef std::complex<double> cplx;
 
 static inline double lcoef(int l_i) { return 4.0 * M_PI / (4.0 * l_i + 1.0); }
@@ -437,7 +436,7 @@ extern "C" int sww_ml_apply_cinv(sww_ctx* c, sww_devptr pix, int max_it, double 
 }
 
 int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
-                             double2* spec, double2* const* out);   // pipelines.cu
+                             double2* spec, double2* const* out, const sww_ctx* out_mesh = nullptr);   // pipelines.cu
 int sww_mas_filter_internal(sww_ctx* c, const double* x, int power, double2* spec, double* out);
 
 // shell row: row[q*n_k + b] = scale * sum_{k in b} w Re[conj(FT[t]) G_q]

@@ -17,7 +17,7 @@ static inline double lcoef(int l_i) { return 4.0 * M_PI / (4.0 * l_i + 1.0); }
 
 // sum_m Y_lm(k^) FT[f Y_lm(r^)] for every multipole; tmp: real scratch [N]; spec: complex scratch [Nc]
 int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool with_coef, bool pruned, double* tmp,
-                             double2* spec, double2* const* out) {
+                             double2* spec, double2* const* out, const sww_ctx* out_mesh = nullptr) {
   int lm = 0;
   if (c->fft_backend == 1 && pruned) {
     // fused: Y_lm(r^) on the load of the z pass, Y_lm(k^) accumulation in the x-pass epilogue
@@ -30,6 +30,11 @@ int sww_ylm_project_internal(sww_ctx* c, const double* f, int mas_power, bool wi
         A.first = (m == 0);
         A.mas_power = mas_power;
         A.coef = (m == nm - 1) ? (with_coef ? lcoef(l_i) : 1.0) : 0.0;
+        if (out_mesh) {   // the box modes go straight into spectra laid out for the coarse row mesh
+          A.dnx = out_mesh->g.nx;
+          A.dny = out_mesh->g.ny;
+          A.dnzh = out_mesh->g.nzh;
+        }
         SWW_TRY(sww_sm100_forward_box(c, f, nullptr, lm, 1, A));
         c->n_fft++;
       }
@@ -57,11 +62,18 @@ struct PkFisherBufs {
   long long S = 0;
 };
 
+int sww_rowmesh_prepare(sww_ctx* c);   // rowmesh.cu
+
+// the context the Fisher rows run on: the coarse row mesh when there is one (rowmesh.cu), else the context itself
+static inline sww_ctx* row_ctx(sww_ctx* c) { return (c->fft_backend == 1 && c->rowc) ? c->rowc : c; }
+
 static void pk_fisher_layout(sww_ctx* c, Arena& ar, PkFisherBufs& b) {
   size_t N = c->g.N, Nc = c->g.Nc;
+  sww_ctx* rc = row_ctx(c);
   ar.reset(c->persist_bytes);
-  for (int l = 0; l < c->n_l; ++l) b.FC[l] = ar.alloc<double2>(Nc);
-  for (int l = 0; l < c->n_l; ++l) b.G[l] = ar.alloc<double2>(Nc);
+  // F^C_l and G_l are only ever read inside the k_max box: with a row mesh they are stored in its (smaller) layout
+  for (int l = 0; l < c->n_l; ++l) b.FC[l] = ar.alloc<double2>((size_t)rc->g.Nc);
+  for (int l = 0; l < c->n_l; ++l) b.G[l] = ar.alloc<double2>((size_t)rc->g.Nc);
   // the fused sm_100a chains never materialise the shell-filtered spectrum or the real-space map
   const bool fused_only = c->fft_backend == 1 && c->tight_ws;
   b.X = fused_only ? nullptr : ar.alloc<double2>(Nc);
@@ -70,8 +82,9 @@ static void pk_fisher_layout(sww_ctx* c, Arena& ar, PkFisherBufs& b) {
   b.nAa = ar.alloc<double>(N);
   b.WS = ar.alloc<double>(N);
   b.row = ar.alloc<double>((size_t)c->n_l * c->g.n_k);
-  if (c->fft_backend == 1 && !getenv("SWW_NO_SHELL_STORE")) {
-    const long long S = sww_sm100_shell_cells(c);
+  const char* no_store = getenv("SWW_NO_SHELL_STORE");
+  if (c->fft_backend == 1 && !(no_store && no_store[0] == '1')) {
+    const long long S = sww_sm100_shell_cells(rc);
     if (S > 0 && c->shell_rows < 0) {
       // rows kept in shell order between two segmented-product launches: all n_b of them if they fit the budget
       size_t free_b = 0, total_b = 0;
@@ -87,7 +100,7 @@ static void pk_fisher_layout(sww_ctx* c, Arena& ar, PkFisherBufs& b) {
       b.S = S;
       b.Us = ar.alloc<double2>((size_t)c->shell_rows * S);
       b.Gs = ar.alloc<double2>((size_t)c->n_l * S);
-      b.sp = ar.alloc<double>((size_t)sww_sm100_shell_chunks(c) * c->shell_rows * 3);
+      b.sp = ar.alloc<double>((size_t)sww_sm100_shell_chunks(rc) * c->shell_rows * 3);
     }
   }
 }
@@ -165,9 +178,13 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
   CHECK_READY(c);
   CHECK_FIELDS(c);
   SWW_REQUIRE(a_ && fish_out && qbar_out, "null device pointer");
+  if (c->fft_backend == 1 && c->rowc && !c->rowc->row_ready) SWW_TRY(sww_rowmesh_prepare(c));
   PkFisherBufs b;
   pk_fisher_layout(c, c->ar, b);
   CHECK_ARENA(c);
+  sww_ctx* rc = row_ctx(c);
+  const sww_ctx* om = rc != c ? rc : nullptr;
+  if (om) SWW_REQUIRE(rc->row_ready, "row mesh: the filtered weight map could not be built (workspace too small)");
   const double* a = (const double*)a_;
   double* F = (double*)fish_out;
   double* qbar = (double*)qbar_out;
@@ -184,8 +201,8 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
   } else {
     SWW_TRY(k_prep_pk(c, a, b.nCa, b.nAa, b.WS));
   }
-  SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC));
-  SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G));
+  SWW_TRY(sww_ylm_project_internal(c, b.nCa, 0, true, true, b.tmp, b.X, b.FC, om));
+  SWW_TRY(sww_ylm_project_internal(c, b.nAa, 0, true, true, b.tmp, b.X, b.G, om));
   // q-bar: one transform of W N A^-1 a, then one binning pass against F^C_l
   if (c->fft_backend == 1) {
     F3Args A = {};
@@ -193,33 +210,44 @@ extern "C" int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a_, sww_devptr f
     A.n_g = n_l;
     A.scale = 0.5 / N;
     A.out_row = qbar;
+    if (om) {
+      A.dnx = om->g.nx;
+      A.dny = om->g.ny;
+      A.dnzh = om->g.nzh;
+    }
     SWW_TRY(sww_sm100_forward_box(c, b.WS, nullptr, -1, 2, A));
     c->n_fft++;
     // Fisher rows: I1 -> I2 -> Z(c2r * nW * r2c) -> F2 -> F3(bin); nothing but the row leaves the chip
     // the n_l rows of one k bin share the shell box and the weight map: one batched chain per bin
+    // the rows run on rc (the coarse row mesh, or c itself): IFT normalised by the full mesh, and
+    // FT_M[w~ u] = (N_M / N) FT[nW u] inside the box, so the bin sums carry N / N_M
+    const double row_scale = 0.5 / ((double)rc->g.N * c->v_cell);
+    const unsigned long long own0 = rc->n_own;
+    int rr = 0;
     if (b.Us) {
       // rows go to HBM in shell order; every block of shells ends with one segmented-product launch
-      SWW_TRY(sww_sm100_shell_sort_g(c, (const double2* const*)b.G, n_l, b.Gs));
+      rr = sww_sm100_shell_sort_g(rc, (const double2* const*)b.G, n_l, b.Gs);
       const int spb = c->shell_rows / n_l;
-      for (int ka0 = 0; ka0 < n_k; ka0 += spb) {
+      for (int ka0 = 0; ka0 < n_k && rr == 0; ka0 += spb) {
         const int nsh = std::min(spb, n_k - ka0);
-        for (int k = 0; k < nsh; ++k) {
-          SWW_TRY(sww_sm100_pk_rows_store(c, n_l, (const double2* const*)b.FC, ka0 + k, c->d_nW, 1.0 / N,
-                                          b.Us + (size_t)k * n_l * b.S));
+        for (int k = 0; k < nsh && rr == 0; ++k) {
+          rr = sww_sm100_pk_rows_store(rc, n_l, (const double2* const*)b.FC, ka0 + k, rc->d_nW, 1.0 / N,
+                                       b.Us + (size_t)k * n_l * b.S);
           c->n_fft += 2 * n_l;
         }
-        SWW_TRY(sww_sm100_shell_dot(c, b.Us, nsh * n_l, b.Gs, n_l, 0.5 / (N * c->v_cell), b.sp, F, n_l, ka0));
+        if (rr == 0) rr = sww_sm100_shell_dot(rc, b.Us, nsh * n_l, b.Gs, n_l, row_scale, b.sp, F, n_l, ka0);
       }
-      SWW_TRY(k_symmetrise(c, F, n_b));
-      return 0;
+    } else {
+      for (int ka = 0; ka < n_k && rr == 0; ++ka) {
+        double* rows[SWW_MAX_L];
+        for (int l_i = 0; l_i < n_l; ++l_i) rows[l_i] = F + (size_t)(l_i * n_k + ka) * n_b;
+        rr = sww_sm100_pk_rows(rc, n_l, (const double2* const*)b.FC, ka, rc->d_nW, 1.0 / N, (const double2* const*)b.G, n_l,
+                               row_scale, rows);
+        c->n_fft += 2 * n_l;
+      }
     }
-    for (int ka = 0; ka < n_k; ++ka) {
-      double* rows[SWW_MAX_L];
-      for (int l_i = 0; l_i < n_l; ++l_i) rows[l_i] = F + (size_t)(l_i * n_k + ka) * n_b;
-      SWW_TRY(sww_sm100_pk_rows(c, n_l, (const double2* const*)b.FC, ka, c->d_nW, 1.0 / N, (const double2* const*)b.G, n_l,
-                                0.5 / (N * c->v_cell), rows));
-      c->n_fft += 2 * n_l;
-    }
+    if (om) c->n_own += rc->n_own - own0;
+    SWW_TRY(rr);
     SWW_TRY(k_symmetrise(c, F, n_b));
     return 0;
   }

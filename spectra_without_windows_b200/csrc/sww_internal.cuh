@@ -128,6 +128,13 @@ struct sww_ctx {
   size_t gram_partial_bytes = 0;
   double* d_q1_scratch = nullptr;
   size_t q1_scratch_elems = 0;
+  // coarse "row mesh" (fft_sm100.cu, "row mesh"): a child context on a smaller power-of-two grid with the same box and
+  // bins, on which the band-limited Fisher rows u_alpha -> FT[nW u_alpha] are evaluated exactly (no aliasing into the
+  // binned modes) against a low-pass-filtered copy of the weight map
+  sww_ctx* rowc = nullptr;
+  sww_ctx* parent = nullptr;   // child: events of the library's launches are recorded in the parent's profile
+  bool is_child = false;
+  bool row_ready = false;     // child: the filtered weight map is current
   // profiling
   bool prof_on = false;
   std::vector<std::string> prof_names;
@@ -138,13 +145,29 @@ struct sww_ctx {
 // ---- profiling (ctx.cu): events around the library's own launches
 struct ProfScope {
   sww_ctx* c;
+  cudaStream_t st;
   int slot;
   ProfScope(sww_ctx* c, const char* name);
   ~ProfScope();
 };
 #define SWW_PROF(c, name) ProfScope prof_scope__(c, name)
 
-static inline int sww_grid_for(long long n, int block, int max_blocks = 148 * 16) {
+// SM count of the current device (148 on B200), queried once: grids are sized in multiples of it
+static inline int sww_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      sms = v;
+    else
+      sms = 148;
+  }
+  return sms;
+}
+#define SMS sww_sm_count()
+
+static inline int sww_grid_for(long long n, int block, int max_blocks = 0) {
+  if (max_blocks <= 0) max_blocks = SMS * 16;
   long long b = (n + block - 1) / block;
   if (b > max_blocks) b = max_blocks;
   if (b < 1) b = 1;
@@ -182,6 +205,8 @@ struct F3Args {
   // MODE 3: store the in-shell modes in shell order (perm[box cell] = position or -1)
   const int* perm;
   double2* sorted_dst;
+  // MODE 0/1 dst and MODE 2 G maps may live on another (coarser) grid with the same box: [dnx][dny][dnzh]  (0: this grid)
+  int dnx, dny, dnzh;
 };
 // gather description for the first inverse pass: sum of up to three compact box spectra, each kept only
 // inside its shell, times coef * Y_lm(k^)  (n_terms == 0: plain spectrum + optional shell filter)

@@ -192,6 +192,12 @@ class Context:
         _lib.check(self.lib.sww_launch_counts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def row_mesh_shape(self):
+        """Grid of the coarse row mesh the Fisher rows run on (csrc/rowmesh.cu), or None on the full mesh."""
+        g = (_lib.i32 * 3)()
+        _lib.check(self.lib.sww_row_mesh(self._h, g))
+        return tuple(int(x) for x in g) if g[0] > 0 else None
+
     def profile(self, enable=True):
         """Start (or stop) CUDA-event profiling of the library's own launches."""
         _lib.check(self.lib.sww_profile_enable(self._h, int(bool(enable))))

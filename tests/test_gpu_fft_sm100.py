@@ -186,3 +186,39 @@ def test_fused_z_pass_nz1024_experimental_kernel(eng):
     F0, q0 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
     assert relerr(F1, F0) < 1e-11 and relerr(q1, q0) < 1e-11
     ctx.close()
+
+
+def test_row_mesh_matches_full_mesh(eng):
+    """Coarse row mesh (csrc/rowmesh.cu): on a 128 x 128 x 256 mesh whose k_max box is b = (14, 14, 28) the Fisher rows run
+    on a 64 x 64 x 128 child grid against the band-limited weight map.  F and q-bar must agree with the full-mesh rows
+    (SWW_ROW_MESH=0) and with the cuFFT backend to round-off -- the identity is exact, not an approximation."""
+    import os
+    from spectra_without_windows_b200 import synthetic as syn
+    grid, box, bc = (128, 128, 256), (1000.0, 1000.0, 2000.0), (1400.0, 60.0, -45.0)
+    mesh = eng.Mesh(box, grid, bc, 0.0, 0.09, 0.015, 4)
+    nbar_r = syn.survey_nbar(box, grid, bc, n0=6e-3)
+    a = None
+    res = {}
+    for tag, env in (("row", None), ("full", "0")):
+        if env is not None:
+            os.environ["SWW_ROW_MESH"] = env
+        try:
+            ctx = eng.Context(mesh, 0, ("ops", "pk_fisher"))
+        finally:
+            os.environ.pop("SWW_ROW_MESH", None)
+        assert ctx.fft_backend == 1
+        nbar_A = ctx.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)
+        if a is None:
+            a = np.random.default_rng(11).normal(size=grid) * np.sqrt(nbar_A)
+        F, q = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+        F2, _ = ctx.pk_fisher(a)
+        assert np.array_equal(F, F2.cpu().numpy())          # deterministic
+        res[tag] = (F, q, ctx.row_mesh_shape())
+        if tag == "full":
+            ctx.set_fft_backend(0)
+            res["cufft"] = tuple(t.cpu().numpy() for t in ctx.pk_fisher(a))
+        ctx.close()
+    assert res["row"][2] == (64, 64, 128) and res["full"][2] is None
+    assert np.max(np.abs(res["full"][0])) > 0
+    assert relerr(res["row"][0], res["full"][0]) < 1e-11 and relerr(res["row"][1], res["full"][1]) < 1e-11
+    assert relerr(res["row"][0], res["cufft"][0]) < 1e-11 and relerr(res["row"][1], res["cufft"][1]) < 1e-11
