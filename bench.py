@@ -115,32 +115,58 @@ def n_fft_min(M, n_b):
     return 2 * M + 1 + 2 * n_b
 
 
+def oracle_axes(wl):
+    """Cell-centre coordinates per axis with the oracle's restatement of load_coord_grids (src/opt_utilities.py:428-430);
+    the reference arm must not lean on the product package."""
+    from oracle import sww_oracle as orc
+    box, grid = np.asarray(wl["box"], float), np.asarray(wl["grid"], int)
+    off = np.asarray(wl["box_center"], float) + 0.5 * box / grid
+    return [(orc._signed_index(grid[i]) * (box[i] / grid[i])).astype("f8") + off[i] for i in range(3)]
+
+
+def reference_arm(wl, workload):
+    from oracle.ref_arm import PkFisherRefArm
+    nb_fn = uniform_nbar_r if workload == "C1F" else survey_nbar_r
+    nbar_r = nb_fn(oracle_axes(wl), np)
+    return PkFisherRefArm(wl["box"], wl["grid"], wl["box_center"], nbar_r, ALPHA, SHOT, *wl["bins"])
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the reference algorithm on the host cores, bounded sample per step."""
+    """CPU arm: the reference's own low_mem algorithm (pk/compute_pk_randoms.py:200-281) on the host cores, shipped
+    precision, all threads; every step is a bounded sample of one realisation at the full mesh size (oracle/ref_arm.py).
+    value = step_fraction / step time, where step_fraction is the share of one realisation's work a step covers."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.cpu_baseline import PkFisherSample
-    from spectra_without_windows_b200 import engine
     wl = WORKLOADS[args.workload]
-    mesh = engine.Mesh(wl["box"], wl["grid"], wl["box_center"], *wl["bins"])
-    nb_fn = uniform_nbar_r if args.workload == "C1F" else survey_nbar_r
-    nbar = nb_fn(mesh.rax, np) * ALPHA
-    smp = PkFisherSample(wl["box"], wl["grid"], wl["box_center"], nbar, *wl["bins"])
+    if wl.get("bk") or wl.get("data"):
+        raise Exception("--impl reference times the pk Fisher workloads (C2, C5, C1F, S256)")
+    arm = reference_arm(wl, args.workload)
+    arm.prologue()
     for _ in range(args.warmup):
-        smp.sample()
-    ts = []
+        arm.step()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        T, parts = smp.sample()
-        ts.append(T)
-    T = float(np.mean(ts))
+        arm.step()
+    wall = time.perf_counter() - t0
+    T = arm.T_real()          # means over all sampled rows (a kind of row not sampled yet is run once, untimed)
+    parts = arm.parts()
+    arm.close()
+    ms_step = wall / args.steps * 1e3
     val = 1.0 / T
+    grid = np.asarray(wl["grid"], int)
+    n_k = int((wl["bins"][1] - wl["bins"][0]) / wl["bins"][2])
+    n_b = n_k * (wl["bins"][3] // 2 + 1)
+    cfg = {"workload": "%s: compute_pk_randoms Fisher realisation, mesh %s, box %s, k in [%.3f,%.3f] dk=%.4f lmax=%d, n_b=%d, FKP weights"
+                       % (args.workload, "x".join(str(int(g)) for g in grid), "x".join("%g" % b for b in wl["box"]), wl["bins"][0],
+                          wl["bins"][1], wl["bins"][2], wl["bins"][3], n_b), "n_b": n_b}
     line = {"impl": "reference", "metric": "pk Fisher MC realisations/s", "value": val, "unit": "realisations/s",
-            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": T * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, mesh),
-            "cpu_baseline": {"value": val, "unit": "realisations/s", "cores": smp.workers, "kind": "port",
-                             "sample": smp.describe(), "parts_s": parts},
+            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "step_fraction_of_realisation": (wall / args.steps) / T, "seconds_per_realisation": T,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64/f64 (the reference's shipped precision)",
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": "realisations/s", "cores": arm.threads, "kind": "port",
+                             "sample": arm.describe(), "parts_s": {k: v for k, v in parts.items() if k != "check"}},
             "e2e": {"value": val, "unit": "realisations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -623,13 +649,14 @@ def main():
         if prof is not None and zkey in prof:
             # dominant kernel: the fused z pass (c2r * nW * r2c in shared memory).  Algorithmic bytes per launch =
             # the weight map (8 N) + the complex input rows of the shell's box + the complex output rows of the k_max box.
-            nx, ny, nz = (int(v) for v in mesh.grid)
+            rmesh = ctx.row_mesh_shape()          # the rows run on the coarse row mesh when there is one (csrc/rowmesh.cu)
+            nx, ny, nz = rmesh if rmesh else (int(v) for v in mesh.grid)
             kFz = 2.0 * np.pi / mesh.box[2]
             kz_of = lambda kmax: min(int(np.floor(np.nextafter(kmax / kFz, 0))) + 1, nz // 2 + 1)
             kz_out = kz_of(mesh.k_hi[-1])
             kz_in_mean = float(np.mean([kz_of(k) for k in mesh.k_hi]))
             rows_per_launch = max(1, round(n_b / prof[zkey]["launches"]))   # the n_l multipoles of one k bin share a launch
-            bytes_launch = 8.0 * mesh.N + rows_per_launch * 16.0 * nx * ny * (kz_in_mean + kz_out)
+            bytes_launch = 8.0 * nx * ny * nz + rows_per_launch * 16.0 * nx * ny * (kz_in_mean + kz_out)
             dur = prof[zkey]["ms"] / prof[zkey]["launches"] * 1e-3
             traffic = None
             try:
@@ -646,17 +673,19 @@ def main():
             roof["traffic"] = traffic
             roof["dominant_kernel"] = {
                 "name": "%s (fused z pass: c2r * nW * r2c of the %d Fisher rows of one k bin)"
-                        % ("pass_z16_fused_kernel<4,3,true>" if nz == 512 and kz_out <= 128 else "pass_zw_kernel<H,1,1,0>", rows_per_launch),
+                        % ("pass_z16p_fused_kernel<NBI,true,3>" if nz == 512 and kz_out <= 128 else "pass_zw_kernel<H,1,1,0>", rows_per_launch),
                 "launches_per_realisation": prof[zkey]["launches"], "avg_launch_ms": dur * 1e3,
                 "share_of_step": prof[zkey]["ms"] / (ms / args.steps),
                 "algorithmic_bytes_per_launch": bytes_launch, "achieved_gbs": bytes_launch / dur / 1e9,
                 "frac_of_hbm_peak": bytes_launch / dur / 1e9 / peak, "dram_traffic_bytes_per_launch_ncu": traffic,
-                "note": "FP64-pipe bound (ncu: 56 % of the pipe, 64 DFMA/clk/SM; two half-length complex FFTs per row), so its HBM fraction is below the step's; see profiles/r1d for the ncu capture",
+                "row_mesh": list(rmesh) if rmesh else None,
+                "note": "FP64-pipe bound (ncu: 56 % of the pipe, 64 DFMA/clk/SM; two half-length complex FFTs per row), so its HBM fraction is below the step's; see profiles/ for the ncu captures",
                 "timing": "CUDA events on the launching stream around every launch of one extra realisation after the timed region"}
         line = {"metric": "pk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args.workload, mesh), "realisations_in_flight": K,
+                "row_mesh": list(ctx.row_mesh_shape()) if ctx.row_mesh_shape() else None,
                 "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
                 "gpu_launches": int((own1 - own0) + (fft1 - fft0)) if ctx.fft_backend == 0 else int(own1 - own0),
                 "own_kernel_launches": int(own1 - own0), "library_fft_calls": int(fft1 - fft0) if ctx.fft_backend == 0 else 0,
@@ -665,12 +694,14 @@ def main():
             line["profile_one_realisation"] = prof
         if world == 1 and not args.no_cpu_baseline:
             try:
-                from oracle.cpu_baseline import PkFisherSample
-                nbar_h = nbar.cpu().numpy()
-                smp = PkFisherSample(wl["box"], wl["grid"], wl["box_center"], nbar_h, *wl["bins"])
-                T, parts = smp.sample()
-                line["cpu_baseline"] = {"value": 1.0 / T, "unit": "realisations/s", "cores": smp.workers, "kind": "port",
-                                        "sample": smp.describe(), "parts_s": parts}
+                arm = reference_arm(wl, args.workload)
+                arm.prologue()
+                dt = arm.step()[0] + arm.step()[0]
+                T, parts = arm.T_real(), arm.parts()
+                arm.close()
+                line["cpu_baseline"] = {"value": 1.0 / T, "unit": "realisations/s", "cores": arm.threads, "kind": "port",
+                                        "sample": arm.describe() + "; one loop-1 row + one loop-2 row step, %.1f s" % dt,
+                                        "parts_s": {k: v for k, v in parts.items() if k != "check"}}
             except Exception as ex:   # the baseline is a reported number, never a reason to lose the bench line
                 line["cpu_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(line))

@@ -18,10 +18,11 @@ One realisation of the reference costs (n_b = n_k (lmax/2+1) bins)
 and cannot be run in full at 512^3 (n_b^2 = 6e4 loads of 2 GB maps): a STEP of this arm is a bounded sample of exactly
 that code path on the full-size mesh --
 
-    one loop-1 row and one loop-2 row at multipole l = 2 (2l+1 = 5 forward transforms = the mean over l = 0,2,4 of the
-    rows of a realisation), with `n_dots` of the loop-2 row's np.load + product-sum terms against the saved loop-1 map
+    alternately one loop-1 row and one loop-2 row at multipole l = 2 (2l+1 = 5 forward transforms = the mean over
+    l = 0,2,4 of the rows of a realisation), the latter with `n_dots` of its np.load + product-sum terms against the saved
+    loop-1 map (the prologue is timed once, outside the steps)
 
--- and the time of one realisation follows from the reference's own loop counts, every term measured inside the step:
+-- and the time of one realisation follows from the reference's own loop counts and the means over the steps:
 
     T_real = t_prologue + n_b (t_row1 + t_row2) + n_b^2 t_dot
 
@@ -70,7 +71,8 @@ class PkFisherRefArm:
         nA[nA == 0] = float(nA[nA != 0].min()) * 0.01
         self.nbar_A = nA
         self.tmpdir = tempfile.mkdtemp(prefix="sww_refarm_", dir=tmpdir)
-        self._seed = 0
+        self._fn = None
+        self.l_i = 1 if self.n_l > 1 else 0
 
     # ---- reference operators, shipped precision -------------------------------------------------------------
     def ft(self, x):
@@ -106,53 +108,92 @@ class PkFisherRefArm:
         tmp2 = 4.0 * np.pi / (4.0 * i + 1.0) * filt * f
         return self.nbar * self.ift(tmp2) / self.v_cell
 
-    # ---- one bounded sample ------------------------------------------------------------------------------------
-    def step(self):
-        """Returns (seconds of the step, T_real extrapolated with the reference's loop counts, parts)."""
+    # ---- bounded samples -------------------------------------------------------------------------------------
+    def prologue(self):
+        """GRF, C^-1 a, A^-1 a, N A^-1 a (pk/compute_pk_randoms.py:139-140, 206-217): once per realisation; timed once."""
         t = self.t
-        self._seed += 1
         T0 = time.perf_counter()
-        # prologue (pk/compute_pk_randoms.py:139-140, 206-217)
-        np.random.seed(self._seed)
+        np.random.seed(1)
         a = t.from_numpy(np.random.normal(loc=0.0, scale=1.0, size=tuple(self.grid))) * t.sqrt(self.nbar_A)
-        Cinv = self.applyCinv_fkp(a).real
-        Ainv = a / self.nbar_A
-        NAinv = self.applyN(Ainv)
-        del a
-        T1 = time.perf_counter()
-        i = 1 if self.n_l > 1 else 0
-        ka = (self.n_k // 2 + self._seed) % self.n_k
-        # one row of loop 1 (:220-226)
-        m1 = self.applyC_alpha_single(Ainv, i, ka)
+        self.Cinv = self.applyCinv_fkp(a).real.contiguous()
+        self.Ainv = a / self.nbar_A
+        self.NAinv = self.applyN(self.Ainv)
+        self.t_prologue = time.perf_counter() - T0
+        self.times = {"row1": [], "row2": [], "dot": []}
+        self._n = 0
+
+    def _row1(self, ka):
+        """one row of loop 1 (:220-226): C_,alpha A^-1 a at l = 2, saved like the reference does"""
+        T0 = time.perf_counter()
+        m1 = self.applyC_alpha_single(self.Ainv, self.l_i, ka)
         fn = os.path.join(self.tmpdir, "C_a_Ai_%d.npy" % ka)
         np.save(fn, m1.numpy())
-        del m1
-        T2 = time.perf_counter()
-        # one row of loop 2 without its beta loop (:244-265)
-        tmp = self.applyC_alpha_single(Cinv, i, ka)
+        self.times["row1"].append(time.perf_counter() - T0)
+        return fn
+
+    def _row2(self, ka, fn):
+        """one row of loop 2 (:244-272): C^-1 C_,alpha C^-1 a, the q-bar dot, and n_dots of its n_b np.load + product-sums"""
+        t = self.t
+        T0 = time.perf_counter()
+        tmp = self.applyC_alpha_single(self.Cinv, self.l_i, ka)
         row = self.applyCinv_fkp(tmp)
         del tmp
-        qb = 0.5 * float(t.sum(row * NAinv).real)
-        T3 = time.perf_counter()
-        # n_dots terms of that row's beta loop (:268-272): np.load + product-sum
+        qb = 0.5 * float(t.sum(row * self.NAinv).real)
+        T1 = time.perf_counter()
         acc = 0.0
         for _ in range(self.n_dots):
             acc += 0.5 * float(t.sum(row * t.from_numpy(np.load(fn))).real)
-        T4 = time.perf_counter()
-        os.remove(fn)
-        parts = {"t_prologue": T1 - T0, "t_row1": T2 - T1, "t_row2": T3 - T2, "t_dot": (T4 - T3) / max(1, self.n_dots),
-                 "check": [qb, acc]}
-        T_real = parts["t_prologue"] + self.n_b * (parts["t_row1"] + parts["t_row2"]) + self.n_b ** 2 * parts["t_dot"]
-        return T4 - T0, T_real, parts
+        T2 = time.perf_counter()
+        self.times["row2"].append(T1 - T0)
+        self.times["dot"].append((T2 - T1) / max(1, self.n_dots))
+        return qb, acc
+
+    def step(self):
+        """One bounded sample: even steps run a loop-1 row, odd steps the loop-2 row of the same bin with n_dots of its
+        product-sums.  Returns (seconds of this step, T_real from the means so far -- None until both kinds of row have
+        been sampled --, parts)."""
+        if not hasattr(self, "times"):
+            self.prologue()
+        T0 = time.perf_counter()
+        ka = (self.n_k // 2 + self._n // 2) % self.n_k
+        if self._n % 2 == 0 or self._fn is None:
+            self._fn = self._row1(ka)
+        else:
+            self._row2(ka, self._fn)
+            os.remove(self._fn)
+            self._fn = None
+        self._n += 1
+        dt = time.perf_counter() - T0
+        both = self.times["row1"] and self.times["row2"]
+        return dt, (self.T_real() if both else None), self.parts()
+
+    def parts(self):
+        mean = lambda v: float(np.mean(v)) if v else float("nan")
+        return {"t_prologue": self.t_prologue, "t_row1": mean(self.times["row1"]), "t_row2": mean(self.times["row2"]),
+                "t_dot": mean(self.times["dot"]), "n_row1": len(self.times["row1"]), "n_row2": len(self.times["row2"])}
+
+    def T_real(self):
+        """seconds per realisation with the reference's loop counts; a missing kind of row is sampled first"""
+        if not self.times["row1"] or not self.times["row2"]:
+            ka = self.n_k // 2
+            fn = self._fn if self._fn else self._row1(ka)
+            if not self.times["row2"]:
+                self._row2(ka, fn)
+            if fn != self._fn:
+                os.remove(fn)
+        p = self.parts()
+        return p["t_prologue"] + self.n_b * (p["t_row1"] + p["t_row2"]) + self.n_b ** 2 * p["t_dot"]
 
     def describe(self):
         return ("reference low_mem branch (pk/compute_pk_randoms.py:200-281) in shipped precision (complex64) on torch-CPU "
-                "kernels with %d threads, full mesh %s: a step = prologue + one loop-1 row + one loop-2 row at l=2 (5 forward "
-                "transforms = the mean row) + %d np.load+product-sum terms; T_real = t_prologue + n_b (t_row1+t_row2) + "
-                "n_b^2 t_dot with n_b=%d, every term measured inside the step"
+                "kernels with %d threads, full mesh %s: steps alternate between one loop-1 row and one loop-2 row at l=2 (5 forward "
+                "transforms = the mean row), the latter with %d of its np.load+product-sum terms; T_real = t_prologue + n_b "
+                "(t_row1+t_row2) + n_b^2 t_dot with n_b=%d from the means over the steps (prologue timed once, outside the steps)"
                 % (self.threads, "x".join(str(int(g)) for g in self.grid), self.n_dots, self.n_b))
 
     def close(self):
+        if self._fn and os.path.exists(self._fn):
+            os.remove(self._fn)
         try:
             os.rmdir(self.tmpdir)
         except OSError:

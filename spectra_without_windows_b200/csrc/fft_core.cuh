@@ -97,8 +97,12 @@ FFT_HD void dft16(double2* u) {
 #pragma unroll
     for (int q = 1; q < 4; ++q) {
       const int n = j * q;
-      double2 w = double2{cs[n], DIR > 0 ? -sn[n] : sn[n]};
-      a[j][q] = c_mul(a[j][q], w);
+      if (n == 4) {   // w16^4 = -i (forward) / +i (inverse): a rotation, no arithmetic
+        a[j][q] = c_rot<DIR>(a[j][q]);
+      } else {
+        double2 w = double2{cs[n], DIR > 0 ? -sn[n] : sn[n]};
+        a[j][q] = c_mul(a[j][q], w);
+      }
     }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {

@@ -907,18 +907,26 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 #pragma unroll
           for (int s = 0; s < IPS; ++s) {
             const int vb = lane + 32 * s, rho = vb / BPS, bi = vb - rho * BPS;
+            // Y_lm(r^) along the row: degree-l Horner polynomial in z with row coefficients, times r^-l (ylm_gen.cuh)
+            double Ac[3], xy2 = 0.0;
+            bool odd = false;
+            const int deg = lmb >= 0 ? SWW_YLM_ZDEG(lmb) : 0;
+            if (lmb >= 0) {
+              const long long row = row0 + rho;
+              const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+              const double X = g.rax[0][ix], Y = g.rax[1][iy];
+              xy2 = X * X + Y * Y;
+              sww_ylm_zpack(lmb, X, Y, Ac, &odd);
+            }
 #pragma unroll
             for (int r = 0; r < SE; ++r) {
               double f0 = 1.0, f1 = 1.0;
               if (lmb >= 0) {
-                const long long row = row0 + rho;
-                const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny), m = bi + r * BPS;
-                double X = g.rax[0][ix], Y = g.rax[1][iy];
-                double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
-                const double xy2 = X * X + Y * Y;
-                const double i0 = inv_norm_eps(xy2 + Z0 * Z0), i1 = inv_norm_eps(xy2 + Z1 * Z1);
-                f0 = sww_ylm_dyn(lmb, X * i0, Y * i0, Z0 * i0);
-                f1 = sww_ylm_dyn(lmb, X * i1, Y * i1, Z1 * i1);
+                const int m = bi + r * BPS;
+                const double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
+                const double w0 = Z0 * Z0, w1 = Z1 * Z1;
+                f0 = sww_ylm_zpacked(deg, Ac, odd, Z0, w0, deg ? 1.0 / (xy2 + w0) : 1.0);
+                f1 = sww_ylm_zpacked(deg, Ac, odd, Z1, w1, deg ? 1.0 / (xy2 + w1) : 1.0);
               }
               acc[s][r].x += f0 * u[s][r].x;
               acc[s][r].y += f1 * u[s][r].y;
@@ -951,6 +959,18 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
         for (int r = 0; r < SE; ++r)
           wv[0][r] = *reinterpret_cast<const double2*>(A.wmap + (row0 + rho) * g.nz + 2 * (bi + r * BPS));
       }
+      // on-the-fly Y_lm(r^): row coefficients of the degree-l polynomial in z (ylm_gen.cuh), hoisted out of the cell loop
+      const bool ylm_fly = YLM && !(INV && !FWD && A.nb > 1) && !(A.lm >= 1 && A.ymaps);
+      double Ac[3], xy2 = 0.0;
+      bool odd = false;
+      const int deg = ylm_fly ? SWW_YLM_ZDEG(A.lm) : 0;
+      if (ylm_fly) {
+        const long long row = row0 + rho;
+        const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+        const double X = g.rax[0][ix], Y = g.rax[1][iy];
+        xy2 = X * X + Y * Y;
+        sww_ylm_zpack(A.lm, X, Y, Ac, &odd);
+      }
 #pragma unroll
       for (int r = 0; r < SE; ++r) {
         double f0 = A.scale, f1 = A.scale;
@@ -963,15 +983,12 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
                                                                2 * (bi + r * BPS));
           f0 *= yv.x;
           f1 *= yv.y;
-        } else if (YLM && !(INV && !FWD && A.nb > 1)) {
-          const long long row = row0 + rho;
-          const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny), m = bi + r * BPS;
-          double X = g.rax[0][ix], Y = g.rax[1][iy];
-          double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
-          const double xy2 = X * X + Y * Y;
-          const double i0 = inv_norm_eps(xy2 + Z0 * Z0), i1 = inv_norm_eps(xy2 + Z1 * Z1);
-          f0 *= sww_ylm_dyn(A.lm, X * i0, Y * i0, Z0 * i0);
-          f1 *= sww_ylm_dyn(A.lm, X * i1, Y * i1, Z1 * i1);
+        } else if (ylm_fly) {
+          const int m = bi + r * BPS;
+          const double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
+          const double w0 = Z0 * Z0, w1 = Z1 * Z1;
+          f0 *= sww_ylm_zpacked(deg, Ac, odd, Z0, w0, deg ? 1.0 / (xy2 + w0) : 1.0);
+          f1 *= sww_ylm_zpacked(deg, Ac, odd, Z1, w1, deg ? 1.0 / (xy2 + w1) : 1.0);
         }
         u[s][r].x *= f0;
         u[s][r].y *= f1;
@@ -1249,6 +1266,165 @@ pass_z16_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
           const double2 dv = make_double2(v1.x - v2.x, v1.y + v2.y);
           const double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);
           dst[k] = make_double2(ev.x + od.x, ev.y + od.y);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass_z16p_fused_kernel: the kernel above with table-driven, branch-free pre- and post-processing (round 2).
+// ncu on the kernel above (profiles/r1e) put 52 % of its stall samples in the Hermitian pre-processing and the r2c
+// post-processing -- 16 + 8 basic blocks of "3 shared loads -> a 10-deep chain of dependent FP64 operations", one after
+// the other -- for a fifth of its FP64 work.  Here:
+//   * Kz_in <= 128 = H/2 means that of Z[k] and Z[H-k] at most ONE is kept, so
+//         Y[k] = Z[k] (1 + i conj w_k)          (k < 128)       Y[k] = conj(Z[H-k]) (1 - i conj w_k)      (k > 128)
+//     is ONE complex product with a table value: preA[k] = (1 - s_k, c_k), preB[j] = (1 + s_j, c_j), w = c - i s.
+//     NBI = number of 16-blocks that can be non-zero at either end (template): the blocks in between are compile-time
+//     zeros, all loads of the phase are issued together, and the 2 NBI products are independent;
+//   * T[k] = V[k] postA[k] + conj(V[H-k]) postB[k] with postA = h (1 - s, -c), postB = h (1 + s, c), h = scale / 2:
+//     all shuffles first, then 8 independent 4-deep FMA chains (8 FP64 operations per output instead of 10), and the
+//     weights stay unscaled in registers (their load is only waited for after the first inverse transform).
+// ------------------------------------------------------------------------------------------
+template <int NBI, bool WREG, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+pass_z16p_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g, int in_len) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = Z16_H, ROW = Z16_ROW, WARPS = 4;
+  double2* preA = reinterpret_cast<double2*>(smem_raw);   // [128]
+  double2* preB = preA + 128;                            // [136] (index 128 is never kept: Kz_in <= 128)
+  double2* postA = preB + 136;                           // [128]
+  double2* postB = postA + 128;                          // [128]
+  double2* tab = postB + 128;                            // [16][16] inter-stage twiddles W_256^(b r) at [r * 16 + b]
+  double2* bufs = tab + 256;                             // [WARPS][2 * ROW] exchange buffers
+  double2* inbs = bufs + WARPS * 2 * ROW;                // [WARPS][2 * in_len] staged input rows
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rho = lane >> 4, b = lane & 15;
+  double2* buf = bufs + warp * 2 * ROW + rho * ROW;
+  double2* inw = inbs + warp * 2 * in_len;
+  const double2* inb = inw + rho * in_len;
+  const double half = 0.5 * A.scale;
+  for (int i = tid; i <= 128; i += WARPS * 32) {
+    const double2 w = twn_g[i];                          // (c, -s)
+    preB[i] = make_double2(1.0 - w.y, w.x);
+    if (i < 128) {
+      preA[i] = make_double2(1.0 + w.y, w.x);
+      postA[i] = make_double2(half * (1.0 + w.y), -half * w.x);
+      postB[i] = make_double2(half * (1.0 - w.y), half * w.x);
+    }
+  }
+  for (int i = tid; i < 256; i += WARPS * 32) tab[i] = twh_g[((i >> 4) * (i & 15)) & (H - 1)];
+  __syncthreads();
+  const long long ngroups = (long long)g.nx * g.ny / 2;
+  const long long gstep = (long long)gridDim.x * WARPS;
+  const int nfb = A.nb > 1 ? A.nb : 1;
+  const int Kz_in = A.Kz_in, Kz_out = A.Kz_out;
+  const int in_last = in_len - 1;
+  auto prefetch_rows = [&](const double2* __restrict__ Qbase, long long r0) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const double2* src = Qbase + (r0 + rr) * A.Kzp_in;
+      double2* row = inw + rr * in_len;
+      for (int k = lane; k < Kz_in; k += 32) {
+        unsigned sa = (unsigned)__cvta_generic_to_shared(row + k);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  long long grp = (long long)blockIdx.x * WARPS + warp;
+  if (grp < ngroups) prefetch_rows(A.Q, grp * 2);
+  for (; grp < ngroups; grp += gstep) {
+    const long long row = grp * 2 + rho;
+    const double* __restrict__ wrow = A.wmap + row * g.nz + 2 * b;
+    // WREG: the weights of the row pair stay in registers for all planes (168 registers, 12 warps / SM); otherwise they are
+    // re-read per plane (L2 hits after the first) right before the inverse transform that hides their latency
+    double2 wreg[16];
+    if (WREG) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) wreg[r] = *reinterpret_cast<const double2*>(wrow + 32 * r);
+    }
+    for (int fb = 0; fb < nfb; ++fb) {
+      double2 u[16];
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncwarp();
+      // ---- inverse: Hermitian pre-processing, one table product per kept element, all loads up front
+#pragma unroll
+      for (int r = NBI; r < 16 - NBI; ++r) u[r] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int q = 0; q < 2 * NBI; ++q) {
+        const int r = q < NBI ? q : 16 - 2 * NBI + q;
+        const int k = b + 16 * r;
+        const int idx = q < NBI ? k : H - k;            // the kept partner: Z[k] or Z[H - k]
+        double2 v = inb[idx < in_last ? idx : in_last];
+        if (idx >= Kz_in) v = make_double2(0.0, 0.0);
+        if (q == 0 && b == 0) v.y = 0.0;                // Z[0] is real
+        if (q < NBI) {                                  // Z[k] (1 + i conj w_k)
+          const double2 cw = preA[k];
+          u[r] = make_double2(v.x * cw.x - v.y * cw.y, v.x * cw.y + v.y * cw.x);
+        } else {                                        // conj(Z[H - k]) (1 - i conj w_k)
+          const double2 cw = preB[idx];
+          u[r] = make_double2(v.x * cw.x + v.y * cw.y, v.x * cw.y - v.y * cw.x);
+        }
+      }
+      __syncwarp();
+      {
+        // the staging buffer is free again: start the copy of the next plane of this warp
+        const bool wrap = fb + 1 >= nfb;
+        const long long ngrp = wrap ? grp + gstep : grp;
+        if (ngrp < ngroups) prefetch_rows(A.Q + (wrap ? 0LL : (long long)(fb + 1) * A.q_stride), ngrp * 2);
+      }
+      dft16<-1>(u);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+      if (!WREG) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) wreg[r] = *reinterpret_cast<const double2*>(wrow + 32 * r);
+      }
+      twiddle16_tab<-1>(u, tab, b);
+      dft16<-1>(u);
+      // ---- real-space step: x[2m], x[2m+1] at m = b + 16 r, times the weight map (scale / 2 sits in the post tables)
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        u[r].x *= wreg[r].x;
+        u[r].y *= wreg[r].y;
+      }
+      // ---- forward: stage 0 from the same registers, one exchange, stage 1
+      dft16<1>(u);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+      twiddle16_tab<1>(u, tab, b);
+      dft16<1>(u);
+      // ---- r2c post-processing: T[k] = V[k] postA[k] + conj(V[H-k]) postB[k]; V[H-k] sits in lane 16 - b, register 15 - r
+      double2* __restrict__ dst = A.R + (long long)fb * A.r_stride + row * A.Kzp_out;
+      const int src_lane = (rho << 4) | ((16 - b) & 15);
+#pragma unroll
+      for (int h4 = 0; h4 < 8; h4 += 4) {   // two batches of four outputs: shuffles first, then independent FMA chains
+        double2 v2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v2[q].x = __shfl_sync(0xffffffffu, u[15 - h4 - q].x, src_lane);
+          v2[q].y = __shfl_sync(0xffffffffu, u[15 - h4 - q].y, src_lane);
+        }
+        if (b == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v2[q] = u[(16 - h4 - q) & 15];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = b + 16 * (h4 + q);
+          const double2 v1 = u[h4 + q], pa = postA[k], pb = postB[k];
+          double2 t;
+          t.x = v1.x * pa.x - v1.y * pa.y + (v2[q].x * pb.x + v2[q].y * pb.y);
+          t.y = v1.x * pa.y + v1.y * pa.x + (v2[q].x * pb.y - v2[q].y * pb.x);
+          if (k < Kz_out) dst[k] = t;
         }
       }
     }
@@ -1787,9 +1963,39 @@ static int launch_z32(sww_ctx* c, Sm100State* s, ZArgs A) {
   return 0;
 }
 
+template <int NBI, bool WREG, int MINB>
+static int launch_z16p_v(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 4;
+  const int in_len = up8(A.Kz_in);
+  const size_t smem = (size_t)(128 + 136 + 128 + 128 + 256 + WARPS * 2 * Z16_ROW + WARPS * 2 * in_len) * sizeof(double2);
+  const long long ngroups = (long long)c->g.nx * c->g.ny / 2;
+  const long long ctas = (ngroups + WARPS - 1) / WARPS;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > MINB) per_sm = MINB;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm * grid_oversub());
+  SWW_TRY((set_smem(pass_z16p_fused_kernel<NBI, WREG, MINB>, smem)));
+  pass_z16p_fused_kernel<NBI, WREG, MINB><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n, in_len);
+  return 0;
+}
+
+template <bool WREG, int MINB>
+static int launch_z16p(sww_ctx* c, Sm100State* s, ZArgs A) {
+  if (A.Kz_in <= 32) return launch_z16p_v<2, WREG, MINB>(c, s, A);
+  if (A.Kz_in <= 64) return launch_z16p_v<4, WREG, MINB>(c, s, A);
+  if (A.Kz_in <= 96) return launch_z16p_v<6, WREG, MINB>(c, s, A);
+  return launch_z16p_v<8, WREG, MINB>(c, s, A);
+}
+
 static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
   const char* e = getenv("SWW_Z16_VARIANT");
   const int v = e ? atoi(e) : 0;
+  if (A.Kz_in <= 128) {
+    // table-driven pre / post-processing; the staged row keeps at most one of Z[k], Z[H-k]
+    if (v == 0) return launch_z16p<true, 3>(c, s, A);    // 12 warps / SM, weights in registers
+    if (v == 6) return launch_z16p<false, 4>(c, s, A);   // 16 warps / SM, weights re-read per plane
+    if (v == 7) return launch_z16p<true, 2>(c, s, A);    // 8 warps / SM, no spills
+  }
   switch (v) {
     case 1: return launch_z16_v<8, 2, false>(c, s, A);   // 16 warps/SM, weights loaded at the point of use (exposed latency)
     case 2: return launch_z16_v<8, 1, true>(c, s, A);    // 8 warps/SM, 224 registers
