@@ -1992,9 +1992,12 @@ static int launch_z16(sww_ctx* c, Sm100State* s, ZArgs A) {
   const int v = e ? atoi(e) : 0;
   if (A.Kz_in <= 128) {
     // table-driven pre / post-processing; the staged row keeps at most one of Z[k], Z[H-k]
-    if (v == 0) return launch_z16p<true, 3>(c, s, A);    // 12 warps / SM, weights in registers
-    if (v == 6) return launch_z16p<false, 4>(c, s, A);   // 16 warps / SM, weights re-read per plane
-    if (v == 7) return launch_z16p<true, 2>(c, s, A);    // 8 warps / SM, no spills
+    // measured per C2 realisation (82 launches): 8 warps / SM at 255 registers without spills 88.0 ms, 12 warps / SM at 168
+    // registers (24-56 B of spills) 90.6 ms, 16 warps / SM with the weights re-read per plane 106.9 ms -- the kernel
+    // wants instruction-level parallelism inside the warp more than it wants warps
+    if (v == 0) return launch_z16p<true, 2>(c, s, A);
+    if (v == 6) return launch_z16p<false, 4>(c, s, A);
+    if (v == 7) return launch_z16p<true, 3>(c, s, A);
   }
   switch (v) {
     case 1: return launch_z16_v<8, 2, false>(c, s, A);   // 16 warps/SM, weights loaded at the point of use (exposed latency)

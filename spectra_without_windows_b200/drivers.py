@@ -95,15 +95,17 @@ class Params:
 def _setup(P: Params, sim_no, pipelines, paint_data):
     """Catalogues -> alpha, shot factor, BoxCenter; n(r) maps; context with fields set.
     Restates pk/compute_pk_randoms.py:142-182 (identical blocks in the other scripts)."""
-    data = load_data(sim_no, P.config, None, fkp_weights=False)
-    rand = load_randoms(P.config, None, fkp_weights=False)
+    from .ingest import Cosmology
+    cosmo_coord = Cosmology(h=P.h_fid).match(Omega0_m=P.OmegaM_fid)   # pk/compute_pk_randoms.py:132
+    data = load_data(sim_no, P.config, cosmo_coord, fkp_weights=False)
+    rand = load_randoms(P.config, cosmo_coord, fkp_weights=False)
     alpha_ran = (data["WEIGHT"].sum() / rand["WEIGHT"].sum()).compute()
     shot_fac = ((data["WEIGHT"] ** 2.0).mean().compute() + alpha_ran * (rand["WEIGHT"] ** 2.0).mean().compute()) / rand["WEIGHT"].mean().compute()
     bc = box_center_of(rand)
     mesh = engine.Mesh(P.boxsize_grid, P.grid_3d, bc, P.k_min, P.k_max, P.dk, P.lmax)
     ctx = engine.Context(mesh, int(os.environ.get("LOCAL_RANK", "0")), pipelines)
     nbar_A = load_nbar(P.config, P.spec, 1.0)
-    nbar_A[nbar_A == 0] = min(nbar_A[nbar_A != 0]) * 0.01
+    nbar_A[nbar_A == 0] = nbar_A[nbar_A != 0].min() * 0.01
     print("Loading nbar from mask")
     nbar_mask = load_nbar(P.config, P.spec, alpha_ran)
     diff = None

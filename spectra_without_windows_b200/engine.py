@@ -144,9 +144,13 @@ class Context:
         self.use_stream(t.cuda.current_stream(self.device))
         _lib.check(self.lib.sww_bind_workspace(self._h, self.workspace.data_ptr(), int(need)))
         self._fields = None
-        # optional cache of the Y_lm(r^) maps (l > 0): used when it costs < 15 % of the device memory
+        # optional cache of the Y_lm(r^) maps (l > 0) for the bispectrum pipelines, when it costs < 15 % of the device memory:
+        # their batched inverse z pass multiplies every plane by a harmonic (340 ms per C4 pair with the cache, 453 ms
+        # evaluating the row polynomials on the fly).  The P_l(k) forward transforms evaluate Y_lm(r^) on the fly (a degree-l
+        # Horner polynomial in z per mesh row, csrc/ylm_gen.cuh): as fast as reading the cached map at 512^3, and no memory.
         self._ylm_cache = None
-        if self.fft_backend == 1 and os.environ.get("SWW_YLM_CACHE", "auto") != "0":
+        want_cache = os.environ.get("SWW_YLM_CACHE", "auto")
+        if self.fft_backend == 1 and want_cache != "0" and (want_cache == "1" or any(p.startswith("bk") for p in pipelines)):
             b = _lib.u64(0)
             _lib.check(self.lib.sww_ylm_cache_bytes(self._h, C.byref(b)))
             total = t.cuda.get_device_properties(self.device).total_memory
@@ -229,7 +233,7 @@ class Context:
         nbar = nbar_weight = alpha * nbar_r; nbar_A = nbar_r with empty cells set to
         0.01 * min(nbar_r > 0)  (pk/compute_pk_randoms.py:135-136,160,173-179)."""
         nbar_A = np.array(nbar_r, dtype=np.float64, copy=True)
-        nbar_A[nbar_A == 0] = min(nbar_A[nbar_A != 0]) * 0.01
+        nbar_A[nbar_A == 0] = nbar_A[nbar_A != 0].min() * 0.01
         nbar = nbar_r * alpha
         self.set_fields(nbar, nbar.copy(), nbar_A, shot_fac, P_fkp)
         return nbar_A

@@ -5,8 +5,8 @@ ndarray in -> ndarray out, like the reference, so the parity tests read like the
 own call sites.  The four driver scripts in pk/ and bk/ do NOT round-trip maps through these
 mirrors: they call the fused device pipelines of `engine.Context` directly.
 
-Out of scope: FITS/CSV ingestion with sky->Cartesian transforms
-(`load_data`/`load_randoms` accept Cartesian .npz catalogues instead) and `plotter`.
+`load_data` / `load_randoms` read FITS binary tables, text catalogues (through `ingest.py`: the reference's column logic
+and a restated sky -> Cartesian transform) and Cartesian .npz catalogues.  Out of scope: `plotter`.
 """
 from __future__ import annotations
 
@@ -76,34 +76,85 @@ class Catalog(dict):
             self.attrs["BoxCenter"] = np.asarray(box_center, dtype=np.float64)
 
 
+def _catalog_from_columns(cat):
+    c = Catalog(cat["Position"], cat["WEIGHT"], cat.get("NBAR"))
+    c["WEIGHT_FKP"] = Column(np.asarray(cat["WEIGHT_FKP"], dtype=np.float64))
+    for k in ("Z", "RA", "DEC"):
+        if k in cat:
+            c[k] = Column(cat[k])
+    return c
+
+
 def _load_cartesian(path):
+    """Cartesian .npz catalogue (pos, w[, nbar, box_center]): positions already in Mpc/h, no redshift cut."""
     if not os.path.exists(path):
         raise Exception("Catalogue file '%s' does not exist!" % path)
-    if not path.endswith(".npz"):
-        raise Exception("Only Cartesian .npz catalogues (pos, w[, nbar, box_center]) are supported by the B200 path; "
-                        "FITS/CSV ingestion and the sky->Cartesian transform are out of scope (SURVEY.md section 2 row 4)")
     z = np.load(path)
     return Catalog(z["pos"], z["w"], z["nbar"] if "nbar" in z else None, z["box_center"] if "box_center" in z else None)
 
 
+def _getlist(config, sec, key):
+    try:
+        return [c for c in config.getlist(sec, key) if c]
+    except Exception:
+        return [c.strip() for c in str(config[sec][key]).split(",") if c.strip()]
+
+
 def load_data(sim_no, config, cosmo, fkp_weights=False, weight_only=False, P_fkp=1e4):
-    """Mirror of src/opt_utilities.py:12-82 for Cartesian catalogues: `data_file` may contain '%d'
-    (replaced by sim_no).  FKP weights are erased unless fkp_weights (as :78-81)."""
+    """Mirror of src/opt_utilities.py:12-82.  `data_file` may contain '%d' (replaced by sim_no, with the zero-padded
+    fall-back of :38-40); `.fits` tables and whitespace-separated text files go through the reference's column logic
+    (redshift cut, WEIGHT conventions, SkyToCartesian with `cosmo`, NBAR / WEIGHT_FKP) in `ingest.py`; Cartesian `.npz`
+    catalogues (pos, w[, nbar, box_center]) are taken as they are."""
+    from . import ingest
     name = str(config["catalogs"]["data_file"])
     if "%d" in name:
-        name = name % sim_no
-    cat = _load_cartesian(name)
-    if fkp_weights:
-        cat["WEIGHT_FKP"] = Column(1.0 / (1.0 + cat["NBAR"].v * P_fkp))
-    return cat
+        if sim_no != -1:
+            datfile = name % sim_no
+            if not os.path.exists(datfile):
+                datfile = datfile.replace("_%d" % sim_no, "_%s" % (str(sim_no).zfill(4)))
+            name = datfile
+        else:
+            sim_no = -1
+    else:
+        sim_no = -1
+    if name.endswith(".npz"):
+        cat = _load_cartesian(name)
+        if weight_only:
+            return cat["WEIGHT"]
+        if fkp_weights:
+            cat["WEIGHT_FKP"] = Column(1.0 / (1.0 + cat["NBAR"].v * P_fkp))
+        return cat
+    if cosmo is None:
+        raise Exception("a fiducial cosmology is needed to convert '%s' to Cartesian co-ordinates" % name)
+    cols = ingest.read_catalog(name, _getlist(config, "catalogs", "data_columns"))
+    cols = ingest.apply_reference_columns(cols, float(config["sample"]["z_min"]), float(config["sample"]["z_max"]), cosmo,
+                                          True, sim_no, fkp_weights, P_fkp)
+    print("Loaded %d galaxies\n" % len(cols["WEIGHT"]))
+    if weight_only:
+        return Column(cols["WEIGHT"])
+    return _catalog_from_columns(cols)
 
 
 def load_randoms(config, cosmo, fkp_weights=False, weight_only=False, P_fkp=1e4):
-    """Mirror of src/opt_utilities.py:84-143 for Cartesian catalogues."""
-    cat = _load_cartesian(str(config["catalogs"]["randoms_file"]))
-    if fkp_weights:
-        cat["WEIGHT_FKP"] = Column(1.0 / (1.0 + cat["NBAR"].v * P_fkp))
-    return cat
+    """Mirror of src/opt_utilities.py:84-143 (see load_data)."""
+    from . import ingest
+    name = str(config["catalogs"]["randoms_file"])
+    if name.endswith(".npz"):
+        cat = _load_cartesian(name)
+        if weight_only:
+            return cat["WEIGHT"]
+        if fkp_weights:
+            cat["WEIGHT_FKP"] = Column(1.0 / (1.0 + cat["NBAR"].v * P_fkp))
+        return cat
+    if cosmo is None:
+        raise Exception("a fiducial cosmology is needed to convert '%s' to Cartesian co-ordinates" % name)
+    cols = ingest.read_catalog(name, _getlist(config, "catalogs", "randoms_columns"))
+    cols = ingest.apply_reference_columns(cols, float(config["sample"]["z_min"]), float(config["sample"]["z_max"]), cosmo,
+                                          False, -1, fkp_weights, P_fkp)
+    print("Loaded %d randoms\n" % len(cols["WEIGHT"]))
+    if weight_only:
+        return Column(cols["WEIGHT"])
+    return _catalog_from_columns(cols)
 
 
 def load_nbar(config, spec_type, alpha_ran):
