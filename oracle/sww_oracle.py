@@ -358,6 +358,27 @@ def tsc_paint(pos, w, box, grid, box_center):
     return out.reshape(grid)
 
 
+def cic_paint(pos, w, box, grid, box_center):
+    """CIC deposit (window='cic' of the same to_mesh call): base cell floor((x - BoxCenter)/H), weights 1-d and d."""
+    grid = np.asarray(grid, int)
+    H = np.asarray(box, float) / grid
+    s = (np.asarray(pos, float) - np.asarray(box_center, float)) / H
+    c = np.floor(s)
+    d = s - c
+    c = c.astype(np.int64)
+    wt = [1.0 - d, d]
+    out = np.zeros(int(grid.prod()))
+    for ix in range(2):
+        i = (c[:, 0] + ix) % grid[0]
+        for iy in range(2):
+            j = (c[:, 1] + iy) % grid[1]
+            for iz in range(2):
+                k = (c[:, 2] + iz) % grid[2]
+                out += np.bincount((i * grid[1] + j) * grid[2] + k,
+                                   weights=w * wt[ix][:, 0] * wt[iy][:, 1] * wt[iz][:, 2], minlength=out.size)
+    return out.reshape(grid)
+
+
 def grid_data(dpos, dw, rpos, rw, box, grid, box_center):
     """(n_g - alpha n_r)/V_cell and alpha n_r/V_cell (src/opt_utilities.py:228,257-267)."""
     alpha = dw.sum() / rw.sum()

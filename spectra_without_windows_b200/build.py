@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "libsww.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
-SOURCES = ["ctx.cu", "kernels.cu", "fft.cu", "fft_sm100.cu", "pipelines.cu", "bk.cu", "gram.cu", "rng.cu", "ml.cu", "rowmesh.cu"]
+SOURCES = ["ctx.cu", "kernels.cu", "fft.cu", "fft_sm100.cu", "pipelines.cu", "bk.cu", "gram.cu", "rng.cu", "ml.cu", "rowmesh.cu", "paint.cu"]
 
 
 def _stamp(paths):
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, logs[src]))
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(10, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(12, len(SOURCES))) as ex:
         objs = list(ex.map(cc, SOURCES))
     with open(os.path.join(bdir, "ptxas.log"), "w") as f:
         for s in SOURCES:

@@ -147,6 +147,7 @@ extern "C" int sww_ctx_destroy(sww_ctx* c) {
   cudaFree(c->d_counter);
   if (c->d_tris) cudaFree(c->d_tris);
   if (c->d_q1_scratch) cudaFree(c->d_q1_scratch);
+  if (c->d_paint_scratch) cudaFree(c->d_paint_scratch);
   if (c->d_gram_partial) cudaFree(c->d_gram_partial);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;

@@ -395,63 +395,7 @@ int k_symmetrise(sww_ctx* c, double* F, int n) {
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// Painting: cell = rint((x - BoxCenter)/H) mod N ; TSC weights 1/2(1/2-d)^2, 3/4-d^2, 1/2(1/2+d)^2
-// (restating FKPCatalog.to_mesh(window='tsc'), src/opt_utilities.py:219-260); CIC: floor + linear.
-// v1: one thread per particle, FP64 RED atomics straight to L2.
-// ------------------------------------------------------------------------------------------
-__global__ void paint_kernel(Geo g, const double* __restrict__ pos, const double* __restrict__ w, unsigned long long n,
-                             double bcx, double bcy, double bcz, double Hx, double Hy, double Hz, int scheme,
-                             double scale, double* __restrict__ out) {
-  for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n;
-       p += (unsigned long long)gridDim.x * blockDim.x) {
-    double s[3] = {(pos[3 * p] - bcx) / Hx, (pos[3 * p + 1] - bcy) / Hy, (pos[3 * p + 2] - bcz) / Hz};
-    int c0[3];
-    double wt[3][3];
-    int ns = scheme;  // 3 = TSC, 2 = CIC
-    for (int d = 0; d < 3; ++d) {
-      if (scheme == 3) {
-        double c = rint(s[d]);
-        double dd = s[d] - c;
-        c0[d] = (int)c - 1;
-        wt[d][0] = 0.5 * (0.5 - dd) * (0.5 - dd);
-        wt[d][1] = 0.75 - dd * dd;
-        wt[d][2] = 0.5 * (0.5 + dd) * (0.5 + dd);
-      } else {
-        double c = floor(s[d]);
-        double dd = s[d] - c;
-        c0[d] = (int)c;
-        wt[d][0] = 1.0 - dd;
-        wt[d][1] = dd;
-        wt[d][2] = 0.0;
-      }
-    }
-    double ww = w[p] * scale;
-    int dims[3] = {g.nx, g.ny, g.nz};
-    for (int a = 0; a < ns; ++a) {
-      int i = ((c0[0] + a) % dims[0] + dims[0]) % dims[0];
-      for (int b = 0; b < ns; ++b) {
-        int j = ((c0[1] + b) % dims[1] + dims[1]) % dims[1];
-        double wab = ww * wt[0][a] * wt[1][b];
-        for (int cz = 0; cz < ns; ++cz) {
-          int k = ((c0[2] + cz) % dims[2] + dims[2]) % dims[2];
-          atomicAdd(&out[((long long)i * g.ny + j) * g.nz + k], wab * wt[2][cz]);
-        }
-      }
-    }
-  }
-}
-
-int k_paint(sww_ctx* c, const double* pos, const double* w, unsigned long long n, const double bc[3], int scheme,
-            double scale, double* out) {
-  if (n == 0) return 0;
-  double Hx = c->box[0] / c->g.nx, Hy = c->box[1] / c->g.ny, Hz = c->box[2] / c->g.nz;
-  paint_kernel<<<sww_grid_for((long long)n, 256, SMS * 16), 256, 0, c->stream>>>(c->g, pos, w, n, bc[0], bc[1], bc[2], Hx,
-                                                                               Hy, Hz, scheme, scale, out);
-  c->n_own++;
-  SWW_CUDA(cudaGetLastError());
-  return 0;
-}
+// painting: paint.cu
 
 // ------------------------------------------------------------------------------------------
 // optional cache of Y_lm(r^) maps, lm >= 1

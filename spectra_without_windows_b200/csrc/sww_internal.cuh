@@ -128,6 +128,8 @@ struct sww_ctx {
   size_t gram_partial_bytes = 0;
   double* d_q1_scratch = nullptr;
   size_t q1_scratch_elems = 0;
+  void* d_paint_scratch = nullptr;    // tile bins of the painter (paint.cu)
+  size_t paint_scratch_bytes = 0;
   // coarse "row mesh" (fft_sm100.cu, "row mesh"): a child context on a smaller power-of-two grid with the same box and
   // bins, on which the band-limited Fisher rows u_alpha -> FT[nW u_alpha] are evaluated exactly (no aliasing into the
   // binned modes) against a low-pass-filtered copy of the weight map

@@ -100,3 +100,21 @@ def test_ylm_table_matches_sympy():
             mono, _ = YLM_TABLE[(f.l, f.m)]
             mine = sum(c * v[0] ** a * v[1] ** b * v[2] ** d for c, a, b, d in mono)
             assert np.max(np.abs(mine - f(*v))) < 1e-14
+
+
+def test_oracle_painters_conserve_mass_and_agree_on_cell_centres():
+    """TSC and CIC restatements (src/opt_utilities.py:219-267 call site): mass conservation, periodic wrap, and a particle
+    on a cell centre deposits (1/8, 3/4, 1/8) per axis with TSC and everything into one cell with CIC."""
+    from oracle import sww_oracle as orc
+    grid, box, bc = (12, 10, 8), (120.0, 100.0, 80.0), (5.0, -3.0, 1.0)
+    rng = np.random.default_rng(2)
+    pos = np.asarray(bc) + rng.uniform(-1.5, 1.5, size=(500, 3)) * np.asarray(box)
+    w = rng.uniform(0.5, 1.5, 500)
+    for f in (orc.tsc_paint, orc.cic_paint):
+        m = f(pos, w, box, grid, bc)
+        assert m.shape == grid and abs(m.sum() - w.sum()) < 1e-10
+    one = np.asarray(bc)[None, :] + np.array([[30.0, 20.0, 10.0]])
+    t = orc.tsc_paint(one, np.ones(1), box, grid, bc)
+    assert abs(t[3, 2, 1] - 0.75 ** 3) < 1e-15 and abs(t[2, 2, 1] - 0.125 * 0.75 ** 2) < 1e-15
+    c = orc.cic_paint(one, np.ones(1), box, grid, bc)
+    assert c[3, 2, 1] == 1.0 and c.sum() == 1.0
