@@ -92,18 +92,19 @@ class Params:
         print("\n########################################################")
 
 
-def _setup(P: Params, sim_no, pipelines, paint_data):
-    """Catalogues -> alpha, shot factor, BoxCenter; n(r) maps; context with fields set.
-    Restates pk/compute_pk_randoms.py:142-182 (identical blocks in the other scripts)."""
+def _catalogues(P: Params, sim_no):
+    """Catalogues of one simulation -> alpha, shot factor, BoxCenter (pk/compute_pk_randoms.py:142-153)."""
     from .ingest import Cosmology
     cosmo_coord = Cosmology(h=P.h_fid).match(Omega0_m=P.OmegaM_fid)   # pk/compute_pk_randoms.py:132
     data = load_data(sim_no, P.config, cosmo_coord, fkp_weights=False)
     rand = load_randoms(P.config, cosmo_coord, fkp_weights=False)
     alpha_ran = (data["WEIGHT"].sum() / rand["WEIGHT"].sum()).compute()
     shot_fac = ((data["WEIGHT"] ** 2.0).mean().compute() + alpha_ran * (rand["WEIGHT"] ** 2.0).mean().compute()) / rand["WEIGHT"].mean().compute()
-    bc = box_center_of(rand)
-    mesh = engine.Mesh(P.boxsize_grid, P.grid_3d, bc, P.k_min, P.k_max, P.dk, P.lmax)
-    ctx = engine.Context(mesh, int(os.environ.get("LOCAL_RANK", "0")), pipelines)
+    return data, rand, alpha_ran, shot_fac, box_center_of(rand)
+
+
+def _fields(P: Params, ctx, data, rand, bc, alpha_ran, paint_data):
+    """n(r) maps of one simulation (and its painted field): pk/compute_pk_randoms.py:155-182."""
     nbar_A = load_nbar(P.config, P.spec, 1.0)
     nbar_A[nbar_A == 0] = nbar_A[nbar_A != 0].min() * 0.01
     print("Loading nbar from mask")
@@ -117,6 +118,16 @@ def _setup(P: Params, sim_no, pipelines, paint_data):
             diff, nbar = d
         else:
             diff = d
+    return nbar, nbar_mask, nbar_A, diff
+
+
+def _setup(P: Params, sim_no, pipelines, paint_data):
+    """Catalogues -> alpha, shot factor, BoxCenter; n(r) maps; context with fields set.
+    Restates pk/compute_pk_randoms.py:142-182 (identical blocks in the other scripts)."""
+    data, rand, alpha_ran, shot_fac, bc = _catalogues(P, sim_no)
+    mesh = engine.Mesh(P.boxsize_grid, P.grid_3d, bc, P.k_min, P.k_max, P.dk, P.lmax)
+    ctx = engine.Context(mesh, int(os.environ.get("LOCAL_RANK", "0")), pipelines)
+    nbar, nbar_mask, nbar_A, diff = _fields(P, ctx, data, rand, bc, alpha_ran, paint_data)
     ctx.set_fields(nbar, nbar_mask, nbar_A, shot_fac)
     ctx.set_include_pix(P.include_pix)
     return ctx, mesh, nbar_A, alpha_ran, shot_fac, diff
@@ -283,12 +294,80 @@ def write_pk_text(path, P, sim_no, p_alpha, n_k):
 
 
 # ------------------------------------------------------------------------------ bk randoms
-BIAS_DTYPE = os.environ.get("SWW_BIAS_DTYPE", "complex128")   # the reference writes complex64 (bk/compute_bk_randoms.py:273)
+BIAS_DTYPE = os.environ.get("SWW_BIAS_DTYPE", "complex64")   # what the reference writes (bk/compute_bk_randoms.py:273)
+
+
+class GmapWriter:
+    """Asynchronous writer of the `*_bk_bias_alpha_*.npz` files (`g_a`, `tilde_g_a`: complex [n_l, n_k, nx, ny, nz],
+    bk/compute_bk_randoms.py:273-274).  The maps are cast to the file dtype ON THE DEVICE, copied to one of `depth`
+    pinned host buffer pairs on a side stream, and `np.savez`ed by a worker thread, so the Monte-Carlo loop only waits
+    when all buffers are still being written (the reference's synchronous np.savez costs seconds per 9 GB seed)."""
+
+    def __init__(self, ctx, depth=2, dtype=None):
+        import queue
+        import threading
+        self.t = engine.torch()
+        self.ctx = ctx
+        self.dtype = np.dtype(dtype or BIAS_DTYPE)
+        self.tdtype = {np.dtype("complex64"): self.t.complex64, np.dtype("complex128"): self.t.complex128}[self.dtype]
+        self.side = self.t.cuda.Stream(device=ctx.device)
+        self.free = queue.Queue()
+        self.todo = queue.Queue()
+        self.depth = depth
+        self.bufs = None
+        self.err = None
+        self.th = threading.Thread(target=self._work, daemon=True)
+        self.th.start()
+
+    def _work(self):
+        while True:
+            item = self.todo.get()
+            if item is None:
+                return
+            path, i, ev = item
+            try:
+                ev.synchronize()
+                g, tg = self.bufs[i]
+                np.savez(path, g_a=g.numpy(), tilde_g_a=tg.numpy())
+            except Exception as ex:      # surfaced by save() / close()
+                self.err = ex
+            self.free.put(i)
+
+    def save(self, path, g, tg):
+        t = self.t
+        if self.err:
+            raise self.err
+        if self.bufs is None:
+            self.bufs = [(t.empty(tuple(g.shape), dtype=self.tdtype).pin_memory(), t.empty(tuple(g.shape), dtype=self.tdtype).pin_memory())
+                         for _ in range(self.depth)]
+            for i in range(self.depth):
+                self.free.put(i)
+        i = self.free.get()                      # back-pressure: waits for a buffer pair whose file is written
+        self.side.wait_stream(self.ctx.stream)
+        with t.cuda.stream(self.side):
+            gc, tgc = g.to(self.tdtype), tg.to(self.tdtype)
+            cast = t.cuda.Event()
+            cast.record(self.side)
+            self.bufs[i][0].copy_(gc, non_blocking=True)
+            self.bufs[i][1].copy_(tgc, non_blocking=True)
+            ev = t.cuda.Event()
+            ev.record(self.side)
+        # the next pair overwrites g / tg on the context stream: it only has to wait for the device-side casts
+        self.ctx.stream.wait_event(cast)
+        self.todo.put((path, i, ev))
+
+    def close(self):
+        self.todo.put(None)
+        self.th.join()
+        if self.err:
+            raise self.err
 
 
 def save_gmaps(path, g, tg):
-    """`g_a`, `tilde_g_a` arrays [n_l, n_k, nx, ny, nz] as in bk/compute_bk_randoms.py:273-274."""
-    np.savez(path, g_a=g.cpu().numpy().astype(BIAS_DTYPE), tilde_g_a=tg.cpu().numpy().astype(BIAS_DTYPE))
+    """`g_a`, `tilde_g_a` arrays [n_l, n_k, nx, ny, nz] as in bk/compute_bk_randoms.py:273-274 (synchronous)."""
+    t = engine.torch()
+    td = t.complex64 if np.dtype(BIAS_DTYPE) == np.dtype("complex64") else t.complex128
+    np.savez(path, g_a=g.to(td).cpu().numpy(), tilde_g_a=tg.to(td).cpu().numpy())
 
 
 def bk_randoms_main(argv):
@@ -323,9 +402,11 @@ def bk_randoms_main(argv):
     print("\n## Computing g-a maps, phi-alpha maps and the Fisher matrix contribution in %d bins on the GPU" % ctx.n_b_bk)
     print("Computing Delta_{abc} normalization")
     F, (gA, tgA, gB, tgB) = ctx.bk_fisher_pair(diffA, diffB)
-    save_gmaps(bias_file_name(rand_it1), gA, tgA)
-    save_gmaps(bias_file_name(rand_it2), gB, tgB)
+    wr = GmapWriter(ctx)                      # the two files are written while the other is cast / copied
+    wr.save(bias_file_name(rand_it1), gA, tgA)
+    wr.save(bias_file_name(rand_it2), gB, tgB)
     np.save(fish_file_name, F.cpu().numpy())
+    wr.close()
     duration = time.time() - init
     print("\n### Exiting after %d seconds (%d minutes)\n" % (duration, duration // 60))
     sys.exit()

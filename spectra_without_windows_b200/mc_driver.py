@@ -8,6 +8,12 @@ the combined `fisher-pk_*` / `bias-pk_*` (or `fisher-bk_*`) files the data scrip
 data-path collective: realisations are independent.
 
     torchrun --nproc-per-node 8 -m spectra_without_windows_b200.mc_driver pk <paramfile> [--per-seed]
+    torchrun --nproc-per-node 8 -m spectra_without_windows_b200.mc_driver bk <paramfile> [--data 1,2,..] [--no-bias-maps]
+
+`--data s1,s2,..` (bispectrum): in-memory hand-off to the data step -- the listed catalogues' g-maps stay on the device,
+every Monte-Carlo seed's g / g~ maps feed their 1-field sums straight from the Fisher pair, one all-reduce of the sums, and
+rank 0 writes the `bk_*.txt` files compute_bk_data.py would write.  The `*_bk_bias_alpha_*.npz` files of the reference's
+contract are written asynchronously (complex64, like the reference) unless `--no-bias-maps`.
 
 `--inflight K` (default 2, P_l(k) with device-generated fields): K realisations are kept in flight per GPU, each on
 its own context and stream, as far as the device memory holds K workspaces.
@@ -84,6 +90,8 @@ def main(argv):
     per_seed = "--per-seed" in argv
     host_rng = "--host-rng" in argv
     inflight = int(argv[argv.index("--inflight") + 1]) if "--inflight" in argv else 2
+    data_sims = [int(v) for v in argv[argv.index("--data") + 1].split(",")] if "--data" in argv else []
+    write_maps = "--no-bias-maps" not in argv
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -94,7 +102,7 @@ def main(argv):
     for d in (P.outdir, P.mcdir):
         os.makedirs(d, exist_ok=True)
     tag = P.ktag()
-    pipe = (("pk_fisher",) if P.wtype == 0 else ("pk_ml",)) if spec == "pk" else ("bk_fisher",)
+    pipe = (("pk_fisher",) if P.wtype == 0 else ("pk_ml",)) if spec == "pk" else (("bk_fisher", "bk_data") if data_sims else ("bk_fisher",))
     ctx, mesh, nbar_A, alpha_ran, shot_fac, _ = drivers._setup(P, 1, pipe, paint_data=False)
     if P.wtype == 1:
         P.load_fiducial_pk(ctx)
@@ -171,15 +179,37 @@ def main(argv):
         fish_name = lambda r: P.mcdir + "%s%d_%s_bk_fish_alpha_beta_%s.npy" % (P.string, r, P.weight_type, tag)
         bias_name = lambda ii: P.mcdir + "%s%d_%s_bk_bias_alpha_%s.npz" % (P.string, ii, P.weight_type, tag)
         maps = None
+        # In-memory hand-off of the g / g~ maps to the data step (bk/compute_bk_randoms.py:273-274 ->
+        # bk/compute_bk_data.py:370-406): with `--data s1,s2,..` the catalogues' own maps are computed first and stay on
+        # the device, and every Monte-Carlo seed's maps go straight from the Fisher pair into the 1-field sums -- they
+        # never leave HBM.  The `.npz` contract files are still written (asynchronously, complex64) unless --no-bias-maps.
+        held = {}
+        if data_sims:
+            for s in data_sims:
+                dat, rnd, alpha_s, shot_s, bc_s = drivers._catalogues(P, s)
+                nbar_s, mask_s, nA_s, diff_s = drivers._fields(P, ctx, dat, rnd, bc_s, alpha_s, True)
+                ctx.set_fields(nbar_s, mask_s, nA_s, shot_s)
+                g_s = ctx.bk_gmaps(diff_s, data=True)
+                held[s] = (g_s, ctx.bk_q3(g_s), ctx.zeros((ctx.n_tri, mesh.n_l)))
+            dat, rnd, alpha_1, shot_1, bc_1 = drivers._catalogues(P, 1)          # back to the Monte-Carlo fields
+            nbar_1, mask_1, nA_1, _ = drivers._fields(P, ctx, dat, rnd, bc_1, alpha_1, False)
+            ctx.set_fields(nbar_1, mask_1, nA_1, shot_1)
+            torch.cuda.synchronize()
+            t_loop = time.time()
+        writer = drivers.GmapWriter(ctx) if write_maps else None
 
         def one(pair, ab):
             nonlocal maps
             aA = ab[0] if host_rng else ctx.grf_legacy(2 * pair, sig_dev)
             aB = ab[1] if host_rng else ctx.grf_legacy(2 * pair + 1, sig_dev)
             F, maps = ctx.bk_fisher_pair(aA, aB, maps)
-            # the g-maps of every seed feed the 1-field term of compute_bk_data.py (bk/compute_bk_randoms.py:273-274)
-            drivers.save_gmaps(bias_name(2 * pair), maps[0], maps[1])
-            drivers.save_gmaps(bias_name(2 * pair + 1), maps[2], maps[3])
+            for g_s, _, q1_s in held.values():
+                ctx.bk_q1_accumulate(g_s, maps[0], maps[1], P.N_mc, q1_s)
+                ctx.bk_q1_accumulate(g_s, maps[2], maps[3], P.N_mc, q1_s)
+            if writer:
+                # the g-maps of every seed feed the 1-field term of compute_bk_data.py (bk/compute_bk_randoms.py:273-274)
+                writer.save(bias_name(2 * pair), maps[0], maps[1])
+                writer.save(bias_name(2 * pair + 1), maps[2], maps[3])
             if per_seed:
                 np.save(fish_name(pair), F.cpu().numpy())
             return (F,)
@@ -187,8 +217,25 @@ def main(argv):
         (F,), n = run_mc(range(1, P.N_mc // 2 + 1), one, lambda: (ctx.zeros((n_b, n_b)),), rank, world,
                          dist if world > 1 else None,
                          prefetch_fn=(lambda p: (grf(2 * p), grf(2 * p + 1))) if host_rng else None, workers=1)
+        if writer:
+            writer.close()
+        reduce_sums([h[2] for h in held.values()], world > 1, dist if world > 1 else None)
         if rank == 0:
-            np.save(P.outdir + "fisher-bk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (F / (P.N_mc // 2)).cpu().numpy())
+            fish = (F / (P.N_mc // 2)).cpu().numpy()
+            np.save(P.outdir + "fisher-bk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), fish)
+            if held:
+                # bk/compute_bk_data.py:409-451 for every held catalogue
+                Delta = ctx.bk_delta().cpu().numpy()
+                nt, n_l = ctx.n_tri, mesh.n_l
+                for s, (_, q3, q1) in held.items():
+                    q = (q3 + q1 if P.use_qbar else q3).cpu().numpy()
+                    q_alpha = np.concatenate([q[:, l_i] / Delta[l_i * nt:(l_i + 1) * nt] for l_i in range(n_l)])
+                    p_alpha = np.matmul(np.linalg.inv(fish), q_alpha)
+                    if s != -1:
+                        name = P.outdir + "bk_%s%d_%s_N%d_%s.txt" % (P.string, s, P.weight_type, P.N_mc, tag)
+                    else:
+                        name = P.outdir + "bk_%s%s_N%d_%s.txt" % (P.string, P.weight_type, P.N_mc, tag)
+                    drivers.write_bk_text(name, P, s, p_alpha, mesh.triangles())
     torch.cuda.synchronize()
     if rank == 0:
         dt = time.time() - t_loop

@@ -80,3 +80,27 @@ def test_mc_driver_writes_combined_files(world, golden, tmp_path):
     run("bk/compute_bk_data.py", 1, p)
     assert relerr(np.loadtxt(glob.glob(od + "pk_*.txt")[0]), g["pk_p"]) < 2e-8
     assert relerr(np.loadtxt(glob.glob(od + "bk_*.txt")[0]), g["bk_p"]) < 2e-8
+
+
+def test_bk_in_memory_handoff_to_the_data_step(world, golden, tmp_path):
+    """`mc_driver bk --data 1`: the Monte-Carlo g / g~ maps feed the catalogue's 1-field sums on the device (no .npz
+    round trip) and rank 0 writes the B_l text compute_bk_data.py would write; the contract files still appear
+    (asynchronous complex64 writer), and the classic two-step path on those files gives the same numbers."""
+    from spectra_without_windows_b200 import synthetic as syn
+    w, g = world("toyD"), golden("toyD")
+    p = syn.write_world_files(w, str(tmp_path))
+    mc, od = str(tmp_path) + "/mc/", str(tmp_path) + "/out/"
+    r = subprocess.run([sys.executable, "-m", "spectra_without_windows_b200.mc_driver", "bk", p, "--data", "1"], capture_output=True,
+                       text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    f = glob.glob(od + "bk_*.txt")[0]
+    assert os.path.basename(f) == str(g["bk_txt_name"])
+    assert open(f).read().split("\n")[:13] == str(g["bk_txt"]).split("\n")[:13]
+    fused = np.loadtxt(f)
+    assert relerr(fused, g["bk_p"]) < 2e-8
+    z = np.load(sorted(glob.glob(mc + "*_FKP_bk_bias_alpha_*.npz"))[0])
+    assert z["g_a"].dtype == np.complex64 and tuple(z["g_a"].shape) == tuple(g["bk_g_shape"])
+    os.remove(f)
+    run("bk/compute_bk_data.py", 1, p)                        # two-step path on the written files (complex64 maps)
+    two = np.loadtxt(glob.glob(od + "bk_*.txt")[0])
+    assert relerr(two[:, 3:], fused[:, 3:]) < 1e-5            # single-precision files, as in the reference
