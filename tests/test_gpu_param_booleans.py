@@ -88,7 +88,9 @@ def test_scripts_with_include_pix(world, golden, tmp_path):
     mc, od = str(tmp_path) + "/mc/", str(tmp_path) + "/out/"
     for script, arg in (("pk/compute_pk_randoms.py", 1), ("pk/compute_pk_randoms.py", 2), ("pk/compute_pk_data.py", 1),
                         ("bk/compute_bk_randoms.py", 1), ("bk/compute_bk_data.py", 1)):
-        r = subprocess.run([sys.executable, os.path.join(ROOT, script), str(arg), p], capture_output=True, text=True)
+        # FP64 goldens: complex128 bias files (the default, complex64 like the reference, costs ~1e-7 on B_l)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, script), str(arg), p], capture_output=True, text=True,
+                           env=dict(os.environ, SWW_BIAS_DTYPE="complex128"))
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     f = glob.glob(od + "pk_*.txt")[0]
     assert open(f).read().split("\n")[:15] == str(g["pk_txt"]).split("\n")[:15]     # header says pixellation : 1

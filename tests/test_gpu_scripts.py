@@ -13,8 +13,13 @@ from conftest import ROOT, relerr
 pytestmark = pytest.mark.gpu
 
 
-def run(script, arg, param):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, script), str(arg), param], capture_output=True, text=True)
+# the goldens come from the FP64-promoted reference: the file-based bispectrum path is pinned with complex128 bias files
+# (the default, like the reference's shipped scripts, is complex64 -- exercised by the hand-off test below)
+ENV128 = dict(os.environ, SWW_BIAS_DTYPE="complex128")
+
+
+def run(script, arg, param, env=ENV128):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, script), str(arg), param], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
 
@@ -70,7 +75,7 @@ def test_mc_driver_writes_combined_files(world, golden, tmp_path):
     od = str(tmp_path) + "/out/"
     for spec in ("pk", "bk"):
         r = subprocess.run([sys.executable, "-m", "spectra_without_windows_b200.mc_driver", spec, p], capture_output=True,
-                           text=True, cwd=ROOT)
+                           text=True, cwd=ROOT, env=ENV128)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert relerr(np.load(glob.glob(od + "fisher-pk_*.npy")[0]), g["pk_fish_comb"]) < 1e-9
     assert relerr(np.load(glob.glob(od + "bias-pk_*.npy")[0]), g["pk_bias_comb"]) < 1e-9
@@ -101,6 +106,6 @@ def test_bk_in_memory_handoff_to_the_data_step(world, golden, tmp_path):
     z = np.load(sorted(glob.glob(mc + "*_FKP_bk_bias_alpha_*.npz"))[0])
     assert z["g_a"].dtype == np.complex64 and tuple(z["g_a"].shape) == tuple(g["bk_g_shape"])
     os.remove(f)
-    run("bk/compute_bk_data.py", 1, p)                        # two-step path on the written files (complex64 maps)
+    run("bk/compute_bk_data.py", 1, p, env=None)              # two-step path on the written files (complex64 maps)
     two = np.loadtxt(glob.glob(od + "bk_*.txt")[0])
     assert relerr(two[:, 3:], fused[:, 3:]) < 1e-5            # single-precision files, as in the reference
