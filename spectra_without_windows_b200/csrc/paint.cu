@@ -23,7 +23,6 @@
 
 #include "sww_internal.cuh"
 
-#define PT_THREADS 128
 
 struct PaintGeo {
   int n[3];        // mesh
@@ -100,11 +99,12 @@ __global__ void paint_scatter_kernel(PaintGeo G, const double* __restrict__ pos,
 
 // one CTA per tile of colour (cx, cy, cz); colours along an axis: tile parity, and 2 for the last tile of an odd count
 template <int NS, int PT_T>   // stencil width (3 = TSC, 2 = CIC), tile edge
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(PT_T == 4 ? 256 : 128)
 paint_tile_kernel(PaintGeo G, int3 ncol, int3 col, const double* __restrict__ pos, const double* __restrict__ w, double scale,
                   const long long* __restrict__ offs, const unsigned int* __restrict__ order,
                   const unsigned long long* __restrict__ maxw, double* __restrict__ out) {
   constexpr int PT_B = PT_T + 2, PT_CELLS = PT_B * PT_B * PT_B;   // block = tile + one-cell halo
+  constexpr int PT_THREADS = PT_T == 4 ? 256 : 128;                // crowded (4^3) tiles get twice the lanes
   __shared__ unsigned long long acc[PT_CELLS];
   const int tid = threadIdx.x;
   // tiles of this colour along each axis
@@ -292,7 +292,7 @@ int k_paint(sww_ctx* c, const double* pos, const double* w, unsigned long long n
           long long tiles = (long long)((G.t[0] + 1) / 2) * ((G.t[1] + 1) / 2) * ((G.t[2] + 1) / 2);
           int grid = (int)std::min<long long>(tiles, (long long)SMS * 16);
 #define PT_LAUNCH(NS_, T_) \
-  paint_tile_kernel<NS_, T_><<<grid, PT_THREADS, 0, c->stream>>>(G, ncol, make_int3(cx, cy, cz), pos, w, scale, offs, order, maxw, out)
+  paint_tile_kernel<NS_, T_><<<grid, (T_) == 4 ? 256 : 128, 0, c->stream>>>(G, ncol, make_int3(cx, cy, cz), pos, w, scale, offs, order, maxw, out)
           if (scheme == 3) {
             if (G.T == 8) PT_LAUNCH(3, 8); else PT_LAUNCH(3, 4);
           } else {

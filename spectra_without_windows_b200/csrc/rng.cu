@@ -12,10 +12,12 @@
 //     [f*x2, f*x1] exactly as legacy_gauss caches them.
 // The uniform stream and the accept/reject decisions are bit-exact; the Gaussian values agree with
 // glibc's to the last bit or two (CUDA's log/sqrt are IEEE-accurate to <= 1 ulp).
+#include "mt_jump_tab.h"
 #include "sww_internal.cuh"
 
 #define MT_N 624
 #define MT_M 397
+#define MT_DEG 19937
 
 __device__ __forceinline__ unsigned mt_mix(unsigned a, unsigned b, unsigned m) {
   unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
@@ -65,6 +67,86 @@ __global__ void __launch_bounds__(256) mt_words_kernel(unsigned* __restrict__ st
   }
   __syncthreads();
   for (int i = t; i < MT_N; i += 256) state[i] = mt[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Jump-ahead (Haramoto et al. 2008): ONE legacy stream split over many CTAs.  Sub-stream u of a field starts u * L0 words
+// into the stream (L0 = MT_JUMP_SUB_BLOCKS * 624); its 624-word window is g(F) applied to the seeded window, with
+// g = x^(u L0) mod phi and F the one-word step.  With Q_k = x^(2^k L0) mod phi from the generated table
+// (tools/mt_jump.py -> mt_jump_tab.h), the windows of all sub-streams follow in ceil(log2 U) rounds: round k multiplies
+// the windows whose index has bit k set by Q_k.  Because F is linear, q(F) w = XOR over the set bits i of q of F^i w, and
+// F^i w is just the window of w's OWN sequence at offset i: the CTA extends the window by 19937 words in shared memory and
+// every thread j accumulates h[j] = XOR_i q_i x[i + j] -- no sequential Horner chain.
+// ------------------------------------------------------------------------------------------
+#define MT_JUMP_X (MT_N + MT_DEG + 3)
+__global__ void mt_replicate_kernel(const unsigned* __restrict__ key, unsigned* __restrict__ windows, int U) {
+  const unsigned* k = key + (long long)blockIdx.y * MT_N;
+  unsigned* w = windows + ((long long)blockIdx.y * U + blockIdx.x) * MT_N;
+  for (int i = threadIdx.x; i < MT_N; i += blockDim.x) w[i] = k[i];
+}
+
+__global__ void __launch_bounds__(640) mt_jump_round_kernel(unsigned* __restrict__ windows, int U, int k,
+                                                            const unsigned* __restrict__ polys) {
+  const int u = blockIdx.x;
+  if (!((u >> k) & 1)) return;
+  extern __shared__ unsigned mt_sm[];
+  unsigned* x = mt_sm;                 // [MT_JUMP_X] the window and the next 19937 words of its sequence
+  unsigned* q = mt_sm + MT_JUMP_X;     // [624] bits of Q_k
+  unsigned* w = windows + ((long long)blockIdx.y * U + u) * MT_N;
+  const int t = threadIdx.x;
+  for (int i = t; i < MT_N; i += 640) {
+    x[i] = w[i];
+    q[i] = polys[k * MT_N + i];
+  }
+  __syncthreads();
+  // x[n + 624] = mix(x[n], x[n + 1], x[n + 397]): 227 consecutive n only depend on words already there
+  for (int base = 0; base < MT_DEG; base += 227) {
+    const int n = base + t;
+    if (t < 227 && n < MT_DEG) x[n + MT_N] = mt_mix(x[n], x[n + 1], x[n + MT_M]);
+    __syncthreads();
+  }
+  if (t < MT_N) {
+    unsigned acc = 0u;
+    for (int wi = 0; wi < MT_N; ++wi) {
+      const unsigned bits = q[wi];
+      if (bits == 0u) continue;        // uniform: q is shared by the CTA
+      const unsigned* xp = x + 32 * wi + t;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) acc ^= xp[b] & (0u - ((bits >> b) & 1u));
+    }
+    w[t] = acc;
+  }
+}
+
+// sub-stream u = u0 + blockIdx.x of seed blockIdx.y: MT_JUMP_SUB_BLOCKS blocks of tempered words from its window
+__global__ void __launch_bounds__(256) mt_words_sub_kernel(const unsigned* __restrict__ windows, int U, int u0,
+                                                           unsigned* __restrict__ out, long long word_stride) {
+  __shared__ unsigned mt[MT_N];
+  const int t = threadIdx.x;
+  const unsigned* w = windows + ((long long)blockIdx.y * U + u0 + blockIdx.x) * MT_N;
+  out += (long long)blockIdx.y * word_stride + (long long)blockIdx.x * MT_JUMP_SUB_BLOCKS * MT_N;
+  for (int i = t; i < MT_N; i += 256) mt[i] = w[i];
+  __syncthreads();
+  for (int b = 0; b < MT_JUMP_SUB_BLOCKS; ++b) {
+    unsigned v = 0;
+    if (t < 227) v = mt_mix(mt[t], mt[t + 1], mt[t + MT_M]);
+    __syncthreads();
+    if (t < 227) mt[t] = v;
+    __syncthreads();
+    if (t < 227) v = mt_mix(mt[t + 227], mt[t + 228], mt[t]);
+    __syncthreads();
+    if (t < 227) mt[t + 227] = v;
+    __syncthreads();
+    if (t < 170) {
+      int k = t + 454;
+      v = mt_mix(mt[k], mt[(k + 1) % MT_N], mt[k - 227]);
+    }
+    __syncthreads();
+    if (t < 170) mt[t + 454] = v;
+    __syncthreads();
+    unsigned* o = out + (long long)b * MT_N;
+    for (int i = t; i < MT_N; i += 256) o[i] = mt_temper(mt[i]);
+  }
 }
 
 __device__ __forceinline__ bool polar_attempt(const unsigned* __restrict__ w, long long i, double& x1, double& x2, double& r2) {
@@ -177,6 +259,9 @@ __global__ void rng_guard_kernel(const long long* __restrict__ running, long lon
 struct RngScratch {
   int* flag = nullptr;
   unsigned* state = nullptr;
+  unsigned* polys = nullptr;     // device copy of MT_JUMP_POLY
+  unsigned* windows = nullptr;   // [batch][U][624] sub-stream windows of the current fields
+  long long cap_windows = 0;
   unsigned* words = nullptr;
   unsigned* counts = nullptr;
   long long* offsets = nullptr;
@@ -197,6 +282,8 @@ void sww_rng_destroy(sww_ctx* c) {
   if (!r) return;
   cudaFree(r->flag);
   cudaFree(r->state);
+  cudaFree(r->polys);
+  cudaFree(r->windows);
   cudaFree(r->words);
   cudaFree(r->counts);
   cudaFree(r->offsets);
@@ -217,6 +304,8 @@ static int rng_reserve(RngScratch& g_rng, long long attempts, int batch) {
     SWW_CUDA(cudaMalloc(&g_rng.running, RNG_MAX_BATCH * sizeof(long long)));
     SWW_CUDA(cudaMalloc(&g_rng.flag, sizeof(int)));
     SWW_CUDA(cudaMemset(g_rng.flag, 0, sizeof(int)));
+    SWW_CUDA(cudaMalloc(&g_rng.polys, sizeof(MT_JUMP_POLY)));
+    SWW_CUDA(cudaMemcpy(g_rng.polys, MT_JUMP_POLY, sizeof(MT_JUMP_POLY), cudaMemcpyHostToDevice));
   }
   if (batch < g_rng.cap_batch) batch = g_rng.cap_batch;
   long long nb = (attempts + PA_BLOCK - 1) / PA_BLOCK;
@@ -275,9 +364,40 @@ extern "C" int sww_grf_legacy_batch(sww_ctx* c, const uint32_t* seeds, int nseed
   long long chunks = (long long)ceil((double)need_pairs / ((double)att_per_chunk * p - 8.0 * sd));
   long long done_pairs = 0;
   const bool async = stream_ != 0;   // side stream: no host synchronisation, the shortfall guard is a device flag (sww_grf_check)
+  // jump-ahead: every chunk is generated by `subs` CTAs per seed instead of one (SWW_RNG_JUMP=0: the sequential walker)
+  const char* ej = getenv("SWW_RNG_JUMP");
+  const int subs = (int)(blocks_per_chunk / MT_JUMP_SUB_BLOCKS);
+  const long long spare = async ? 0 : 1;                        // the synchronous path may ask for one more chunk
+  const long long U = (chunks + spare) * subs;
+  const bool jump = !(ej && ej[0] == '0') && U < (1LL << MT_JUMP_K);
+  if (jump) {
+    if (g_rng.cap_windows < U * nseeds) {
+      if (g_rng.windows) cudaFree(g_rng.windows);
+      g_rng.windows = nullptr;
+      g_rng.cap_windows = 0;
+      SWW_CUDA(cudaMalloc(&g_rng.windows, (size_t)U * RNG_MAX_BATCH * MT_N * sizeof(unsigned)));
+      g_rng.cap_windows = U * RNG_MAX_BATCH;
+    }
+    const size_t jsm = (size_t)(MT_JUMP_X + MT_N) * sizeof(unsigned);
+    SWW_CUDA(cudaFuncSetAttribute(mt_jump_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
+    mt_replicate_kernel<<<dim3((unsigned)U, nseeds), 256, 0, c->stream>>>(g_rng.state, g_rng.windows, (int)U);
+    c->n_own++;
+    for (int k = 0; (1LL << k) < U; ++k) {
+      mt_jump_round_kernel<<<dim3((unsigned)U, nseeds), 640, jsm, c->stream>>>(g_rng.windows, (int)U, k, g_rng.polys);
+      c->n_own++;
+    }
+    SWW_CUDA(cudaGetLastError());
+  }
+  long long chunk_no = 0;
   while (done_pairs < need_pairs) {
-    for (long long k = 0; k < chunks; ++k) {
-      mt_words_kernel<<<nseeds, 256, 0, c->stream>>>(g_rng.state, g_rng.words, blocks_per_chunk, g_rng.word_stride);
+    for (long long k = 0; k < chunks; ++k, ++chunk_no) {
+      if (jump) {
+        SWW_REQUIRE((chunk_no + 1) * subs <= U, "device RNG: more chunks needed than sub-stream windows were prepared");
+        mt_words_sub_kernel<<<dim3(subs, nseeds), 256, 0, c->stream>>>(g_rng.windows, (int)U, (int)(chunk_no * subs), g_rng.words,
+                                                                      g_rng.word_stride);
+      } else {
+        mt_words_kernel<<<nseeds, 256, 0, c->stream>>>(g_rng.state, g_rng.words, blocks_per_chunk, g_rng.word_stride);
+      }
       polar_count_kernel<<<dim3(nb, nseeds), PA_BLOCK, 0, c->stream>>>(g_rng.words, att_per_chunk, g_rng.counts, g_rng.word_stride,
                                                                         g_rng.count_stride);
       scan_counts_kernel<<<nseeds, 1024, 0, c->stream>>>(g_rng.counts, g_rng.offsets, nb, g_rng.running, g_rng.count_stride,

@@ -65,3 +65,27 @@ def test_batched_fields_and_pipeline_match_numpy(world):
         for s in seeds:
             assert np.max(np.abs(got[s].cpu().numpy() - ref(s)) / np.maximum(np.abs(ref(s)), 1e-300)) < 1e-14, (batch, s)
     ctx.close()
+
+
+def test_jump_ahead_substreams_are_bit_identical_to_the_sequential_walker(world):
+    """One legacy stream split over 128 CTAs per chunk (MT19937 jump-ahead, csrc/rng.cu) must emit exactly the words the
+    single-CTA walker emits: same field bit for bit, across chunk boundaries and for a batch of seeds."""
+    import os
+    from spectra_without_windows_b200 import engine
+    w = world("toyD")
+    mesh = engine.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
+    ctx = engine.Context(mesh, 0, ("ops",))
+    sigma = np.random.default_rng(4).random((190, 170, 180)) + 0.5      # 5.8e6 values: three chunks of 2.56e6 attempts
+    seeds = [3, 4000000001, 77]
+    fast = [o.cpu().numpy() for o in ctx.grf_legacy_batch(seeds, sigma)]
+    os.environ["SWW_RNG_JUMP"] = "0"
+    try:
+        slow = [o.cpu().numpy() for o in ctx.grf_legacy_batch(seeds, sigma)]
+    finally:
+        del os.environ["SWW_RNG_JUMP"]
+    for a, b in zip(fast, slow):
+        assert np.array_equal(a, b)
+    np.random.seed(77)
+    ref = np.random.normal(loc=0.0, scale=sigma, size=sigma.shape)
+    assert np.max(np.abs(fast[2] - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-14
+    ctx.close()
