@@ -29,7 +29,7 @@ WORKLOADS = {
     "C2": dict(grid=(512, 512, 512), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
                bins=(0.0, 0.41, 0.005, 4)),
     "C5": dict(grid=(1024, 1024, 1024), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
-               bins=(0.0, 0.40, 0.005, 4)),
+               bins=(0.0, 0.40, 0.005, 4), n_mc_job=200),
     "C1F": dict(grid=(128, 128, 128), box=(1000.0, 1000.0, 1000.0), box_center=(0.0, 0.0, 2000.0),
                 bins=(0.0, 0.25, 0.01, 4)),
     # bispectrum Fisher (a step = one PAIR of realisations): 256^3, k in [0,0.11] dk=0.01, l<=4 -> 191 triangles, n_b=573
@@ -394,6 +394,89 @@ def run_bk(args, wl, mesh, rank, world, local, dev):
         dist.destroy_process_group()
 
 
+def run_job(args, wl, mesh, ctx, sig, rank, world, local, dev, big):
+    """The Monte-Carlo job the reference runs as N_mc SLURM tasks + the fold in compute_pk_data.py
+    (pk/compute_pk_randoms.py:135-287 per seed, pk/compute_pk_data.py:227-247): seeds 1..N_mc dealt round-robin to the
+    ranks, every field drawn ON THE DEVICE from numpy's legacy stream (seed = rand_it), Fisher realisations with K in
+    flight, one all-reduce, rank 0 writes the combined fisher-pk / bias-pk files.  The clock starts when the contexts
+    exist and the NCCL communicator is built (the reference's counterpart: interpreter + imports + load_nbar, which it pays
+    per seed) and stops when the files are on disk: first field, loop, all-reduce and writes are all inside."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from spectra_without_windows_b200 import mc_driver
+    N_mc = args.n_mc or wl.get("n_mc_job", 100)
+    K = 1 if big else max(1, min(int(args.inflight), 4))
+    ctxs, streams = mc_driver.make_inflight_contexts(ctx, K, ("pk_fisher",))
+    n_b = ctx.n_b
+    outdir = tempfile.mkdtemp(prefix="sww_job_")
+
+    def one(seed, a, c):
+        return c.pk_fisher(a)
+
+    # untimed warm-up: one realisation per context (kernel attributes, shell order, RNG scratch)
+    mc_driver.pk_device_rng_loop(ctx, [10 ** 6 + rank * 8 + k for k in range(len(ctxs))], sig, one, K, ("pk_fisher",), ctxs, streams)
+    if world > 1:
+        dist.barrier()                     # also builds the NCCL communicator before the clock starts
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    counts0 = [c_.launch_counts() for c_ in ctxs]
+    marks = {}
+    t0 = time.perf_counter()
+    seeds = mc_driver.shard(range(1, N_mc + 1), rank, world)
+    F, q, _ = mc_driver.pk_device_rng_loop(ctx, seeds, sig, one, K, ("pk_fisher",), ctxs, streams, marks)
+    t1 = time.perf_counter()
+    if world > 1:
+        dist.all_reduce(F)
+        dist.all_reduce(q)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    if rank == 0:
+        np.save(os.path.join(outdir, "fisher-pk_job.npy"), (F / N_mc).cpu().numpy())
+        np.save(os.path.join(outdir, "bias-pk_job.npy"), (q / N_mc).cpu().numpy())
+    t3 = time.perf_counter()
+    tt = torch.tensor([t3 - t0, t1 - t0, t2 - t1, t3 - t2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total, t_loop, t_red, t_write = (float(v) for v in tt.tolist())
+    clocks = sampler.stop() if sampler else None
+    counts1 = [c_.launch_counts() for c_ in ctxs]
+    own = sum(c1[0] - c0[0] for c0, c1 in zip(counts0, counts1))
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        M = sum(2 * l + 1 for l in range(0, mesh.lmax + 1, 2))
+        b_alg = 16.0 * mesh.N * n_fft_min(M, n_b)
+        value = N_mc / total
+        achieved = b_alg * value / world / 1e9
+        Fh = np.load(os.path.join(outdir, "fisher-pk_job.npy"))
+        line = {"metric": "pk Fisher MC realisations/s", "mode": "job", "value": value, "unit": "realisations/s", "n_gpus": world,
+                "steps": N_mc, "warmup": len(ctxs), "ms_per_step": total / N_mc * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(workload_config(args.workload, mesh), N_mc=N_mc,
+                               job="seeds 1..N_mc round-robin over the ranks; fields from the device legacy RNG (numpy stream, seed = rand_it)"),
+                "realisations_in_flight": len(ctxs), "row_mesh": list(ctx.row_mesh_shape()) if ctx.row_mesh_shape() else None,
+                "gpu_launches": int(own), "clocks": clocks,
+                "phases_s": {"total": total, "mc_loop": t_loop, "first_field_enqueued": marks.get("first_field_enqueued_s"),
+                             "all_reduce": t_red, "write_combined_files": t_write,
+                             "realisations_on_busiest_rank": int(np.ceil(N_mc / world))},
+                "e2e": {"value": value, "unit": "realisations/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": int((n_b * n_b + n_b) * 8 / max(1, N_mc)),
+                        "note": "the job IS the end-to-end path: fields are generated on the device (no host RNG, no H2D), the result leaves once"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "whole job under the SURVEY 8d convention (16 N bytes x (2M+1+2 n_b) transforms per realisation), per GPU"},
+                "check": {"fisher_trace": float(np.trace(Fh)), "fisher_finite": bool(np.all(np.isfinite(Fh)))}}
+        print(json.dumps(line))
+    import shutil
+    shutil.rmtree(outdir, ignore_errors=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,6 +491,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="after the timed region, one extra realisation with CUDA-event profiling per kernel family")
+    ap.add_argument("--mode", default="step", choices=["step", "job"],
+                    help="job: the whole Monte-Carlo job of the workload (N_mc realisations SHARDED over the ranks = strong scaling): "
+                         "fields drawn on the device from numpy's legacy stream, accumulation, all-reduce, combined files written")
+    ap.add_argument("--n-mc", type=int, default=0, help="job mode: realisations of the job (default: 100 for C2, 200 for C5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -450,6 +537,8 @@ def main():
     del rax_d, nbar_r
     n_b = ctx.n_b
     sig = torch.sqrt(nbar_A)
+    if args.mode == "job":
+        return run_job(args, wl, mesh, ctx, sig, rank, world, local, dev, big)
 
     # synthetic Gaussian fields a ~ N(0, nbar_A) (pk/compute_pk_randoms.py:139-140), one per realisation;
     # each rank draws its own independent realisations (seed offset by rank)

@@ -45,7 +45,9 @@ def run_world(name, fp64=True, include_pix=False, rand_nbar=False):
             out["pk_nfft"] = np.asarray(cnt)
             out["pk_qbar_%d" % r] = np.load(glob.glob(mc + "*%d_FKP_pk_q-bar_a_*.npy" % r)[0])
             out["pk_fish_%d" % r] = np.load(glob.glob(mc + "*%d_FKP_pk_fish_a_*.npy" % r)[0])
-        rh.run_script("pk/compute_pk_data.py", 1, p)
+        cap = []
+        rh.run_script("pk/compute_pk_data.py", 1, p, capture=cap)
+        out["pk_p_f64"] = cap[-1]                      # p_alpha in full precision (pk/compute_pk_data.py:250)
         out["pk_bias_comb"] = np.load(glob.glob(od + "bias-pk_*.npy")[0])
         out["pk_fish_comb"] = np.load(glob.glob(od + "fisher-pk_*.npy")[0])
         f = glob.glob(od + "pk_*.txt")[0]
@@ -67,7 +69,9 @@ def run_world(name, fp64=True, include_pix=False, rand_nbar=False):
         out["bk_g_plane"] = np.real(ga[:, :, :, :, 3])
         out["bk_tg_plane"] = np.real(tga[:, :, :, :, 3])
         out["bk_g_maximag"] = np.asarray(np.abs(ga.imag).max() / np.abs(ga.real).max())
-        rh.run_script("bk/compute_bk_data.py", 1, p)
+        cap = []
+        rh.run_script("bk/compute_bk_data.py", 1, p, capture=cap)
+        out["bk_p_f64"] = cap[-1]                      # p_alpha in full precision (bk/compute_bk_data.py:417)
         out["bk_fish_comb"] = np.load(glob.glob(od + "fisher-bk_*.npy")[0])
         f = glob.glob(od + "bk_*.txt")[0]
         out["bk_txt_name"] = np.asarray(os.path.basename(f))

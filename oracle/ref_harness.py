@@ -202,12 +202,25 @@ def bind_world(world, fp64=True):
     return ou, cp
 
 
-def run_script(script_rel, int_arg, paramfile, quiet=True):
-    """runpy one of the four reference scripts, verbatim.  Returns (n_fwd, n_inv) FFT counts."""
+def run_script(script_rel, int_arg, paramfile, quiet=True, capture=None):
+    """runpy one of the four reference scripts, verbatim.  Returns (n_fwd, n_inv) FFT counts.
+    `capture` (a list) receives every 1-D result of np.inner / np.matmul during the run: the FP64 p_alpha vectors of
+    pk/compute_pk_data.py:250 and bk/compute_bk_data.py:417, which the scripts only write as '%.8e' text."""
     _state["nfft"] = [0, 0]
     argv = sys.argv
     sys.argv = [REF + "/" + script_rel, str(int_arg), paramfile]
     out = sys.stdout
+    import numpy as _np
+    saved = (_np.inner, _np.matmul)
+    if capture is not None:
+        def _wrap(fn):
+            def f(*a, **k):
+                r = fn(*a, **k)
+                if getattr(r, "ndim", 0) == 1:
+                    capture.append(_np.array(r, dtype=_np.float64, copy=True))
+                return r
+            return f
+        _np.inner, _np.matmul = _wrap(saved[0]), _wrap(saved[1])
     try:
         if quiet:
             sys.stdout = open(os.devnull, "w")
@@ -216,6 +229,7 @@ def run_script(script_rel, int_arg, paramfile, quiet=True):
         except SystemExit:
             pass
     finally:
+        _np.inner, _np.matmul = saved
         if quiet:
             sys.stdout.close()
         sys.stdout = out

@@ -79,6 +79,54 @@ def run_mc(seeds, realisation_fn, zeros_fn, rank=0, world=1, dist=None, prefetch
     return sums, len(mine)
 
 
+def make_inflight_contexts(ctx, inflight, pipe):
+    """K contexts on K streams (the first is `ctx` itself), as many as the device memory holds workspaces for."""
+    import torch
+    torch.cuda.synchronize()
+    footprint = torch.cuda.memory_allocated()
+    free_b, _ = torch.cuda.mem_get_info()
+    K = max(1, min(inflight, 4, 1 + int((free_b - (12 << 30)) // max(1, footprint))))
+    ctxs, streams = [ctx], [ctx.stream]
+    for k in range(1, K):
+        st = torch.cuda.Stream()
+        ctxs.append(ctx.clone_for_stream(st, pipe))
+        streams.append(st)
+    torch.cuda.synchronize()
+    return ctxs, streams
+
+
+def pk_device_rng_loop(ctx, seeds, sig_dev, one, inflight, pipe, ctxs=None, streams=None, marks=None):
+    """The P_l(k) Monte-Carlo loop of one rank with device-generated fields: batch j+1 is generated on a side stream while
+    the Fisher kernels of batch j run; K contexts on K streams keep K realisations in flight.  `one(seed, field, ctx)`
+    -> (F, q).  Returns (sum F, sum q, time the loop started); `marks` (dict) receives host time stamps of the phases."""
+    import time
+    import torch
+    if ctxs is None:
+        ctxs, streams = make_inflight_contexts(ctx, inflight, pipe)
+    K = len(ctxs)
+    n_b = ctx.n_b
+    Fk = [ctx.zeros((n_b, n_b)) for _ in range(K)]
+    qk = [ctx.zeros((n_b,)) for _ in range(K)]
+    torch.cuda.synchronize()
+    t_loop = time.time()      # the extra contexts are set-up, like the first one
+    for i, (seed, a) in enumerate(ctx.field_pipeline(seeds, sig_dev, consumers=streams)):
+        k = i % K
+        if i == 0 and marks is not None:
+            marks["first_field_enqueued_s"] = time.time() - t_loop
+        with torch.cuda.stream(streams[k]):
+            Fi, qi = one(seed, a, ctxs[k])
+            Fk[k] += Fi
+            qk[k] += qi
+    torch.cuda.synchronize()
+    if marks is not None:
+        marks["loop_s"] = time.time() - t_loop
+    F, q = Fk[0], qk[0]
+    for k in range(1, K):
+        F += Fk[k]
+        q += qk[k]
+    return F, q, t_loop
+
+
 def main(argv):
     import torch
     import torch.distributed as dist
@@ -142,34 +190,7 @@ def main(argv):
             (F, q), n = run_mc(range(1, P.N_mc + 1), one, lambda: (ctx.zeros((n_b, n_b)), ctx.zeros((n_b,))), rank, world,
                                dist if world > 1 else None, prefetch_fn=grf)
         else:
-            # device RNG: batch j+1 is generated on a side stream while the Fisher kernels of batch j run; K contexts
-            # on K streams keep K realisations in flight (as many as the device memory holds workspaces for)
-            torch.cuda.synchronize()
-            footprint = torch.cuda.memory_allocated()
-            free_b, _ = torch.cuda.mem_get_info()
-            K = max(1, min(inflight, 4, 1 + int((free_b - (12 << 30)) // max(1, footprint))))
-            if P.wtype == 1:
-                K = 1      # the conjugate-gradient solver synchronises with the host every iteration
-            ctxs, streams = [ctx], [ctx.stream]
-            for k in range(1, K):
-                st = torch.cuda.Stream()
-                ctxs.append(ctx.clone_for_stream(st, pipe))
-                streams.append(st)
-            Fk = [ctx.zeros((n_b, n_b)) for _ in range(K)]
-            qk = [ctx.zeros((n_b,)) for _ in range(K)]
-            torch.cuda.synchronize()
-            t_loop = time.time()      # the extra contexts are set-up, like the first one
-            for i, (seed, a) in enumerate(ctx.field_pipeline(shard(range(1, P.N_mc + 1), rank, world), sig_dev, consumers=streams)):
-                k = i % K
-                with torch.cuda.stream(streams[k]):
-                    Fi, qi = one(seed, a, ctxs[k])
-                    Fk[k] += Fi
-                    qk[k] += qi
-            torch.cuda.synchronize()
-            F, q = Fk[0], qk[0]
-            for k in range(1, K):
-                F += Fk[k]
-                q += qk[k]
+            F, q, t_loop = pk_device_rng_loop(ctx, shard(range(1, P.N_mc + 1), rank, world), sig_dev, one, inflight if P.wtype == 0 else 1, pipe)
             reduce_sums([F, q], world > 1, dist if world > 1 else None)
         if rank == 0:
             np.save(P.outdir + "fisher-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (F / P.N_mc).cpu().numpy())

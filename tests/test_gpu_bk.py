@@ -84,3 +84,4 @@ def test_bk_fisher_pair_and_data(name, world, golden, eng):
     assert relerr(qa, q_o) < TOL
     p = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qa)
     assert relerr(p, g["bk_p"][:, 3:].T.ravel()) < 2e-8     # '%.8e' text
+    assert relerr(p, g["bk_p_f64"]) < 1e-9                  # the script's FP64 p_alpha (bk/compute_bk_data.py:417)

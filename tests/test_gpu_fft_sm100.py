@@ -105,6 +105,7 @@ def test_bk_pipelines_on_fused_chains(eng, world, golden):
     qa = np.concatenate([q[:, l] / D[l * nt:(l + 1) * nt] for l in range(mesh.n_l)])
     p = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qa)
     assert relerr(p, g["bk_p"][:, 3:].T.ravel()) < 2e-8
+    assert relerr(p, g["bk_p_f64"]) < 1e-9
     ctx.close()
 
 

@@ -38,6 +38,7 @@ def test_pipelines(variant, world, golden):
             q = ctx.pk_data_q(diff).cpu().numpy()
             p = np.inner(np.linalg.inv(g["pk_fish_comb"]), q - g["pk_bias_comb"])
             assert relerr(p, g["pk_p"][:, 1:].T.ravel()) < 2e-8
+            assert relerr(p, g["pk_p_f64"]) < 1e-9
         else:
             F, (gA, tgA, gB, tgB) = ctx.bk_fisher_pair(S.grf(2), S.grf(3))
             assert relerr(F.cpu().numpy(), g["bk_fish_1"]) < TOL
@@ -52,6 +53,7 @@ def test_pipelines(variant, world, golden):
             qa = np.concatenate([q[:, l] / D[l * nt:(l + 1) * nt] for l in range(mesh.n_l)])
             p = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qa)
             assert relerr(p, g["bk_p"][:, 3:].T.ravel()) < 2e-8
+            assert relerr(p, g["bk_p_f64"]) < 1e-9
         ctx.close()
 
 

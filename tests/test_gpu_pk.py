@@ -118,6 +118,7 @@ def test_paint_and_pk_data(name, world, golden, eng):
     assert relerr(q, g["pk_q"]) < TOL
     p = np.inner(np.linalg.inv(g["pk_fish_comb"]), q - g["pk_bias_comb"])
     assert relerr(p, g["pk_p"][:, 1:].T.ravel()) < 2e-8     # '%.8e' text
+    assert relerr(p, g["pk_p_f64"]) < 1e-9                  # the script's FP64 p_alpha (pk/compute_pk_data.py:250)
 
 
 def test_paint_edge_cases(world, eng):

@@ -39,6 +39,7 @@ def test_paint_and_pk_data(name, world, golden):
     p_txt = g["pk_p"][:, 1:].T.ravel()           # text rows are k | P0 P2 P4 -> alpha = l*n_k + a
     assert p.size == n_k * S.n_l
     assert relerr(p, p_txt) < 2e-8               # limited by the '%.8e' text format
+    assert relerr(p, g["pk_p_f64"]) < 1e-10     # the script's own FP64 p_alpha (pk/compute_pk_data.py:250)
 
 
 @pytest.mark.parametrize("name", WORLDS)
@@ -70,6 +71,7 @@ def test_bk_fisher_and_data(name, world, golden):
     p_txt = g["bk_p"][:, 3:].T.ravel()
     assert p.size == nt * S.n_l
     assert relerr(p, p_txt) < 2e-8
+    assert relerr(p, g["bk_p_f64"]) < 1e-9      # the script's own FP64 p_alpha (bk/compute_bk_data.py:417)
 
 
 @pytest.mark.parametrize("name", WORLDS)
@@ -107,12 +109,14 @@ def test_param_booleans_match_reference_scripts(variant, world, golden):
     q = orc.pk_data_q(S, diff)
     p = orc.pk_solve(g["pk_fish_comb"], q, g["pk_bias_comb"])
     assert relerr(p, g["pk_p"][:, 1:].T.ravel()) < 2e-8
+    assert relerr(p, g["pk_p_f64"]) < 1e-10
     Sb = _variant_setup(w, "bk", variant)
     F, (gA, tgA), (gB, tgB) = orc.bk_fisher_pair(Sb, Sb.grf(2), Sb.grf(3), return_g=True)
     assert relerr(F, g["bk_fish_1"]) < 1e-10
     qb = orc.bk_data_q(Sb, diff, mc_maps=[(gA, tgA), (gB, tgB)], N_mc=2)
     pb = np.matmul(np.linalg.inv(g["bk_fish_comb"]), qb)
     assert relerr(pb, g["bk_p"][:, 3:].T.ravel()) < 2e-8
+    assert relerr(pb, g["bk_p_f64"]) < 1e-9
 
 
 # ---- maximum-likelihood weights (src/covariances_pk.py:10-95, 222-327): restatement vs reference functions
