@@ -39,6 +39,9 @@ WORKLOADS = {
     # g-maps + 3-field term + the 1-field term over N_mc = 10 resident bias simulations
     "C3": dict(grid=(256, 256, 256), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
                bins=(0.0, 0.11, 0.01, 2), bk=True, bk_data=True, n_mc=10),
+    # the Gram's comparison point: cuBLAS DGEMM on [573 x K] . [K x 573] (K = 2^22 cells of the 256^3 maps) against gram_dmma_kernel
+    "DGEMM": dict(grid=(256, 256, 256), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
+                  bins=(0.0, 0.11, 0.01, 4), bk=True, dgemm=True),
     "C4S": dict(grid=(128, 128, 128), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
                 bins=(0.0, 0.11, 0.01, 2), bk=True),
     # pk data path (paint + q_alpha): config C1 of SURVEY 8d; a step = one catalogue
@@ -373,13 +376,56 @@ def run_bk(args, wl, mesh, rank, world, local, dev):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
     maps = maps[0]
+    # ---- end to end through the public call with HOST buffers: both fields H2D from pinned memory, F D2H, every pair
+    e2e = None
+    if not args.no_e2e:
+        hA, hB = aA.cpu().pin_memory(), aB.cpu().pin_memory()
+        dA, dB = torch.empty_like(aA), torch.empty_like(aB)
+        F_host = torch.empty((n_b, n_b), dtype=torch.float64).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            dA.copy_(hA, non_blocking=True)
+            dB.copy_(hB, non_blocking=True)
+            F, maps = ctx.bk_fisher_pair(dA, dB, maps)
+            F_host.copy_(F, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        e2e = {"value": 2.0 * world * args.steps / float(tdt.item()), "unit": "realisations/s", "h2d_bytes_per_step": int(2 * mesh.N * 8),
+               "d2h_bytes_per_step": int(n_b * n_b * 8), "note": "two fields H2D from pinned memory and F D2H per pair; host RNG not included"}
+        del hA, hB, dA, dB
     prof = None
     if rank == 0:
+        fft_before = ctx.launch_counts()[1]
         ctx.profile(True)
         ctx.bk_fisher_pair(aA, aB, maps)
         prof = {k: {"launches": n, "ms": round(m_, 3)} for k, (n, m_) in ctx.profile_report().items()}
         ctx.profile(False)
+        fft_pair = ctx.launch_counts()[1] - fft_before
         value = 2.0 * world * args.steps / (ms * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # B_alg = 16 N x N_FFT,min per pair (8 628 transforms for n_k = 11, lmax = 4, 191 triangles) + the Gram flops
+        nfft_min = 8628 if (n_b == 573 and mesh.n_k == 11) else int(fft_pair)
+        b_alg = 16.0 * mesh.N * nfft_min
+        achieved = b_alg * (world * args.steps / (ms * 1e-3)) / world / 1e9
+        gram_ms = prof.get("gram.dmma f64", {}).get("ms")
+        gram_flop = 2.0 * n_b * n_b * mesh.N
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                "kernel": "whole pair under the SURVEY 8d convention: 16 N bytes x %d transforms (the Gram's %.3g flop are extra work, "
+                          "not counted as bytes)" % (nfft_min, gram_flop),
+                "transforms_performed_per_pair": int(fft_pair),
+                "gram": {"flop_full": gram_flop, "flop_computed_upper_trapezoid": gram_flop * (n_b + 1) / (2.0 * n_b), "ms": gram_ms,
+                         "tflops_useful_full_equivalent": (gram_flop / (gram_ms * 1e-3) / 1e12) if gram_ms else None,
+                         "compare": "bench.py --workload DGEMM times cuBLAS DGEMM and this kernel on the same [n_b x K] shapes"}}
         line = {"metric": "bk Fisher MC realisations/s", "value": value, "unit": "realisations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -387,11 +433,60 @@ def run_bk(args, wl, mesh, rank, world, local, dev):
                            % (args.workload, "x".join(str(int(g)) for g in mesh.grid), mesh.k_min, mesh.k_max, mesh.dk, mesh.lmax, ctx.n_tri, n_b),
                            "l2": "inputs>L2"}, "pairs_in_flight": K,
                 "fft_backend": "sm100a-passes" if ctx.fft_backend == 1 else "cufft",
-                "gpu_launches": int(own1 - own0), "clocks": clocks, "profile_one_pair": prof,
+                "gpu_launches": int(own1 - own0), "clocks": clocks, "e2e": e2e, "roofline": roof, "profile_one_pair": prof,
                 "gram_flop_per_pair": 2.0 * n_b * n_b * mesh.N}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle.ref_arm import bk_pair_sample
+                line["cpu_baseline"] = bk_pair_sample(tuple(int(g) for g in mesh.grid), n_b, mesh.n_l, mesh.n_k)
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_dgemm(args, wl, mesh, rank, world, local, dev):
+    """FP64 Gram C = A B^T with A, B [n_b x K]: this repo's DMMA kernel (sww_gram_f64, csrc/gram.cu) against cuBLAS DGEMM
+    (torch.matmul) on the same buffers -- the measured FP64 matrix throughput of the box, and the comparison SURVEY K6 asks for
+    (bk/compute_bk_randoms.py:489-497 is the contraction)."""
+    import torch
+    from spectra_without_windows_b200 import engine
+    ctx = engine.Context(mesh, local, ("ops",))
+    n_b, K = 573, 1 << 22
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    A = torch.randn((n_b, K), generator=gen, device=dev, dtype=torch.float64)
+    B = torch.randn((n_b, K), generator=gen, device=dev, dtype=torch.float64)
+    flop = 2.0 * n_b * n_b * K
+
+    def timeit(fn):
+        for _ in range(max(3, args.warmup)):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    out = ctx.zeros((n_b, n_b))
+    ms_own = timeit(lambda: ctx.gram(A, B, out=out))
+    ms_blas = timeit(lambda: torch.matmul(A, B.T))
+    ref = torch.matmul(A, B.T)
+    err = float((ctx.gram(A, B) - ref).abs().max() / ref.abs().max())
+    Bsq = None
+    line = {"metric": "FP64 Gram TFLOP/s", "value": flop / (ms_own * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_own, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "DGEMM: C[573 x 573] = A[573 x 2^22] B^T, FP64; inputs 2 x 19 GB > L2"},
+            "gram_dmma_kernel": {"ms": ms_own, "tflops": flop / (ms_own * 1e-3) / 1e12,
+                                 "note": "computes the upper trapezoid only when A is B's partner in the Fisher assembly; here the full product"},
+            "cublas_dgemm": {"ms": ms_blas, "tflops": flop / (ms_blas * 1e-3) / 1e12, "api": "torch.matmul (cuBLAS)"},
+            "max_rel_diff": err}
+    print(json.dumps(line))
 
 
 def run_job(args, wl, mesh, ctx, sig, rank, world, local, dev, big):
@@ -518,6 +613,8 @@ def main():
     if big:
         os.environ["SWW_TIGHT_WS"] = "1"     # 1024^3: size the workspace for the fused chains only
     mesh = engine.Mesh(wl["box"], wl["grid"], wl["box_center"], *wl["bins"])
+    if wl.get("dgemm"):
+        return run_dgemm(args, wl, mesh, rank, world, local, dev)
     if wl.get("bk_data"):
         return run_bk_data(args, wl, mesh, rank, world, local, dev)
     if wl.get("bk"):

@@ -198,3 +198,43 @@ class PkFisherRefArm:
             os.rmdir(self.tmpdir)
         except OSError:
             pass
+
+
+def bk_pair_sample(grid, n_b, n_l, n_k, threads=None, n_rep=3):
+    """CPU baseline of one bispectrum Fisher PAIR (bk/compute_bk_randoms.py:222-517), bounded sample: the three operations
+    that dominate the reference -- a complex64 3-D FFT (pyfftw at src/opt_utilities.py:502-555; here torch CPU / MKL on all
+    threads), an np.save of a phi map (:396-412) and an np.load + product-sum of two maps (load_row, :477-501) -- timed on the
+    full mesh and multiplied by the reference's own counts for n_k = 11, lmax = 4: 22 535 transforms,
+    4 n_b saved maps, n_b (n_b + 1) loaded pairs.  Element-wise work between the transforms is NOT counted, so this is an
+    upper bound on the reference's speed."""
+    import torch
+    threads = int(threads or os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    x = torch.randn(tuple(grid), dtype=torch.float64)
+    xc = x.to(torch.complex64)
+    torch.fft.fftn(xc)
+    t0 = time.perf_counter()
+    for _ in range(n_rep):
+        torch.fft.fftn(xc)
+    t_fft = (time.perf_counter() - t0) / n_rep
+    d = tempfile.mkdtemp(prefix="sww_bkarm_")
+    fn = os.path.join(d, "phi.npy")
+    t0 = time.perf_counter()
+    for _ in range(n_rep):
+        np.save(fn, x.numpy())
+    t_save = (time.perf_counter() - t0) / n_rep
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(n_rep):
+        acc += float(torch.sum(torch.from_numpy(np.load(fn)) * x))
+    t_dot = (time.perf_counter() - t0) / n_rep
+    os.remove(fn)
+    os.rmdir(d)
+    # counts of SURVEY.md 3.3 scale with the number of bins: 22 535 transforms at n_b = 573 (n_k = 11, lmax = 4)
+    n_fft = 22535.0 * n_b / 573.0
+    T = n_fft * t_fft + 4.0 * n_b * t_save + n_b * (n_b + 1.0) * t_dot
+    return {"value": 2.0 / T, "unit": "realisations/s", "cores": threads, "kind": "port",
+            "sample": "one complex64 FFT, one np.save and one np.load + product-sum of full %s maps (torch CPU, %d threads), times the "
+                      "reference's counts per pair: %.0f transforms, %d saved maps, %d loaded pairs; element-wise work not counted "
+                      "(upper bound on the reference's speed)" % ("x".join(str(g) for g in grid), threads, n_fft, 4 * n_b, n_b * (n_b + 1)),
+            "parts_s": {"t_fft": t_fft, "t_save": t_save, "t_load_dot": t_dot, "seconds_per_pair": T}}
