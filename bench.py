@@ -38,7 +38,7 @@ WORKLOADS = {
     # bispectrum data path (config 3 of BASELINE.json): 256^3, k in [0,0.11] dk=0.01, l = 0,2; a step = one data catalogue's
     # g-maps + 3-field term + the 1-field term over N_mc = 10 resident bias simulations
     "C3": dict(grid=(256, 256, 256), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
-               bins=(0.0, 0.11, 0.01, 2), bk=True, bk_data=True, n_mc=10),
+               bins=(0.0, 0.11, 0.01, 2), bk=True, bk_data=True, n_mc=100),
     # the Gram's comparison point: cuBLAS DGEMM on [573 x K] . [K x 573] (K = 2^22 cells of the 256^3 maps) against gram_dmma_kernel
     "DGEMM": dict(grid=(256, 256, 256), box=(1750.0, 3220.0, 1830.0), box_center=(1200.0, 0.0, 0.0),
                   bins=(0.0, 0.11, 0.01, 4), bk=True, dgemm=True),
@@ -252,15 +252,19 @@ def run_bk_data(args, wl, mesh, rank, world, local, dev):
     diff = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * torch.sqrt(nbar)
     aA = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig
     aB = torch.randn(mesh.shape, generator=gen, device=dev, dtype=torch.float64) * sig
-    _, (gA, tgA, gB, tgB) = ctx.bk_fisher_pair(aA, aB)
-    n_mc = wl["n_mc"]
+    n_mc = args.n_mc or wl["n_mc"]
+    del aA, aB
 
     def step():
+        """One catalogue: its g-maps, the 3-field sums, and the 1-field term over N_mc bias simulations whose Gaussian
+        fields (numpy legacy stream, seeds 2..N_mc+1 like bk/compute_bk_data.py:371) and g / g~ maps are produced on the
+        device and consumed straight away -- the in-memory hand-off of `mc_driver bk --data` without the Fisher pairs."""
         gd = ctx.bk_gmaps(diff, data=True)
         q = ctx.bk_q3(gd)
-        for i in range(n_mc // 2):
-            ctx.bk_q1_accumulate(gd, gA, tgA, n_mc, q)
-            ctx.bk_q1_accumulate(gd, gB, tgB, n_mc, q)
+        for ii in range(2, n_mc + 2):
+            a_mc = ctx.grf_legacy(ii, sig)
+            g_mc, tg_mc = ctx.bk_gmaps(a_mc)
+            ctx.bk_q1_accumulate(gd, g_mc, tg_mc, n_mc, q)
         return q
 
     for _ in range(args.warmup):
@@ -281,12 +285,30 @@ def run_bk_data(args, wl, mesh, rank, world, local, dev):
     step()
     prof = {k: {"launches": n, "ms": round(m_, 3)} for k, (n, m_) in ctx.profile_report().items()}
     ctx.profile(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # 16 N per transform of the catalogue (M + n_l n_k + ...) + 16 N n_l n_k per bias simulation (its g and g~ maps read once)
+    M = sum(2 * l + 1 for l in range(0, mesh.lmax + 1, 2))
+    nfft = M + mesh.n_l * mesh.n_k
+    b_alg = 16.0 * mesh.N * nfft + 16.0 * mesh.N * mesh.n_l * mesh.n_k * n_mc
+    achieved = b_alg * (args.steps / (ms * 1e-3)) / 1e9
+    g3 = prof.get("gram3.dmma f64", {}).get("ms")
+    flop3 = 3.0 * 2.0 * mesh.n_k * mesh.n_k * mesh.n_l * mesh.n_k * mesh.N * n_mc      # three trilinear Grams per simulation
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "whole catalogue under the SURVEY 8d convention (16 N x %d transforms + 16 N n_l n_k N_mc map bytes); the 1-field "
+                      "term is FP64-tensor work (trilinear Gram), %.3g flop" % (nfft, flop3),
+            "gram3": {"ms": g3, "tflops": (flop3 / (g3 * 1e-3) / 1e12) if g3 else None}}
     print(json.dumps({"metric": "bk data catalogues/s", "value": args.steps / (ms * 1e-3), "unit": "catalogues/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": "C3: compute_bk_data (g-maps, 3-field term, 1-field term over N_mc=%d resident bias simulations), "
-                                 "mesh 256^3, k in [0,0.11] dk=0.01 l=0,2, %d triangles" % (n_mc, ctx.n_tri), "l2": "inputs>L2"},
-                      "gpu_launches": int(own1 - own0), "clocks": clocks, "profile_one_step": prof,
+                      "config": {"workload": "C3: compute_bk_data (g-maps, 3-field term, 1-field term over N_mc=%d bias simulations generated "
+                                 "and consumed on the device), mesh 256^3, k in [0,0.11] dk=0.01 l=0,2, %d triangles" % (n_mc, ctx.n_tri),
+                                 "l2": "inputs>L2"},
+                      "gpu_launches": int(own1 - own0), "clocks": clocks, "roofline": roof, "profile_one_step": prof,
                       "q_finite": bool(torch.isfinite(q).all())}))
 
 

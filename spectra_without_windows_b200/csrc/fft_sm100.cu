@@ -243,7 +243,7 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
 pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Pbase, const double2* __restrict__ twg,
-               double2* __restrict__ Qbase, int nb, long long pstride, long long qstride) {
+               double2* __restrict__ Qbase, int nb, long long pstride, long long qstride, int q_tiled) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -276,7 +276,10 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
         int ia = bi + r * (N / RL);
-        Q[row_of<AX>(ia, f, ny) * Kzp + iz0 + cc] = u[s][r];
+        if (q_tiled)   // tile-major Q: [f][z-tile][ia][8], contiguous per item
+          Q[(((long long)f * ztiles + zt) * N + ia) * FFT_TZ + cc] = u[s][r];
+        else
+          Q[row_of<AX>(ia, f, ny) * Kzp + iz0 + cc] = u[s][r];
       }
     }
   }
@@ -286,7 +289,7 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
 pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Rbase, const double2* __restrict__ twg,
-               double2* __restrict__ Pbase, int nb, long long rstride, long long pstride) {
+               double2* __restrict__ Pbase, int nb, long long rstride, long long pstride, int r_tiled) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -305,7 +308,12 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
     const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    fft_first<N, 1, false>(tile, tid, [&](int ia, int cc) { return R[row_of<AX>(ia, ic, ny) * Kzp + iz0 + cc]; });
+    if (r_tiled) {   // tile-major R: this item's tile is one contiguous block [ia][8]
+      const double2* __restrict__ Rt = R + ((long long)ic * ztiles + zt) * N * FFT_TZ;
+      fft_first<N, 1, false>(tile, tid, [&](int ia, int cc) { return Rt[ia * FFT_TZ + cc]; });
+    } else {
+      fft_first<N, 1, false>(tile, tid, [&](int ia, int cc) { return R[row_of<AX>(ia, ic, ny) * Kzp + iz0 + cc]; });
+    }
     FFT_MID(N, 1, false, tile, tw, tid);
     double2 u[16 / RL][RL];
     fft_last<N, 1, false, RL>(tile, tw, tid, u);
@@ -584,6 +592,11 @@ struct ZArgs {
   long long r_stride;    // INV && FWD: nb > 1 transforms nb planes (Q + b*q_stride -> R + b*r_stride) per weight load
   const double* ymaps;   // optional cache [lm-1][N] of Y_lm(r^)
   long long N;
+  // Tile-major intermediates (fused row chain, z16p kernel only): instead of rows [nx*ny][Kzp] the complex planes are laid
+  // out as the 8-column tiles of the adjacent column pass, [f][z-tile][ia][8] with ia along that pass's transform axis
+  // (q_tile / r_tile = 1: x, 2: y, 0: row-major).  The column pass then moves whole tiles as ONE contiguous block
+  // (64 KB at N = 512) and this FP64-bound kernel absorbs the 128-byte pieces.
+  int q_tile, r_tile;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1320,14 +1333,30 @@ pass_z16p_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const 
   const int nfb = A.nb > 1 ? A.nb : 1;
   const int Kz_in = A.Kz_in, Kz_out = A.Kz_out;
   const int in_last = in_len - 1;
+  // element (row, k) of a tile-major plane: ((f * ztiles + k / 8) * n_ax + ia) * 8 + k % 8
+  auto tile_base = [&](long long row_, int axis, int Kzp, long long& zstep) -> long long {
+    const int ix = (int)(row_ / g.ny), iy = (int)(row_ - (long long)ix * g.ny);
+    const int ia = axis == 0 ? ix : iy, f = axis == 0 ? iy : ix, n_ax = axis == 0 ? g.nx : g.ny;
+    zstep = (long long)n_ax * 8;
+    return ((long long)f * (Kzp >> 3) * n_ax + ia) * 8;
+  };
   auto prefetch_rows = [&](const double2* __restrict__ Qbase, long long r0) {
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const double2* src = Qbase + (r0 + rr) * A.Kzp_in;
       double2* row = inw + rr * in_len;
-      for (int k = lane; k < Kz_in; k += 32) {
-        unsigned sa = (unsigned)__cvta_generic_to_shared(row + k);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+      if (A.q_tile > 0) {
+        long long zstep;
+        const double2* src = Qbase + tile_base(r0 + rr, A.q_tile - 1, A.Kzp_in, zstep);
+        for (int k = lane; k < Kz_in; k += 32) {
+          unsigned sa = (unsigned)__cvta_generic_to_shared(row + k);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + (k >> 3) * zstep + (k & 7)));
+        }
+      } else {
+        const double2* src = Qbase + (r0 + rr) * A.Kzp_in;
+        for (int k = lane; k < Kz_in; k += 32) {
+          unsigned sa = (unsigned)__cvta_generic_to_shared(row + k);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+        }
       }
     }
     asm volatile("cp.async.commit_group;\n" ::);
@@ -1337,6 +1366,8 @@ pass_z16p_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const 
   for (; grp < ngroups; grp += gstep) {
     const long long row = grp * 2 + rho;
     const double* __restrict__ wrow = A.wmap + row * g.nz + 2 * b;
+    long long r_zstep = 0;
+    const long long r_off = A.r_tile > 0 ? tile_base(row, A.r_tile - 1, A.Kzp_out, r_zstep) : row * A.Kzp_out;
     // WREG: the weights of the row pair stay in registers for all planes (168 registers, 12 warps / SM); otherwise they are
     // re-read per plane (L2 hits after the first) right before the inverse transform that hides their latency
     double2 wreg[16];
@@ -1403,7 +1434,8 @@ pass_z16p_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const 
       twiddle16_tab<1>(u, tab, b);
       dft16<1>(u);
       // ---- r2c post-processing: T[k] = V[k] postA[k] + conj(V[H-k]) postB[k]; V[H-k] sits in lane 16 - b, register 15 - r
-      double2* __restrict__ dst = A.R + (long long)fb * A.r_stride + row * A.Kzp_out;
+      double2* __restrict__ dst = A.R + (long long)fb * A.r_stride + r_off;
+      const bool r_tiled = A.r_tile > 0;
       const int src_lane = (rho << 4) | ((16 - b) & 15);
 #pragma unroll
       for (int h4 = 0; h4 < 8; h4 += 4) {   // two batches of four outputs: shuffles first, then independent FMA chains
@@ -1424,7 +1456,7 @@ pass_z16p_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const 
           double2 t;
           t.x = v1.x * pa.x - v1.y * pa.y + (v2[q].x * pb.x + v2[q].y * pb.y);
           t.y = v1.x * pa.y + v1.y * pa.x + (v2[q].x * pb.y - v2[q].y * pb.x);
-          if (k < Kz_out) dst[k] = t;
+          if (k < Kz_out) dst[r_tiled ? (k >> 3) * r_zstep + (k & 7) : k] = t;
         }
       }
     }
@@ -1772,21 +1804,22 @@ static int launch_i1(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, 
 }
 template <int N, int AX>
 static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, double2* Qdst, int nb, long long pstride,
-                     long long qstride) {
+                     long long qstride, int q_tiled) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)nF * (Kzp / FFT_TZ) * nb;
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i2_kernel<N, AX>, smem));
-  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride);
+  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride, q_tiled);
   return 0;
 }
 template <int N, int AX>
-static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int nb, long long rstride, long long pstride) {
+static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int nb, long long rstride, long long pstride,
+                     int r_tiled) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)nC * (Kzp / FFT_TZ) * nb;
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_f2_kernel<N, AX>, smem));
-  pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride);
+  pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride, r_tiled);
   return 0;
 }
 template <int N, int AX>
@@ -1834,7 +1867,8 @@ static int axis_len(const Geo& g, int ax) { return ax == 0 ? g.nx : g.ny; }
 
 // inverse column passes: spectrum (box, optional shell filter) -> Q[nx][ny][Kzp]
 static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, const double2* src, int shell,
-                            const GatherArgs* gap = nullptr, int nb = 1, double2* Qdst = nullptr, long long qstride = 0) {
+                            const GatherArgs* gap = nullptr, int nb = 1, double2* Qdst = nullptr, long long qstride = 0,
+                            int q_tiled = 0) {
   if (!Qdst) Qdst = s->Q;
   const int a1 = pl.x_first_fwd ? 1 : 0;   // first inverse axis = the weakly pruned one
   const int a2 = 1 - a1;
@@ -1862,7 +1896,7 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     }
     {
       SWW_PROF(c, a2 == 0 ? "fft.I2 x-inverse" : "fft.I2 y-inverse");
-#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst + (long long)b0 * qstride, nbc, pstride, qstride)
+#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst + (long long)b0 * qstride, nbc, pstride, qstride, q_tiled)
       DISPATCH_AX(n2, a2, CALL)
 #undef CALL
       c->n_own++;
@@ -1874,7 +1908,7 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
 
 // forward column passes: R[nx][ny][Kzp] -> epilogue `mode`
 static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, int mode, F3Args A,
-                            int nb = 1, long long rstride = 0, const F3Args* Ab = nullptr) {
+                            int nb = 1, long long rstride = 0, const F3Args* Ab = nullptr, int r_tiled = 0) {
   const int a1 = pl.x_first_fwd ? 0 : 1;   // first forward axis = the strongly pruned one
   const int a2 = 1 - a1;
   const BoxAxis b1 = a1 == 0 ? pl.bx : pl.by, b2 = a2 == 0 ? pl.bx : pl.by;
@@ -1883,7 +1917,7 @@ static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
   SWW_REQUIRE((size_t)pstride * nb <= s->buf_elems, "forward batch of %d planes does not fit the pass buffer", nb);
   {
     SWW_PROF(c, a1 == 0 ? "fft.F2 x-forward" : "fft.F2 y-forward");
-#define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp, nb, rstride, pstride)
+#define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp, nb, rstride, pstride, r_tiled)
     DISPATCH_AX(n1, a1, CALL)
 #undef CALL
     c->n_own++;
@@ -2016,6 +2050,14 @@ static inline bool env_on(const char* name) {
   return e && e[0] == '1' && e[1] == 0;
 }
 
+// the fused nz = 512 kernel with table-driven pre / post-processing (pass_z16p_fused_kernel) takes this launch
+static bool z16p_takes(const sww_ctx* c, const ZArgs& A) {
+  const char* e = getenv("SWW_Z16_VARIANT");
+  const int v = e ? atoi(e) : 0;
+  return c->g.nz / 2 == Z16_H && A.lm < 0 && A.wmap && A.Kz_out <= 128 && A.Kz_in <= 128 && !env_on("SWW_NO_Z16") &&
+         (c->g.nx * (long long)c->g.ny) % 2 == 0 && (v == 0 || v == 6 || v == 7);
+}
+
 static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   SWW_PROF(c, inv && fwd ? "fft.Z c2r*w*r2c fused" : (inv ? "fft.Z c2r" : "fft.Z r2c"));
   A.ymaps = c->ylm_maps;
@@ -2030,6 +2072,7 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
     SWW_CUDA(cudaGetLastError());
     return 0;
   }
+  SWW_REQUIRE(!(A.q_tile || A.r_tile) || (inv && fwd && z16p_takes(c, A)), "tile-major planes need the fused nz = 512 kernel");
   if (inv && fwd && !ylm && H == Z16_H && A.wmap && A.Kz_out <= 128 && A.Kz_in <= Z16_H + 1 && !no_z16 &&
       (c->g.nx * (long long)c->g.ny) % 2 == 0) {
     SWW_TRY(launch_z16(c, s, A));
@@ -2454,7 +2497,6 @@ int sww_sm100_pk_rows_store(sww_ctx* c, int nrows, const double2* const* F, int 
     ga[b].src = F[b];
     ga[b].shell = shell;
   }
-  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride));
   ZArgs Z = {};
   Z.Q = s->Q;
   Z.Kz_in = Kzi;
@@ -2468,13 +2510,21 @@ int sww_sm100_pk_rows_store(sww_ctx* c, int nrows, const double2* const* F, int 
   Z.nb = nrows;
   Z.q_stride = qstride;
   Z.r_stride = rstride;
+  // tile-major Q and R when the fused nz = 512 kernel runs the z pass: the column passes next to it (second inverse,
+  // first forward) then move each 8-column tile as one contiguous block
+  const char* etl = getenv("SWW_TILE_MAJOR");
+  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {
+    Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
+    Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
+  }
+  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
   SWW_TRY(run_z(c, s, true, true, Z));
   F3Args Ab[SWW_MAX_L] = {};
   for (int b = 0; b < nrows; ++b) {
     Ab[b].perm = s->d_perm;
     Ab[b].sorted_dst = Us_rows + (long long)b * s->S;
   }
-  return run_forward_cols(c, s, plo, Kzo, Kzpo, 3, Ab[0], nrows, rstride, Ab);
+  return run_forward_cols(c, s, plo, Kzo, Kzpo, 3, Ab[0], nrows, rstride, Ab, Z.r_tile);
 }
 
 int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,
@@ -2494,7 +2544,6 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
     ga[b].src = F[b];
     ga[b].shell = shell;
   }
-  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride));
   ZArgs Z = {};
   Z.Q = s->Q;
   Z.Kz_in = Kzi;
@@ -2508,6 +2557,14 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
   Z.nb = nrows;
   Z.q_stride = qstride;
   Z.r_stride = rstride;
+  // tile-major Q and R when the fused nz = 512 kernel runs the z pass: the column passes next to it (second inverse,
+  // first forward) then move each 8-column tile as one contiguous block
+  const char* etl = getenv("SWW_TILE_MAJOR");
+  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {
+    Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
+    Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
+  }
+  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
   SWW_TRY(run_z(c, s, true, true, Z));
   F3Args Ab[SWW_MAX_L] = {};
   for (int b = 0; b < nrows; ++b) {
@@ -2516,5 +2573,5 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
     Ab[b].scale = scale;
     Ab[b].out_row = out_rows[b];
   }
-  return run_forward_cols(c, s, plo, Kzo, Kzpo, 2, Ab[0], nrows, rstride, Ab);
+  return run_forward_cols(c, s, plo, Kzo, Kzpo, 2, Ab[0], nrows, rstride, Ab, Z.r_tile);
 }
