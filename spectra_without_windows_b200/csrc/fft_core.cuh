@@ -152,23 +152,23 @@ FFT_HD void stage_twiddle(int N, int p, int k, const double2* tw, double2* u) {
 // One Stockham stage, radix R, for work item (butterfly bi, column c) of a tile [N][FFT_LDT].
 //   p  : product of the radices of the previous stages (1 for the first stage)
 //   tw : table W_N[j] = exp(-2 pi i j / N), j < N
-template <int R, int DIR>
+template <int R, int DIR, int LDT = FFT_LDT>
 FFT_HD void stage_load(const double2* tile, int N, int p, int bi, int c, const double2* tw, double2* u) {
   const int T = N / R;
   const int k = bi & (p - 1);
 #pragma unroll
-  for (int r = 0; r < R; ++r) u[r] = tile[(bi + r * T) * FFT_LDT + c];
+  for (int r = 0; r < R; ++r) u[r] = tile[(bi + r * T) * LDT + c];
   stage_twiddle<R, DIR>(N, p, k, tw, u);
   dftR<R, DIR>(u);
 }
 
-template <int R>
+template <int R, int LDT = FFT_LDT>
 FFT_HD void stage_store(double2* tile, int N, int p, int bi, int c, const double2* u) {
   (void)N;
   const int k = bi & (p - 1);
   const int j = (bi - k) * R + k;
 #pragma unroll
-  for (int r = 0; r < R; ++r) tile[(j + r * p) * FFT_LDT + c] = u[r];
+  for (int r = 0; r < R; ++r) tile[(j + r * p) * LDT + c] = u[r];
 }
 
 // Radix plan: N = R0*R1[*R2].

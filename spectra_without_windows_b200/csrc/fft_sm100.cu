@@ -55,7 +55,7 @@ struct PlanRadix {
   static constexpr int value = REV ? FftPlan<N>::R[FftPlan<N>::NS - 1 - S] : FftPlan<N>::R[S];
 };
 
-template <int N, int DIR, bool REV, int S, int P>
+template <int N, int DIR, bool REV, int S, int P, int LDT = FFT_LDT>
 struct MidStages {   // stages 1 .. NS-2, fully in shared memory
   static __device__ __forceinline__ void run(double2* tile, const double2* tw, int tid) {
     if constexpr (S < FftPlan<N>::NS - 1) {
@@ -66,16 +66,16 @@ struct MidStages {   // stages 1 .. NS-2, fully in shared memory
 #pragma unroll
       for (int s = 0; s < IPT; ++s) {
         int w = tid + s * NT;
-        stage_load<R, DIR>(tile, N, P, w >> 3, w & 7, tw, u[s]);
+        stage_load<R, DIR, LDT>(tile, N, P, w >> 3, w & 7, tw, u[s]);
       }
       __syncthreads();
 #pragma unroll
       for (int s = 0; s < IPT; ++s) {
         int w = tid + s * NT;
-        stage_store<R>(tile, N, P, w >> 3, w & 7, u[s]);
+        stage_store<R, LDT>(tile, N, P, w >> 3, w & 7, u[s]);
       }
       __syncthreads();
-      MidStages<N, DIR, REV, S + 1, P * R>::run(tile, tw, tid);
+      MidStages<N, DIR, REV, S + 1, P * R, LDT>::run(tile, tw, tid);
     }
   }
 };
@@ -126,7 +126,7 @@ __device__ __forceinline__ void fft_first_regs(double2* tile, int tid, double2 (
 }
 
 // Last stage: outputs u[s][r] sit at position bi + r*P of column c (P = N/R).
-template <int N, int DIR, bool REV, int R>
+template <int N, int DIR, bool REV, int R, int LDT = FFT_LDT>
 __device__ __forceinline__ void fft_last(const double2* tile, const double2* tw, int tid, double2 (*u)[R]) {
   static_assert(R == PlanRadix<N, REV, FftPlan<N>::NS - 1>::value, "radix mismatch");
   constexpr int NT = N / 2, IPT = 16 / R;
@@ -134,8 +134,38 @@ __device__ __forceinline__ void fft_last(const double2* tile, const double2* tw,
 #pragma unroll
   for (int s = 0; s < IPT; ++s) {
     int w = tid + s * NT;
-    stage_load<R, DIR>(tile, N, P, w >> 3, w & 7, tw, u[s]);
+    stage_load<R, DIR, LDT>(tile, N, P, w >> 3, w & 7, tw, u[s]);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bulk asynchronous copies (the TMA engine, non-tensor form) completing on an mbarrier: one thread issues the copy of a
+// whole contiguous tile, the CTA waits on the barrier's phase.  cp.async.bulk / mbarrier are sm_90+ PTX; the SASS shows
+// UBLKCP and SYNCS.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 
 #define FFT_LAST_RADIX(N, REV) (PlanRadix<N, REV, FftPlan<N>::NS - 1>::value)
@@ -326,6 +356,101 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
         if (bA.has(ia)) P[((long long)bA.pos(ia) * nC + ic) * Kzp + iz0 + cc] = u[s][r];
       }
     }
+  }
+}
+
+// The same pass on tile-major R planes with double-buffered bulk asynchronous copies: a tile [N][8] is ONE contiguous block,
+// thread 0 issues cp.async.bulk for the NEXT item into the other buffer before the CTA transforms the current one, and the
+// CTA waits on the buffer's mbarrier.  Stage 0 reads the tile from shared memory (dense pitch 8: every quarter-warp access is
+// a full 128-byte row, conflict-free) instead of global memory.  One CTA per SM (two 64 KB buffers at N = 512).
+template <int N, int AX>
+__global__ void __launch_bounds__(N / 2, 1)
+pass_f2_bulk_kernel(int nC, BoxAxis bA, int Kzp, const double2* __restrict__ Rbase, const double2* __restrict__ twg,
+                    double2* __restrict__ Pbase, int nb, long long rstride, long long pstride) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int LDT = FFT_TZ;                    // dense tiles
+  constexpr int TE = N * FFT_TZ;                 // elements per tile
+  constexpr unsigned BYTES = TE * sizeof(double2);
+  double2* tiles = reinterpret_cast<double2*>(smem_raw);
+  double2* tw = tiles + 2 * TE;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(tw + N);
+  const int tid = threadIdx.x;
+  constexpr int NT = N / 2;
+  constexpr int R0 = PlanRadix<N, false, 0>::value;
+  constexpr int RL = FFT_LAST_RADIX(N, false);
+  for (int i = tid; i < N; i += NT) tw[i] = twg[i];
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ztiles = Kzp / FFT_TZ;
+  const long long per = (long long)nC * ztiles;
+  const long long items = per * nb;
+  auto src_of = [&](long long it0) -> const double2* {
+    const int bat = (int)(it0 / per);
+    const long long it = it0 - (long long)bat * per;     // = ic * ztiles + zt
+    return Rbase + (long long)bat * rstride + it * TE;
+  };
+  unsigned phase0 = 0, phase1 = 0;
+  int cur = 0;
+  long long it0 = blockIdx.x;
+  if (it0 < items && tid == 0) {
+    mbar_expect_tx(bar, BYTES);
+    bulk_g2s(tiles, src_of(it0), BYTES, bar);
+  }
+  for (; it0 < items; it0 += gridDim.x, cur ^= 1) {
+    const long long nxt = it0 + gridDim.x;
+    if (nxt < items && tid == 0) {
+      fence_proxy_async();        // the other buffer was last touched by generic-proxy loads / stores (before the barrier below)
+      mbar_expect_tx(bar + (cur ^ 1), BYTES);
+      bulk_g2s(tiles + (cur ^ 1) * TE, src_of(nxt), BYTES, bar + (cur ^ 1));
+    }
+    if (cur == 0) {
+      mbar_wait(bar, phase0);
+      phase0 ^= 1;
+    } else {
+      mbar_wait(bar + 1, phase1);
+      phase1 ^= 1;
+    }
+    double2* tile = tiles + cur * TE;
+    const int bat = (int)(it0 / per);
+    const long long it = it0 - (long long)bat * per;
+    double2* __restrict__ P = Pbase + (long long)bat * pstride;
+    const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
+    const int iz0 = zt * FFT_TZ;
+    {   // stage 0 from the tile: all loads, barrier, butterflies + scatter
+      constexpr int IPT = 16 / R0, T = N / R0;
+      double2 u0[IPT][R0];
+#pragma unroll
+      for (int s = 0; s < IPT; ++s) {
+        const int w = tid + s * NT, bi = w >> 3, c = w & 7;
+#pragma unroll
+        for (int r = 0; r < R0; ++r) u0[s][r] = tile[(bi + r * T) * LDT + c];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < IPT; ++s) {
+        const int w = tid + s * NT;
+        dftR<R0, 1>(u0[s]);
+        stage_store<R0, LDT>(tile, N, 1, w >> 3, w & 7, u0[s]);
+      }
+      __syncthreads();
+    }
+    MidStages<N, 1, false, 1, R0, LDT>::run(tile, tw, tid);
+    double2 u[16 / RL][RL];
+    fft_last<N, 1, false, RL, LDT>(tile, tw, tid, u);
+#pragma unroll
+    for (int s = 0; s < 16 / RL; ++s) {
+      int w = tid + s * NT, bi = w >> 3, cc = w & 7;
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        int ia = bi + r * (N / RL);
+        if (bA.has(ia)) P[((long long)bA.pos(ia) * nC + ic) * Kzp + iz0 + cc] = u[s][r];
+      }
+    }
+    __syncthreads();   // every thread is done with this buffer before it is refilled two items later
   }
 }
 
@@ -1817,6 +1942,18 @@ static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int
                      int r_tiled) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)nC * (Kzp / FFT_TZ) * nb;
+  if constexpr (N <= 512) {
+    const char* eb = getenv("SWW_F2_BULK");
+    if (r_tiled && !(eb && eb[0] == '0')) {
+      // double-buffered bulk asynchronous tile loads (TMA engine), one CTA per SM
+      const size_t bsm = (size_t)2 * N * FFT_TZ * 16 + (size_t)N * 16 + 64;
+      const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (bsm + 1024))));
+      int bgrid = grid_for_items(items, per_sm);
+      SWW_TRY(set_smem(pass_f2_bulk_kernel<N, AX>, bsm));
+      pass_f2_bulk_kernel<N, AX><<<bgrid, N / 2, bsm, c->stream>>>(nC, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride);
+      return 0;
+    }
+  }
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_f2_kernel<N, AX>, smem));
   pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride, r_tiled);
@@ -2513,9 +2650,9 @@ int sww_sm100_pk_rows_store(sww_ctx* c, int nrows, const double2* const* F, int 
   // tile-major Q and R when the fused nz = 512 kernel runs the z pass: the column passes next to it (second inverse,
   // first forward) then move each 8-column tile as one contiguous block
   const char* etl = getenv("SWW_TILE_MAJOR");
-  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {
-    Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
-    Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
+  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {      // SWW_TILE_MAJOR = 0 | q | r (A/B switches), default: both
+    if (!(etl && etl[0] == 'r')) Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
+    if (!(etl && etl[0] == 'q')) Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
   }
   SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
   SWW_TRY(run_z(c, s, true, true, Z));
@@ -2560,9 +2697,9 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
   // tile-major Q and R when the fused nz = 512 kernel runs the z pass: the column passes next to it (second inverse,
   // first forward) then move each 8-column tile as one contiguous block
   const char* etl = getenv("SWW_TILE_MAJOR");
-  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {
-    Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
-    Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
+  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {      // SWW_TILE_MAJOR = 0 | q | r (A/B switches), default: both
+    if (!(etl && etl[0] == 'r')) Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
+    if (!(etl && etl[0] == 'q')) Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
   }
   SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
   SWW_TRY(run_z(c, s, true, true, Z));
