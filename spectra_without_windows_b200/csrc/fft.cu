@@ -67,8 +67,14 @@ int sww_c2r(sww_ctx* c, double2* in, double* out) {
 }
 
 int sww_c2c(sww_ctx* c, const double2* in, double2* out, int inverse) {
-  SWW_TRY(ensure_z2z(c));
   c->n_fft++;
+  if (c->fft_backend == 1 && c->fft_work && sww_fft_sm100_c2c_supported(c)) {
+    // hand-written passes: complex z pass + the two column passes over the full box
+    SWW_TRY(sww_fft_sm100_c2c(c, in, out, inverse));
+    if (inverse) SWW_TRY(k_scale_c(c, out, 1.0 / (double)c->g.N, c->g.N));
+    return 0;
+  }
+  SWW_TRY(ensure_z2z(c));
   SWW_CUFFT(cufftExecZ2Z(c->plan_z2z, (cufftDoubleComplex*)in, (cufftDoubleComplex*)out,
                          inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
   if (inverse) SWW_TRY(k_scale_c(c, out, 1.0 / (double)c->g.N, c->g.N));

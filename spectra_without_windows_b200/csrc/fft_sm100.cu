@@ -1212,6 +1212,63 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
 }
 
 // ------------------------------------------------------------------------------------------
+// Complex z pass (C2C transforms: the ft / ift mirrors and the maximum-likelihood operators, which keep full complex
+// maps): in-place FFT of length H = nz along the contiguous axis, one warp per row (two or four rows for short rows), the
+// stages of the warp-per-row machinery above with no real-data pre / post-processing.
+// ------------------------------------------------------------------------------------------
+template <int H, int DIR>
+__global__ void __launch_bounds__(256, 2)
+pass_zc_kernel(long long nrows, double2* __restrict__ data, const double2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int WARPS = 8;
+  constexpr int RW = WGeo<H>::RW, ROWLEN = WGeo<H>::ROWLEN;
+  constexpr int T = WTabSize<H, false>::value;
+  double2* tabs = reinterpret_cast<double2*>(smem_raw);
+  double2* bufs = tabs + T;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double2* buf = bufs + warp * (RW * ROWLEN + 8);
+  w_fill_tab<H, false, 0>(tabs, tw_g, tid, 256);
+  __syncthreads();
+  const long long ngroups = nrows / RW;
+  for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * WARPS) {
+    double2* rows = data + grp * RW * H;
+    __syncwarp();
+#pragma unroll
+    for (int rho = 0; rho < RW; ++rho)
+      for (int i = lane; i < H; i += 32) buf[rho * ROWLEN + zpad(i)] = rows[rho * H + i];
+    __syncwarp();
+    {   // stage 0: no twiddles
+      constexpr int R = WRadix<H, false, 0>::value;
+      constexpr int BPR = H / R;
+      constexpr int IPT = RW * BPR / 32;
+      double2 u[IPT][R];
+#pragma unroll
+      for (int s = 0; s < IPT; ++s) {
+        const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+        const double2* row = buf + rho * ROWLEN;
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[s][r] = row[zpad(bi + r * BPR)];
+        dftR<R, DIR>(u[s]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < IPT; ++s) {
+        const int vb = lane + 32 * s, rho = vb / BPR, bi = vb - rho * BPR;
+        double2* row = buf + rho * ROWLEN;
+#pragma unroll
+        for (int r = 0; r < R; ++r) row[zpad(bi * R + r)] = u[s][r];
+      }
+      __syncwarp();
+    }
+    w_mid_stage<H, DIR, false, 1>(buf, tabs, lane);
+    if constexpr (WPlan<H>::NS == 3) w_mid_stage<H, DIR, false, 2>(buf, tabs, lane);
+#pragma unroll
+    for (int rho = 0; rho < RW; ++rho)
+      for (int i = lane; i < H; i += 32) rows[rho * H + i] = buf[rho * ROWLEN + zpad(i)];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused z pass for nz = 512 (H = 256 = 16 x 16): c2r * wmap * r2c with TWO exchanges through shared
 // memory per row instead of the eleven of the generic warp-per-row kernel above, which is bound by the
 // 128 B/clk shared-memory crossbar, not by the FP64 pipe.
@@ -1752,6 +1809,7 @@ pass_z32_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
 // ------------------------------------------------------------------------------------------
 struct Sm100State {
   double2 *tw_x = nullptr, *tw_y = nullptr, *tw_h = nullptr, *tw_n = nullptr;
+  double2* tw_c = nullptr;      // exp(-2 pi i j / nz), j < nz: complex z pass (built on first use)
   double2 *P = nullptr, *Q = nullptr, *R = nullptr;
   size_t buf_elems = 0;
   std::vector<int> shell_bx, shell_by, shell_bz;  // per-bin inverse boxes
@@ -1828,6 +1886,7 @@ void sww_fft_sm100_destroy(sww_ctx* c) {
   cudaFree(s->tw_y);
   cudaFree(s->tw_h);
   cudaFree(s->tw_n);
+  if (s->tw_c) cudaFree(s->tw_c);
   if (s->d_perm) cudaFree(s->d_perm);
   if (s->d_chunks) cudaFree(s->d_chunks);
   if (s->d_bin_chunk) cudaFree(s->d_bin_chunk);
@@ -1944,7 +2003,7 @@ static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int
   long long items = (long long)nC * (Kzp / FFT_TZ) * nb;
   if constexpr (N <= 512) {
     const char* eb = getenv("SWW_F2_BULK");
-    if (r_tiled && !(eb && eb[0] == '0')) {
+    if (r_tiled && eb && eb[0] == '1') {   // opt-in (measured slower than the two-CTA kernel: see sww_sm100_pk_rows_store)
       // double-buffered bulk asynchronous tile loads (TMA engine), one CTA per SM
       const size_t bsm = (size_t)2 * N * FFT_TZ * 16 + (size_t)N * 16 + 64;
       const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (bsm + 1024))));
@@ -2291,6 +2350,77 @@ int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out) {
   Z.scale = 1.0;
   Z.lm = -1;
   return run_z(c, s, true, false, Z);
+}
+
+// ---- complex 3-D transforms on the same passes: z (complex, in place) + the two column passes over the full box ----
+int sww_fft_sm100_c2c_supported(const sww_ctx* c) {
+  const int nz = c->g.nz;
+  return sww_fft_sm100_supported(c) && (nz == 64 || nz == 128 || nz == 256 || nz == 512);
+}
+
+template <int DIR>
+static int run_zc(sww_ctx* c, Sm100State* s, double2* data) {
+  SWW_PROF(c, DIR > 0 ? "fft.Zc forward (complex)" : "fft.Zc inverse (complex)");
+  const int H = c->g.nz;
+  const long long nrows = (long long)c->g.nx * c->g.ny;
+#define M(HH)                                                                                                     \
+  {                                                                                                               \
+    const size_t smem = (size_t)(WTabSize<HH, false>::value + 8 * (WGeo<HH>::RW * WGeo<HH>::ROWLEN + 8)) * 16;   \
+    const long long ctas = (nrows / WGeo<HH>::RW + 7) / 8;                                                        \
+    const int grid = (int)std::min<long long>(ctas, (long long)SMS * 2);                                          \
+    SWW_TRY((set_smem(pass_zc_kernel<HH, DIR>, smem)));                                                           \
+    pass_zc_kernel<HH, DIR><<<grid, 256, smem, c->stream>>>(nrows, data, s->tw_c);                               \
+  }
+  switch (H) {
+    case 64: M(64); break;
+    case 128: M(128); break;
+    case 256: M(256); break;
+    case 512: M(512); break;
+    default: SWW_REQUIRE(false, "complex z pass: unsupported length %d", H);
+  }
+#undef M
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out = DFT(in) (forward, e^{-i..}) or the unnormalised inverse; in == out allowed.  The pass buffers of the real
+// transforms (one contiguous region) serve as the single intermediate of N complex values.
+int sww_fft_sm100_c2c(sww_ctx* c, const double2* in, double2* out, int inverse) {
+  Sm100State* s;
+  SWW_TRY(get_state(c, &s));
+  SWW_REQUIRE(sww_fft_sm100_c2c_supported(c), "complex transforms on the sm_100a passes need nz in {64,128,256,512}");
+  Geo& g = c->g;
+  if (!s->tw_c) {
+    std::vector<double2> t = make_tw(g.nz, g.nz);
+    SWW_CUDA(cudaMalloc(&s->tw_c, t.size() * sizeof(double2)));
+    SWW_CUDA(cudaMemcpy(s->tw_c, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  SWW_REQUIRE(3 * s->buf_elems >= (size_t)g.N, "pass buffers too small for a complex transform");
+  // the column passes index a spectrum as [nx][ny][nzh]: for complex data every z index is a column
+  const int save_nzh = g.nzh;
+  const size_t save_elems = s->buf_elems;
+  double2* save_R = s->R;
+  g.nzh = g.nz;
+  s->buf_elems = 3 * save_elems;
+  AxisPlan pl = make_plan(g, full_axis(g.nx), full_axis(g.ny));
+  const int Kz = g.nz, Kzp = g.nz;
+  int rc = 0;
+  if (!inverse) {
+    if (in != out) rc = cudaMemcpyAsync(out, in, sizeof(double2) * (size_t)g.N, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess ? 0 : -2;
+    if (rc == 0) rc = run_zc<1>(c, s, out);
+    s->R = out;
+    F3Args A = {};
+    A.dst = out;
+    if (rc == 0) rc = run_forward_cols(c, s, pl, Kz, Kzp, 0, A);
+  } else {
+    rc = run_inverse_cols(c, s, pl, Kz, Kzp, in, -1, nullptr, 1, out, 0);
+    if (rc == 0) rc = run_zc<-1>(c, s, out);
+  }
+  g.nzh = save_nzh;
+  s->buf_elems = save_elems;
+  s->R = save_R;
+  return rc;
 }
 
 // ---- pruned / fused chains ----
@@ -2650,9 +2780,12 @@ int sww_sm100_pk_rows_store(sww_ctx* c, int nrows, const double2* const* F, int 
   // tile-major Q and R when the fused nz = 512 kernel runs the z pass: the column passes next to it (second inverse,
   // first forward) then move each 8-column tile as one contiguous block
   const char* etl = getenv("SWW_TILE_MAJOR");
-  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {      // SWW_TILE_MAJOR = 0 | q | r (A/B switches), default: both
-    if (!(etl && etl[0] == 'r')) Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
-    if (!(etl && etl[0] == 'q')) Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
+  // Measured on C2 / C5 (profiles/r2j): R tile-major F2 42.3 -> 40.7 ms but the z pass 92.2 -> 93.6 ms; Q tile-major I2
+  // 24.5 -> 23.9 ms, z pass +5 ms; the bulk-copy F2 kernel (one CTA per SM) 44.3 ms.  F2 already moves 5.3 TB/s (82 % of
+  // the measured HBM peak) in row-major form, so the layout is OFF by default: SWW_TILE_MAJOR = q | r | b(oth) opts in.
+  if (z16p_takes(c, Z) && etl && (etl[0] == 'q' || etl[0] == 'r' || etl[0] == 'b')) {
+    if (etl[0] != 'r') Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
+    if (etl[0] != 'q') Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
   }
   SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
   SWW_TRY(run_z(c, s, true, true, Z));
@@ -2697,9 +2830,12 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
   // tile-major Q and R when the fused nz = 512 kernel runs the z pass: the column passes next to it (second inverse,
   // first forward) then move each 8-column tile as one contiguous block
   const char* etl = getenv("SWW_TILE_MAJOR");
-  if (z16p_takes(c, Z) && !(etl && etl[0] == '0')) {      // SWW_TILE_MAJOR = 0 | q | r (A/B switches), default: both
-    if (!(etl && etl[0] == 'r')) Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
-    if (!(etl && etl[0] == 'q')) Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
+  // Measured on C2 / C5 (profiles/r2j): R tile-major F2 42.3 -> 40.7 ms but the z pass 92.2 -> 93.6 ms; Q tile-major I2
+  // 24.5 -> 23.9 ms, z pass +5 ms; the bulk-copy F2 kernel (one CTA per SM) 44.3 ms.  F2 already moves 5.3 TB/s (82 % of
+  // the measured HBM peak) in row-major form, so the layout is OFF by default: SWW_TILE_MAJOR = q | r | b(oth) opts in.
+  if (z16p_takes(c, Z) && etl && (etl[0] == 'q' || etl[0] == 'r' || etl[0] == 'b')) {
+    if (etl[0] != 'r') Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
+    if (etl[0] != 'q') Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
   }
   SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
   SWW_TRY(run_z(c, s, true, true, Z));

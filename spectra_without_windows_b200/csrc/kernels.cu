@@ -77,10 +77,10 @@ int k_prep_static(sww_ctx* c) {
 
 // nCa = n C^-1 a ; nAa = n A^-1 a ; WS = W * (N A^-1 a)
 // include_pix: a_c = M a replaces a in the C^-1 branch, ainv_in = M^-1 (a / n_A) replaces a / n_A
+// a_c / ainv_in may alias nCa / WS-side scratch (the include_pix path prepares them in place): no __restrict__ on those
 __global__ void prep_pk_kernel(long long N, const double* __restrict__ a, const double* __restrict__ n,
                                const double* __restrict__ nw, const double* __restrict__ nA, double shot, double P,
-                               double v_cell, double* __restrict__ nCa, double* __restrict__ nAa,
-                               double* __restrict__ WS, const double* __restrict__ a_c, const double* __restrict__ ainv_in) {
+                               double v_cell, double* nCa, double* nAa, double* WS, const double* a_c, const double* ainv_in) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
     double x = a_c ? a_c[i] : a[i], nn = n[i], w = nw[i];
     double fkp = w * (w * P + shot);
@@ -132,8 +132,8 @@ int k_apply_n(sww_ctx* c, const double* x, const double* nbar, double v_cell, do
   return 0;
 }
 
-__global__ void mul_kernel(long long N, const double* __restrict__ a, const double* __restrict__ b, double s,
-                           double* __restrict__ out) {
+// `out` may alias `a` or `b` (k_weight, sww_fft_c2r scale in place): element i is read before it is written, no __restrict__
+__global__ void mul_kernel(long long N, const double* a, const double* b, double s, double* out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
     out[i] = b ? a[i] * b[i] * s : a[i] * s;
 }

@@ -186,6 +186,8 @@ int sww_c2c(sww_ctx* c, const double2* in, double2* out, int inverse);
 int sww_fft_sm100_supported(const sww_ctx* c);
 int sww_fft_sm100_r2c(sww_ctx* c, const double* in, double2* out);
 int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out);
+int sww_fft_sm100_c2c_supported(const sww_ctx* c);
+int sww_fft_sm100_c2c(sww_ctx* c, const double2* in, double2* out, int inverse);   // unnormalised
 size_t sww_fft_sm100_work_bytes(const sww_ctx* c);
 void sww_fft_sm100_destroy(sww_ctx* c);
 void sww_rng_destroy(sww_ctx* c);   // rng.cu

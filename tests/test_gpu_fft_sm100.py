@@ -223,3 +223,46 @@ def test_row_mesh_matches_full_mesh(eng):
     assert np.max(np.abs(res["full"][0])) > 0
     assert relerr(res["row"][0], res["full"][0]) < 1e-11 and relerr(res["row"][1], res["full"][1]) < 1e-11
     assert relerr(res["row"][0], res["cufft"][0]) < 1e-11 and relerr(res["row"][1], res["cufft"][1]) < 1e-11
+
+
+def test_tile_major_planes_and_bulk_copy_f2(eng):
+    """Opt-in tile-major Q / R planes (SWW_TILE_MAJOR=b) and the bulk-asynchronous-copy F2 kernel (SWW_F2_BULK=1,
+    cp.async.bulk + mbarrier) must reproduce the default row-major chain bit for bit: same arithmetic, other data movement."""
+    import os
+    from spectra_without_windows_b200 import synthetic as syn
+    grid, box, bc = (64, 128, 512), (1280.0, 2816.0, 5120.0), (1700.0, 60.0, -45.0)
+    mesh = eng.Mesh(box, grid, bc, 0.0, 0.12, 0.02, 4)
+    ctx = eng.Context(mesh, 0, ("ops", "pk_fisher"))
+    nbar_A = ctx.set_fields_from_randoms_density(syn.survey_nbar(box, grid, bc, n0=6e-3), 0.05, 1.05)
+    a = np.random.default_rng(3).normal(size=grid) * np.sqrt(nbar_A)
+    F0, q0 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+    for env in ({"SWW_TILE_MAJOR": "b"}, {"SWW_TILE_MAJOR": "r", "SWW_F2_BULK": "1"}, {"SWW_TILE_MAJOR": "q"}):
+        os.environ.update(env)
+        try:
+            F1, q1 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert np.array_equal(F1, F0) and np.array_equal(q1, q0), env
+    ctx.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 64, 256), (64, 256, 512)])
+def test_complex_transforms_on_own_passes(eng, shape):
+    """ft / ift (src/opt_utilities.py:502-555) as complex 3-D transforms on the hand-written passes (complex z pass + the
+    two column passes over the full box) against numpy.fft, and against the cuFFT Z2Z path."""
+    box = tuple(20.0 * s for s in shape)
+    mesh = eng.Mesh(box, shape, (0.0, 0.0, 0.0), 0.0, 0.1, 0.05, 0)
+    ctx = eng.Context(mesh, 0, ("ops",))
+    assert ctx.fft_backend == 1
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+    own0, fft0 = ctx.launch_counts()
+    X = ctx.fft_c2c(x).cpu().numpy()
+    own1, _ = ctx.launch_counts()
+    assert own1 - own0 >= 3                                   # the passes ran (no cuFFT plan involved)
+    assert relerr(X, np.fft.fftn(x)) < 1e-13
+    assert relerr(ctx.fft_c2c(X, inverse=True).cpu().numpy(), x) < 1e-13
+    ctx.set_fft_backend(0)
+    assert relerr(ctx.fft_c2c(x).cpu().numpy(), X) < 1e-13
+    ctx.close()

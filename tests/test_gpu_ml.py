@@ -75,7 +75,8 @@ def test_ml_fisher_realisation(eng, world, golden):
 
 
 def test_ml_on_power_of_two_mesh_against_oracle(eng, world, golden):
-    """64 x 64 x 128: real transforms run on the hand-written passes, the complex ones on the C2C plan."""
+    """64 x 64 x 128: every transform of the ML operators -- real and complex -- runs on the hand-written passes (complex z
+    pass + column passes over the full box; no cuFFT plan is involved on power-of-two meshes with nz <= 512)."""
     from oracle import sww_oracle as orc
     w = world("toyD")
     table = golden("toyA_ml")["ml_pk_table"]
