@@ -198,7 +198,7 @@ template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
 pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ src, int shell,
                const double2* __restrict__ twg, double2* __restrict__ Pbase, GatherBatch gb, BoxAxis cbx, BoxAxis cby,
-               long long pstride) {
+               long long pstride, double klim2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -216,6 +216,12 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
     double2* __restrict__ P = Pbase + (long long)bat * pstride;
     const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
     const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
+    if (klim2 > 0.0) {
+      // every mode of this (k_o, k_z tile) column lies outside the sphere |k| < k_lim: the column is identically zero
+      // and the next pass never reads it (same predicate there)
+      const double ko = g.kax[AX == 0 ? 1 : 0][io], kz0 = g.kax[2][iz0];
+      if (ko * ko + kz0 * kz0 >= klim2) continue;
+    }
     __syncthreads();
     fft_first<N, -1, false>(tile, tid, [&](int ia, int cc) {
       double2 v = make_double2(0.0, 0.0);
@@ -273,7 +279,8 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
 pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Pbase, const double2* __restrict__ twg,
-               double2* __restrict__ Qbase, int nb, long long pstride, long long qstride, int q_tiled) {
+               double2* __restrict__ Qbase, int nb, long long pstride, long long qstride, int q_tiled,
+               const double* __restrict__ kax_a, const double* __restrict__ kax_z, double klim2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -292,9 +299,11 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
     const int f = (int)(it / ztiles), zt = (int)(it - (long long)f * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
+    const double kz2 = klim2 > 0.0 ? kax_z[iz0] * kax_z[iz0] : 0.0;
     fft_first<N, -1, false>(tile, tid, [&](int ia, int cc) {
       double2 v = make_double2(0.0, 0.0);
-      if (bA.has(ia)) v = P[((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc];
+      // columns outside the sphere |k| < k_lim were skipped by the first pass: they are zero, not stored
+      if (bA.has(ia) && !(klim2 > 0.0 && kax_a[ia] * kax_a[ia] + kz2 >= klim2)) v = P[((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc];
       return v;
     });
     FFT_MID(N, -1, false, tile, tw, tid);
@@ -319,7 +328,8 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
 template <int N, int AX>
 __global__ void __launch_bounds__(N / 2)
 pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Rbase, const double2* __restrict__ twg,
-               double2* __restrict__ Pbase, int nb, long long rstride, long long pstride, int r_tiled) {
+               double2* __restrict__ Pbase, int nb, long long rstride, long long pstride, int r_tiled,
+               const double* __restrict__ kax_a, const double* __restrict__ kax_z, double klim2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);
   double2* tw = tile + N * FFT_LDT;
@@ -337,6 +347,7 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
     double2* __restrict__ P = Pbase + (long long)bat * pstride;
     const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
+    const double kz2 = klim2 > 0.0 ? kax_z[iz0] * kax_z[iz0] : 0.0;
     __syncthreads();
     if (r_tiled) {   // tile-major R: this item's tile is one contiguous block [ia][8]
       const double2* __restrict__ Rt = R + ((long long)ic * ztiles + zt) * N * FFT_TZ;
@@ -353,7 +364,9 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
         int ia = bi + r * (N / RL);
-        if (bA.has(ia)) P[((long long)bA.pos(ia) * nC + ic) * Kzp + iz0 + cc] = u[s][r];
+        // columns outside the sphere |k| < k_lim hold no binned mode: the last pass skips them, nothing is stored
+        if (bA.has(ia) && !(klim2 > 0.0 && kax_a[ia] * kax_a[ia] + kz2 >= klim2))
+          P[((long long)bA.pos(ia) * nC + ic) * Kzp + iz0 + cc] = u[s][r];
       }
     }
   }
@@ -504,6 +517,10 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
   for (long long it = blk; it < items; it += nblk) {
     const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
     const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
+    if (A.klim2 > 0.0) {   // no binned mode in this (k_o, k_z tile) column: nothing to store or bin (uniform per CTA)
+      const double ko = g.kax[AX == 0 ? 1 : 0][io], kz0 = g.kax[2][iz0];
+      if (ko * ko + kz0 * kz0 >= A.klim2) continue;
+    }
     __syncthreads();
     fft_first<N, 1, false>(tile, tid,
                            [&](int ia, int cc) { return P[((long long)jo * N + ia) * Kzp + iz0 + cc]; });
@@ -1976,34 +1993,35 @@ static const double2* tw_of(Sm100State* s, int ax) { return ax == 0 ? s->tw_x : 
 
 template <int N, int AX>
 static int launch_i1(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* src, int shell,
-                     const GatherBatch& gb, long long pstride) {
+                     const GatherBatch& gb, long long pstride, double klim2) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)bO.K * (Kzp / FFT_TZ) * (gb.nb > 0 ? gb.nb : 1);
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i1_kernel<N, AX>, smem));
   pass_i1_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, gb,
                                                          box_axis_of(c->g.nx, c->g.bx), box_axis_of(c->g.ny, c->g.by),
-                                                         pstride);
+                                                         pstride, klim2);
   return 0;
 }
 template <int N, int AX>
 static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, double2* Qdst, int nb, long long pstride,
-                     long long qstride, int q_tiled) {
+                     long long qstride, int q_tiled, double klim2) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)nF * (Kzp / FFT_TZ) * nb;
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i2_kernel<N, AX>, smem));
-  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride, q_tiled);
+  pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride, q_tiled,
+                                                         c->g.kax[AX], c->g.kax[2], klim2);
   return 0;
 }
 template <int N, int AX>
 static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int nb, long long rstride, long long pstride,
-                     int r_tiled) {
+                     int r_tiled, double klim2) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)nC * (Kzp / FFT_TZ) * nb;
   if constexpr (N <= 512) {
     const char* eb = getenv("SWW_F2_BULK");
-    if (r_tiled && eb && eb[0] == '1') {   // opt-in (measured slower than the two-CTA kernel: see sww_sm100_pk_rows_store)
+    if (r_tiled && eb && eb[0] == '1' && klim2 <= 0.0) {   // opt-in (measured slower than the two-CTA kernel: see sww_sm100_pk_rows_store)
       // double-buffered bulk asynchronous tile loads (TMA engine), one CTA per SM
       const size_t bsm = (size_t)2 * N * FFT_TZ * 16 + (size_t)N * 16 + 64;
       const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (bsm + 1024))));
@@ -2015,7 +2033,8 @@ static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int
   }
   int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_f2_kernel<N, AX>, smem));
-  pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride, r_tiled);
+  pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride, r_tiled,
+                                                         c->g.kax[AX], c->g.kax[2], klim2);
   return 0;
 }
 template <int N, int AX>
@@ -2064,7 +2083,7 @@ static int axis_len(const Geo& g, int ax) { return ax == 0 ? g.nx : g.ny; }
 // inverse column passes: spectrum (box, optional shell filter) -> Q[nx][ny][Kzp]
 static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, const double2* src, int shell,
                             const GatherArgs* gap = nullptr, int nb = 1, double2* Qdst = nullptr, long long qstride = 0,
-                            int q_tiled = 0) {
+                            int q_tiled = 0, double klim2 = 0.0) {
   if (!Qdst) Qdst = s->Q;
   const int a1 = pl.x_first_fwd ? 1 : 0;   // first inverse axis = the weakly pruned one
   const int a2 = 1 - a1;
@@ -2084,7 +2103,7 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     }
     {
       SWW_PROF(c, a1 == 0 ? "fft.I1 x-inverse (gather)" : "fft.I1 y-inverse (gather)");
-#define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell, gb, pstride)
+#define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell, gb, pstride, klim2)
       DISPATCH_AX(n1, a1, CALL)
 #undef CALL
       c->n_own++;
@@ -2092,7 +2111,7 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     }
     {
       SWW_PROF(c, a2 == 0 ? "fft.I2 x-inverse" : "fft.I2 y-inverse");
-#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst + (long long)b0 * qstride, nbc, pstride, qstride, q_tiled)
+#define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst + (long long)b0 * qstride, nbc, pstride, qstride, q_tiled, klim2)
       DISPATCH_AX(n2, a2, CALL)
 #undef CALL
       c->n_own++;
@@ -2104,7 +2123,7 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
 
 // forward column passes: R[nx][ny][Kzp] -> epilogue `mode`
 static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int Kz, int Kzp, int mode, F3Args A,
-                            int nb = 1, long long rstride = 0, const F3Args* Ab = nullptr, int r_tiled = 0) {
+                            int nb = 1, long long rstride = 0, const F3Args* Ab = nullptr, int r_tiled = 0, double klim2 = 0.0) {
   const int a1 = pl.x_first_fwd ? 0 : 1;   // first forward axis = the strongly pruned one
   const int a2 = 1 - a1;
   const BoxAxis b1 = a1 == 0 ? pl.bx : pl.by, b2 = a2 == 0 ? pl.bx : pl.by;
@@ -2113,7 +2132,7 @@ static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
   SWW_REQUIRE((size_t)pstride * nb <= s->buf_elems, "forward batch of %d planes does not fit the pass buffer", nb);
   {
     SWW_PROF(c, a1 == 0 ? "fft.F2 x-forward" : "fft.F2 y-forward");
-#define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp, nb, rstride, pstride, r_tiled)
+#define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp, nb, rstride, pstride, r_tiled, klim2)
     DISPATCH_AX(n1, a1, CALL)
 #undef CALL
     c->n_own++;
@@ -2787,14 +2806,20 @@ int sww_sm100_pk_rows_store(sww_ctx* c, int nrows, const double2* const* F, int 
     if (etl[0] != 'r') Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
     if (etl[0] != 'q') Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
   }
-  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
+  // columns of the (k_o, k_z) plane outside the sphere of the shell (inverse) / of k_max (forward) are skipped by the
+  // column passes (a margin of 1e-12 keeps modes that numpy's sqrt comparison might still bin); SWW_NO_SPHERE_SKIP=1: off
+  const bool sphere = !env_on("SWW_NO_SPHERE_SKIP");
+  const double khi_a = c->h_khi[shell], kmax_all = *std::max_element(c->h_khi.begin(), c->h_khi.end());
+  const double klim_i = sphere ? khi_a * khi_a * (1.0 + 1e-12) : 0.0, klim_o = sphere ? kmax_all * kmax_all * (1.0 + 1e-12) : 0.0;
+  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile, klim_i));
   SWW_TRY(run_z(c, s, true, true, Z));
   F3Args Ab[SWW_MAX_L] = {};
   for (int b = 0; b < nrows; ++b) {
     Ab[b].perm = s->d_perm;
     Ab[b].sorted_dst = Us_rows + (long long)b * s->S;
+    Ab[b].klim2 = klim_o;
   }
-  return run_forward_cols(c, s, plo, Kzo, Kzpo, 3, Ab[0], nrows, rstride, Ab, Z.r_tile);
+  return run_forward_cols(c, s, plo, Kzo, Kzpo, 3, Ab[0], nrows, rstride, Ab, Z.r_tile, klim_o);
 }
 
 int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell, const double* wmap, double inv_scale,
@@ -2837,7 +2862,12 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
     if (etl[0] != 'r') Z.q_tile = (pli.x_first_fwd ? 0 : 1) + 1;      // axis of the second inverse pass
     if (etl[0] != 'q') Z.r_tile = (plo.x_first_fwd ? 0 : 1) + 1;      // axis of the first forward pass
   }
-  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile));
+  // columns of the (k_o, k_z) plane outside the sphere of the shell (inverse) / of k_max (forward) are skipped by the
+  // column passes (a margin of 1e-12 keeps modes that numpy's sqrt comparison might still bin); SWW_NO_SPHERE_SKIP=1: off
+  const bool sphere = !env_on("SWW_NO_SPHERE_SKIP");
+  const double khi_a = c->h_khi[shell], kmax_all = *std::max_element(c->h_khi.begin(), c->h_khi.end());
+  const double klim_i = sphere ? khi_a * khi_a * (1.0 + 1e-12) : 0.0, klim_o = sphere ? kmax_all * kmax_all * (1.0 + 1e-12) : 0.0;
+  SWW_TRY(run_inverse_cols(c, s, pli, Kzi, Kzpi, nullptr, -1, ga, nrows, s->Q, qstride, Z.q_tile, klim_i));
   SWW_TRY(run_z(c, s, true, true, Z));
   F3Args Ab[SWW_MAX_L] = {};
   for (int b = 0; b < nrows; ++b) {
@@ -2845,6 +2875,7 @@ int sww_sm100_pk_rows(sww_ctx* c, int nrows, const double2* const* F, int shell,
     Ab[b].n_g = n_g;
     Ab[b].scale = scale;
     Ab[b].out_row = out_rows[b];
+    Ab[b].klim2 = klim_o;
   }
-  return run_forward_cols(c, s, plo, Kzo, Kzpo, 2, Ab[0], nrows, rstride, Ab, Z.r_tile);
+  return run_forward_cols(c, s, plo, Kzo, Kzpo, 2, Ab[0], nrows, rstride, Ab, Z.r_tile, klim_o);
 }

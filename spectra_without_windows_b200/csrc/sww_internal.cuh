@@ -211,6 +211,9 @@ struct F3Args {
   double2* sorted_dst;
   // MODE 0/1 dst and MODE 2 G maps may live on another (coarser) grid with the same box: [dnx][dny][dnzh]  (0: this grid)
   int dnx, dny, dnzh;
+  // > 0: (k_o, k_z tile) columns with k_o^2 + k_z0^2 >= klim2 hold no binned mode and are skipped (the first forward pass
+  // does not store them either)
+  double klim2;
 };
 // gather description for the first inverse pass: sum of up to three compact box spectra, each kept only
 // inside its shell, times coef * Y_lm(k^)  (n_terms == 0: plain spectrum + optional shell filter)

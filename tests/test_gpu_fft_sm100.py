@@ -236,7 +236,9 @@ def test_tile_major_planes_and_bulk_copy_f2(eng):
     nbar_A = ctx.set_fields_from_randoms_density(syn.survey_nbar(box, grid, bc, n0=6e-3), 0.05, 1.05)
     a = np.random.default_rng(3).normal(size=grid) * np.sqrt(nbar_A)
     F0, q0 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
-    for env in ({"SWW_TILE_MAJOR": "b"}, {"SWW_TILE_MAJOR": "r", "SWW_F2_BULK": "1"}, {"SWW_TILE_MAJOR": "q"}):
+    # ... and so must the chain without the sphere skipping of the column passes (skipped columns are exact zeros)
+    for env in ({"SWW_TILE_MAJOR": "b"}, {"SWW_TILE_MAJOR": "r", "SWW_F2_BULK": "1", "SWW_NO_SPHERE_SKIP": "1"}, {"SWW_TILE_MAJOR": "q"},
+                {"SWW_NO_SPHERE_SKIP": "1"}):
         os.environ.update(env)
         try:
             F1, q1 = (t.cpu().numpy() for t in ctx.pk_fisher(a))
