@@ -141,6 +141,10 @@ int sww_grf_check(sww_ctx* c);
 int sww_pk_fisher_realisation(sww_ctx* c, sww_devptr a, sww_devptr fish_out, sww_devptr qbar_out);
 /* q_alpha [n_b] of a painted (n_g - alpha n_r)/V_cell map.  Replaces pk/compute_pk_data.py:191-206. */
 int sww_pk_data_q(sww_ctx* c, sww_devptr diff, sww_devptr q_out);
+/* After the sum over realisations and ranks (one host-side all-reduce of n_b^2 + n_b doubles, torch.distributed / NCCL):
+ * the mean and the symmetrisation of pk/compute_pk_data.py:227-247 / pk/compute_pk_randoms.py:281, in place.
+ * qbar_sum may be 0 (bispectrum Fisher: pairs instead of realisations, no bias vector). */
+int sww_mc_finalize(sww_ctx* c, sww_devptr fish_sum, sww_devptr qbar_sum, int32_t n_b, int32_t n_realisations);
 
 /* ---- maximum-likelihood weights (`weights = ML`; workspace selector SWW_WS_PK_ML) ----
  * These operators work on FULL COMPLEX maps double2[nx][ny][nz], like the reference's complex128 arrays: on the

@@ -55,6 +55,7 @@ SIGNATURES = {
     "sww_grf_legacy_batch": [ctxp, C.POINTER(C.c_uint32), C.c_int, u64, C.POINTER(u64), u64, u64],
     "sww_pk_fisher_realisation": [ctxp, u64, u64, u64],
     "sww_pk_data_q": [ctxp, u64, u64],
+    "sww_mc_finalize": [ctxp, u64, u64, i32, i32],
     "sww_set_fiducial_pk": [ctxp, u64],
     "sww_ml_apply": [ctxp, C.c_int, u64, u64],
     "sww_ml_apply_cinv": [ctxp, u64, C.c_int, f64, f64, u64, C.POINTER(i32), C.POINTER(i32)],

@@ -187,6 +187,17 @@ struct BoxAxis {
 //     inverse:  first pass (gather)  spectrum -> P[Ko][nA][Kzp],   second pass  P -> Q[nx][ny][Kzp]
 //     forward:  first pass           R -> P[K_B][nC][Kzp],          last pass    P -> epilogue
 // ------------------------------------------------------------------------------------------
+// Sphere pruning of the column passes: within the z tile starting at k_z0 only the indices |i| <= lim along an axis with
+// fundamental kF can hold a mode with |k|^2 < klim2 (one index of margin against rounding).  All four passes use this one
+// function, so a column skipped by the pass that would write it is skipped by the pass that would read it.
+__device__ __forceinline__ int sphere_lim(double klim2, double kz0, double kF, int n) {
+  if (klim2 <= 0.0) return n;
+  const double r2 = klim2 - kz0 * kz0;
+  if (r2 <= 0.0) return -1;
+  return (int)(sqrt(r2) / kF) + 1;
+}
+__device__ __forceinline__ int sidx_abs(int i, int n) { return 2 * i <= n ? i : n - i; }
+
 template <int AX>
 __device__ __forceinline__ long long row_of(int a, int o, int ny) {
   return AX == 0 ? (long long)a * ny + o : (long long)o * ny + a;
@@ -219,8 +230,8 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
     if (klim2 > 0.0) {
       // every mode of this (k_o, k_z tile) column lies outside the sphere |k| < k_lim: the column is identically zero
       // and the next pass never reads it (same predicate there)
-      const double ko = g.kax[AX == 0 ? 1 : 0][io], kz0 = g.kax[2][iz0];
-      if (ko * ko + kz0 * kz0 >= klim2) continue;
+      const int n_o = AX == 0 ? g.ny : g.nx;
+      if (sidx_abs(io, n_o) > sphere_lim(klim2, g.kax[2][iz0], g.kax[AX == 0 ? 1 : 0][1], n_o)) continue;
     }
     __syncthreads();
     fft_first<N, -1, false>(tile, tid, [&](int ia, int cc) {
@@ -299,11 +310,11 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
     const int f = (int)(it / ztiles), zt = (int)(it - (long long)f * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    const double kz2 = klim2 > 0.0 ? kax_z[iz0] * kax_z[iz0] : 0.0;
+    const int lim = sphere_lim(klim2, kax_z[iz0], kax_a[1], N);
     fft_first<N, -1, false>(tile, tid, [&](int ia, int cc) {
       double2 v = make_double2(0.0, 0.0);
       // columns outside the sphere |k| < k_lim were skipped by the first pass: they are zero, not stored
-      if (bA.has(ia) && !(klim2 > 0.0 && kax_a[ia] * kax_a[ia] + kz2 >= klim2)) v = P[((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc];
+      if (bA.has(ia) && sidx_abs(ia, N) <= lim) v = P[((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc];
       return v;
     });
     FFT_MID(N, -1, false, tile, tw, tid);
@@ -347,7 +358,7 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
     double2* __restrict__ P = Pbase + (long long)bat * pstride;
     const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
-    const double kz2 = klim2 > 0.0 ? kax_z[iz0] * kax_z[iz0] : 0.0;
+    const int lim = sphere_lim(klim2, kax_z[iz0], kax_a[1], N);
     __syncthreads();
     if (r_tiled) {   // tile-major R: this item's tile is one contiguous block [ia][8]
       const double2* __restrict__ Rt = R + ((long long)ic * ztiles + zt) * N * FFT_TZ;
@@ -365,8 +376,7 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
       for (int r = 0; r < RL; ++r) {
         int ia = bi + r * (N / RL);
         // columns outside the sphere |k| < k_lim hold no binned mode: the last pass skips them, nothing is stored
-        if (bA.has(ia) && !(klim2 > 0.0 && kax_a[ia] * kax_a[ia] + kz2 >= klim2))
-          P[((long long)bA.pos(ia) * nC + ic) * Kzp + iz0 + cc] = u[s][r];
+        if (bA.has(ia) && sidx_abs(ia, N) <= lim) P[((long long)bA.pos(ia) * nC + ic) * Kzp + iz0 + cc] = u[s][r];
       }
     }
   }
@@ -518,8 +528,8 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
     const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
     const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
     if (A.klim2 > 0.0) {   // no binned mode in this (k_o, k_z tile) column: nothing to store or bin (uniform per CTA)
-      const double ko = g.kax[AX == 0 ? 1 : 0][io], kz0 = g.kax[2][iz0];
-      if (ko * ko + kz0 * kz0 >= A.klim2) continue;
+      const int n_o = AX == 0 ? g.ny : g.nx;
+      if (sidx_abs(io, n_o) > sphere_lim(A.klim2, g.kax[2][iz0], g.kax[AX == 0 ? 1 : 0][1], n_o)) continue;
     }
     __syncthreads();
     fft_first<N, 1, false>(tile, tid,

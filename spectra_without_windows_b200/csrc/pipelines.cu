@@ -388,3 +388,28 @@ extern "C" int sww_mas_filter(sww_ctx* c, sww_devptr x, int power, sww_devptr ou
   CHECK_ARENA(c);
   return sww_mas_filter_internal(c, (const double*)x, power, b.spec, (double*)out);
 }
+
+// Mean over the Monte-Carlo realisations of the summed F and q-bar (pk/compute_pk_data.py:227-247, the fold of the per-seed
+// files) and a final symmetrisation, in place on the device -- what remains of SURVEY's K9 once the sum over ranks is done.
+// The sum over ranks itself is ONE all-reduce of n_b^2 + n_b doubles issued by the host through torch.distributed (NCCL):
+// the communicator belongs to the host framework, so libsww does not link NCCL (Boundary).
+__global__ void mc_finalize_kernel(double* __restrict__ F, double* __restrict__ q, int n, double inv) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+    const int i = idx / n, j = idx - i * n;
+    if (i <= j) {
+      const double v = 0.5 * (F[i * n + j] + F[j * n + i]) * inv;
+      F[i * n + j] = v;
+      F[j * n + i] = v;
+    }
+    if (q && idx < n) q[idx] *= inv;
+  }
+}
+
+extern "C" int sww_mc_finalize(sww_ctx* c, sww_devptr fish_sum, sww_devptr qbar_sum, int32_t n_b, int32_t n_realisations) {
+  SWW_REQUIRE(c && fish_sum && n_b > 0 && n_realisations > 0, "mc_finalize: bad argument");
+  mc_finalize_kernel<<<sww_grid_for((long long)n_b * n_b, 256), 256, 0, c->stream>>>((double*)fish_sum, (double*)qbar_sum, n_b,
+                                                                                    1.0 / (double)n_realisations);
+  c->n_own++;
+  SWW_CUDA(cudaGetLastError());
+  return 0;
+}

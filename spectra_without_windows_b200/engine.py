@@ -343,6 +343,12 @@ class Context:
         _lib.check(self.lib.sww_pk_fisher_realisation(self._h, a.data_ptr(), F.data_ptr(), q.data_ptr()))
         return F, q
 
+    def mc_finalize(self, F_sum, q_sum, n_realisations):
+        """Mean over realisations + symmetrisation of the summed Fisher / bias (after the all-reduce), in place."""
+        _lib.check(self.lib.sww_mc_finalize(self._h, F_sum.data_ptr(), 0 if q_sum is None else q_sum.data_ptr(), int(F_sum.shape[0]),
+                                            int(n_realisations)))
+        return F_sum, q_sum
+
     def pk_data_q(self, diff):
         d = self.dev(diff)
         q = self.empty((self.n_b,))

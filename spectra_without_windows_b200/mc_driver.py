@@ -193,8 +193,9 @@ def main(argv):
             F, q, t_loop = pk_device_rng_loop(ctx, shard(range(1, P.N_mc + 1), rank, world), sig_dev, one, inflight if P.wtype == 0 else 1, pipe)
             reduce_sums([F, q], world > 1, dist if world > 1 else None)
         if rank == 0:
-            np.save(P.outdir + "fisher-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (F / P.N_mc).cpu().numpy())
-            np.save(P.outdir + "bias-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), (q / P.N_mc).cpu().numpy())
+            ctx.mc_finalize(F, q, P.N_mc)
+            np.save(P.outdir + "fisher-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), F.cpu().numpy())
+            np.save(P.outdir + "bias-pk_%s%d_%s_%s.npy" % (P.string, P.N_mc, P.weight_type, tag), q.cpu().numpy())
     else:
         n_b = ctx.n_b_bk
         fish_name = lambda r: P.mcdir + "%s%d_%s_bk_fish_alpha_beta_%s.npy" % (P.string, r, P.weight_type, tag)
