@@ -173,7 +173,7 @@ extern "C" int sww_set_fft_backend(sww_ctx* c, int backend) {
   SWW_REQUIRE(c, "null context");
   SWW_REQUIRE(backend == 0 || backend == 1, "unknown FFT backend %d", backend);
   SWW_REQUIRE(!(c->tight_ws && c->ar.base && backend != c->fft_backend), "SWW_TIGHT_WS=1: the FFT backend is fixed once the workspace is bound");
-  if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes (nx,ny in [64,1024], nz in [128,1024])");
+  if (backend == 1) SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two axes (nx, ny in [64,1024], nz in [128,1024]) or axes of at most 640 points");
   c->fft_backend = backend;
   return 0;
 }

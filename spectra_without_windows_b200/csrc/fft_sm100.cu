@@ -27,16 +27,24 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "fft_any.cuh"
 #include "sww_internal.cuh"
 #include "ylm_gen.cuh"
 
 
 static inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
+// an axis runs on the templated power-of-two kernels, or -- any other length up to ANY_MAX_N -- on the run-time radix plans of
+// fft_any.cuh / fft_any_passes.cuh (the reference's production meshes: 258 x 496 x 274, 172 x 330 x 182, 167 x 307 x 175)
+static inline bool col_pow2(int n) { return is_pow2(n) && n >= 64 && n <= 1024; }
+static inline bool z_pow2(int n) { return is_pow2(n) && n >= 128 && n <= 1024; }
+static inline bool any_len(int n) { return n >= 2 && n <= ANY_MAX_N; }
+
 int sww_fft_sm100_supported(const sww_ctx* c) {
   const Geo& g = c->g;
-  auto ok = [](int n) { return is_pow2(n) && n >= 64 && n <= 1024; };
-  return ok(g.nx) && ok(g.ny) && is_pow2(g.nz) && g.nz >= 128 && g.nz <= 1024;
+  if (const char* e = getenv("SWW_NO_ANY_LENGTH"))   // A/B switch: power-of-two meshes only (the other meshes take cuFFT)
+    if (e[0] == '1') return col_pow2(g.nx) && col_pow2(g.ny) && z_pow2(g.nz);
+  return (col_pow2(g.nx) || any_len(g.nx)) && (col_pow2(g.ny) || any_len(g.ny)) && (z_pow2(g.nz) || any_len(g.nz));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1831,10 +1839,14 @@ pass_z32_fused_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const d
   }
 }
 
+#include "fft_any_passes.cuh"
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct Sm100State {
+  AnyPlan plan_x, plan_y, plan_z;   // run-time radix plans of the axes that are not powers of two
+  bool any_x = false, any_y = false, any_z = false;
   double2 *tw_x = nullptr, *tw_y = nullptr, *tw_h = nullptr, *tw_n = nullptr;
   double2* tw_c = nullptr;      // exp(-2 pi i j / nz), j < nz: complex z pass (built on first use)
   double2 *P = nullptr, *Q = nullptr, *R = nullptr;
@@ -1884,10 +1896,16 @@ static int max_abs_idx(const sww_ctx* c, int axis, double kmax) {
 
 int sww_fft_sm100_init(sww_ctx* c) {
   if (c->sm100) return 0;
-  SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two mesh sizes (nx,ny in [64,1024], nz in [128,2048])");
+  SWW_REQUIRE(sww_fft_sm100_supported(c), "the sm_100a FFT passes need power-of-two axes (nx, ny in [64,1024], nz in [128,1024]) or axes of at most %d points", ANY_MAX_N);
   Sm100State* s = new Sm100State();
   const Geo& g = c->g;
   const int H = g.nz / 2;
+  s->any_x = !col_pow2(g.nx);
+  s->any_y = !col_pow2(g.ny);
+  s->any_z = !z_pow2(g.nz);
+  s->plan_x = any_make_plan(g.nx);
+  s->plan_y = any_make_plan(g.ny);
+  s->plan_z = any_make_plan(g.nz);
   auto up = [&](const std::vector<double2>& h, double2** d) -> int {
     SWW_CUDA(cudaMalloc(d, h.size() * sizeof(double2)));
     SWW_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice));
@@ -1897,6 +1915,7 @@ int sww_fft_sm100_init(sww_ctx* c) {
   SWW_TRY(up(make_tw(g.ny, g.ny), &s->tw_y));
   SWW_TRY(up(make_tw(H, H), &s->tw_h));
   SWW_TRY(up(make_tw(g.nz, H + 1), &s->tw_n));
+  if (s->any_z) SWW_TRY(up(make_tw(g.nz, g.nz), &s->tw_c));
   for (int a = 0; a < g.n_k; ++a) {
     s->shell_bx.push_back(max_abs_idx(c, 0, c->h_khi[a]));
     s->shell_by.push_back(max_abs_idx(c, 1, c->h_khi[a]));
@@ -2078,6 +2097,96 @@ static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO
   return 0;
 }
 
+// ---- launchers of the any-length column passes (fft_any_passes.cuh) ----
+static const AnyPlan& plan_of(Sm100State* s, int ax) { return ax == 0 ? s->plan_x : s->plan_y; }
+static bool any_ax(Sm100State* s, int ax) { return ax == 0 ? s->any_x : s->any_y; }
+static int any_occ(size_t smem, int threads) {
+  int o = (int)((227 * 1024) / (smem + 1024));
+  const int by_threads = 1536 / threads;   // resident threads per SM at <= 128 registers ... the kernels use more: cap at 3
+  if (o > by_threads) o = by_threads;
+  if (o > 3) o = 3;
+  if (o < 1) o = 1;
+  return o;
+}
+template <int AX>
+static int launch_i1_any(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* src, int shell,
+                         const GatherBatch& gb, long long pstride, double klim2) {
+  const AnyPlan& pl = plan_of(s, AX);
+  const size_t smem = ANY_SMEM_TILES(pl.n);
+  const int threads = any_threads_for(pl);
+  long long items = (long long)bO.K * ((Kzp + FFT_TZ - 1) / FFT_TZ) * (gb.nb > 0 ? gb.nb : 1);
+  int grid = grid_for_items(items, any_occ(smem, threads));
+  SWW_TRY(set_smem(gpass_i1_kernel<AX>, smem));
+  gpass_i1_kernel<AX><<<grid, threads, smem, c->stream>>>(c->g, pl, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, gb,
+                                                          box_axis_of(c->g.nx, c->g.bx), box_axis_of(c->g.ny, c->g.by), pstride,
+                                                          klim2);
+  return 0;
+}
+template <int AX>
+static int launch_i2_any(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, double2* Qdst, int nb, long long pstride,
+                         long long qstride, int q_tiled, double klim2) {
+  SWW_REQUIRE(!q_tiled, "tile-major planes need power-of-two axes");
+  const AnyPlan& pl = plan_of(s, AX);
+  const size_t smem = ANY_SMEM_TILES(pl.n);
+  const int threads = any_threads_for(pl);
+  long long items = (long long)nF * ((Kzp + FFT_TZ - 1) / FFT_TZ) * nb;
+  int grid = grid_for_items(items, any_occ(smem, threads));
+  SWW_TRY(set_smem(gpass_i2_kernel<AX>, smem));
+  gpass_i2_kernel<AX><<<grid, threads, smem, c->stream>>>(pl, nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride,
+                                                          c->g.kax[AX], c->g.kax[2], klim2);
+  return 0;
+}
+template <int AX>
+static int launch_f2_any(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int nb, long long rstride, long long pstride,
+                         int r_tiled, double klim2) {
+  SWW_REQUIRE(!r_tiled, "tile-major planes need power-of-two axes");
+  const AnyPlan& pl = plan_of(s, AX);
+  const size_t smem = ANY_SMEM_TILES(pl.n);
+  const int threads = any_threads_for(pl);
+  long long items = (long long)nC * ((Kzp + FFT_TZ - 1) / FFT_TZ) * nb;
+  int grid = grid_for_items(items, any_occ(smem, threads));
+  SWW_TRY(set_smem(gpass_f2_kernel<AX>, smem));
+  gpass_f2_kernel<AX><<<grid, threads, smem, c->stream>>>(pl, nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride,
+                                                          c->g.kax[AX], c->g.kax[2], klim2);
+  return 0;
+}
+template <int AX>
+static int launch_f3_any(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, F3Args A,
+                         const double2* Psrc) {
+  const AnyPlan& pl = plan_of(s, AX);
+  const int threads = any_threads_for(pl);
+  const int hist = (mode == 2) ? (threads / 32) * A.n_g * c->g.n_k : 0;
+  const size_t smem = ANY_SMEM_TILES(pl.n) + (size_t)hist * 8;
+  long long items = (long long)bO.K * ((Kzp + FFT_TZ - 1) / FFT_TZ);
+  const int nrows = (mode == 2 && A.nrows > 1) ? A.nrows : 1;
+  int grid = grid_for_items(items * nrows, any_occ(smem, threads));
+  if (nrows > 1) grid = std::max(1, grid / nrows) * nrows;
+  if (mode == 2) {
+    SWW_REQUIRE(nrows <= 16, "F3 bin: too many rows in a batch");
+    SWW_REQUIRE((size_t)grid * A.n_g * c->g.n_k <= c->partial_elems, "F3 bin: partial buffer too small");
+    A.partial = c->d_partial;
+    A.counter = c->d_counter;
+  }
+#define LAUNCH_F3_ANY(MM)                                                                                                  \
+  {                                                                                                                        \
+    SWW_TRY((set_smem(gpass_f3_kernel<AX, MM>, smem)));                                                                    \
+    gpass_f3_kernel<AX, MM><<<grid, threads, smem, c->stream>>>(c->g, pl, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);        \
+  }
+  if (mode == 0) LAUNCH_F3_ANY(0)
+  else if (mode == 1) LAUNCH_F3_ANY(1)
+  else if (mode == 3) LAUNCH_F3_ANY(3)
+  else LAUNCH_F3_ANY(2)
+#undef LAUNCH_F3_ANY
+  return 0;
+}
+// any-length axis: the run-time plan kernels; power-of-two axis: the templated ones
+#define DISPATCH_AX_ANY(s, n, ax, CALL, CALL_ANY)                     \
+  if (any_ax(s, ax)) {                                                \
+    if (ax == 0) { SWW_TRY((CALL_ANY(0))); } else { SWW_TRY((CALL_ANY(1))); } \
+  } else {                                                            \
+    DISPATCH_AX(n, ax, CALL)                                          \
+  }
+
 #define DISPATCH_AX(n, ax, CALL)                                                   \
   switch (n) {                                                                     \
     case 64: if (ax == 0) { SWW_TRY((CALL(64, 0))); } else { SWW_TRY((CALL(64, 1))); } break;       \
@@ -2114,7 +2223,9 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     {
       SWW_PROF(c, a1 == 0 ? "fft.I1 x-inverse (gather)" : "fft.I1 y-inverse (gather)");
 #define CALL(NN, AA) launch_i1<NN, AA>(c, s, b1, b2, Kz, Kzp, src, shell, gb, pstride, klim2)
-      DISPATCH_AX(n1, a1, CALL)
+#define CALL_ANY(AA) launch_i1_any<AA>(c, s, b1, b2, Kz, Kzp, src, shell, gb, pstride, klim2)
+      DISPATCH_AX_ANY(s, n1, a1, CALL, CALL_ANY)
+#undef CALL_ANY
 #undef CALL
       c->n_own++;
       SWW_CUDA(cudaGetLastError());
@@ -2122,7 +2233,9 @@ static int run_inverse_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     {
       SWW_PROF(c, a2 == 0 ? "fft.I2 x-inverse" : "fft.I2 y-inverse");
 #define CALL(NN, AA) launch_i2<NN, AA>(c, s, n1, b2, Kzp, Qdst + (long long)b0 * qstride, nbc, pstride, qstride, q_tiled, klim2)
-      DISPATCH_AX(n2, a2, CALL)
+#define CALL_ANY(AA) launch_i2_any<AA>(c, s, n1, b2, Kzp, Qdst + (long long)b0 * qstride, nbc, pstride, qstride, q_tiled, klim2)
+      DISPATCH_AX_ANY(s, n2, a2, CALL, CALL_ANY)
+#undef CALL_ANY
 #undef CALL
       c->n_own++;
       SWW_CUDA(cudaGetLastError());
@@ -2143,7 +2256,9 @@ static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
   {
     SWW_PROF(c, a1 == 0 ? "fft.F2 x-forward" : "fft.F2 y-forward");
 #define CALL(NN, AA) launch_f2<NN, AA>(c, s, n2, b1, Kzp, nb, rstride, pstride, r_tiled, klim2)
-    DISPATCH_AX(n1, a1, CALL)
+#define CALL_ANY(AA) launch_f2_any<AA>(c, s, n2, b1, Kzp, nb, rstride, pstride, r_tiled, klim2)
+    DISPATCH_AX_ANY(s, n1, a1, CALL, CALL_ANY)
+#undef CALL_ANY
 #undef CALL
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
@@ -2157,7 +2272,9 @@ static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     for (int b = 0; b < nb; ++b) Ax.out_rows[b] = Ab[b].out_row;
     const double2* Psrc = s->P;
 #define CALL(NN, AA) launch_f3<NN, AA>(c, s, mode, b2, b1, Kz, Kzp, Ax, Psrc)
-    DISPATCH_AX(n2, a2, CALL)
+#define CALL_ANY(AA) launch_f3_any<AA>(c, s, mode, b2, b1, Kz, Kzp, Ax, Psrc)
+    DISPATCH_AX_ANY(s, n2, a2, CALL, CALL_ANY)
+#undef CALL_ANY
 #undef CALL
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
@@ -2169,7 +2286,9 @@ static int run_forward_cols(sww_ctx* c, Sm100State* s, const AxisPlan& pl, int K
     const F3Args& Ax = Ab ? Ab[b] : A;
     const double2* Psrc = s->P + (long long)b * pstride;
 #define CALL(NN, AA) launch_f3<NN, AA>(c, s, mode, b2, b1, Kz, Kzp, Ax, Psrc)
-    DISPATCH_AX(n2, a2, CALL)
+#define CALL_ANY(AA) launch_f3_any<AA>(c, s, mode, b2, b1, Kz, Kzp, Ax, Psrc)
+    DISPATCH_AX_ANY(s, n2, a2, CALL, CALL_ANY)
+#undef CALL_ANY
 #undef CALL
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
@@ -2289,6 +2408,28 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   A.N = c->g.N;
   const int H = c->g.nz / 2;
   const bool ylm = A.lm >= 0;
+  if (s->any_z) {
+    SWW_REQUIRE(!(A.q_tile || A.r_tile), "tile-major planes need power-of-two axes");
+    const AnyPlan& pl = s->plan_z;
+    const size_t smem = ANY_SMEM_TILES(pl.n);
+    const int threads = any_threads_for(pl);
+    const long long tiles = ((long long)c->g.nx * c->g.ny + 15) / 16;
+    const int grid = grid_for_items(tiles, any_occ(smem, threads));
+    if (inv && fwd) {
+      SWW_REQUIRE(!ylm, "fused z pass has no Y_lm variant");
+      SWW_TRY((set_smem(gpass_z_kernel<true, true>, smem)));
+      gpass_z_kernel<true, true><<<grid, threads, smem, c->stream>>>(c->g, pl, A, s->tw_c);
+    } else if (inv) {
+      SWW_TRY((set_smem(gpass_z_kernel<true, false>, smem)));
+      gpass_z_kernel<true, false><<<grid, threads, smem, c->stream>>>(c->g, pl, A, s->tw_c);
+    } else {
+      SWW_TRY((set_smem(gpass_z_kernel<false, true>, smem)));
+      gpass_z_kernel<false, true><<<grid, threads, smem, c->stream>>>(c->g, pl, A, s->tw_c);
+    }
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
   const bool no_z16 = env_on("SWW_NO_Z16");
   if (inv && fwd && !ylm && H == Z32_H && A.wmap && A.Kz_out <= 256 && A.Kz_in <= Z32_H + 1 && env_on("SWW_Z32")) {
     // experimental (not yet validated on a GPU): opt-in only
@@ -2384,7 +2525,10 @@ int sww_fft_sm100_c2r(sww_ctx* c, double2* in, double* out) {
 // ---- complex 3-D transforms on the same passes: z (complex, in place) + the two column passes over the full box ----
 int sww_fft_sm100_c2c_supported(const sww_ctx* c) {
   const int nz = c->g.nz;
-  return sww_fft_sm100_supported(c) && (nz == 64 || nz == 128 || nz == 256 || nz == 512);
+  if (!sww_fft_sm100_supported(c)) return 0;
+  if (nz == 128 || nz == 256 || nz == 512) return 1;
+  // any-length z axis: the planes have pitch nz; a ragged last 8-column tile is only handled by the any-length column passes
+  return !z_pow2(nz) && any_len(nz) && (nz % 8 == 0 || (!col_pow2(c->g.nx) && !col_pow2(c->g.ny)));
 }
 
 template <int DIR>
@@ -2392,6 +2536,17 @@ static int run_zc(sww_ctx* c, Sm100State* s, double2* data) {
   SWW_PROF(c, DIR > 0 ? "fft.Zc forward (complex)" : "fft.Zc inverse (complex)");
   const int H = c->g.nz;
   const long long nrows = (long long)c->g.nx * c->g.ny;
+  if (s->any_z) {
+    const AnyPlan& pl = s->plan_z;
+    const size_t smem = ANY_SMEM_TILES(pl.n);
+    const int threads = any_threads_for(pl);
+    const int grid = grid_for_items((nrows + 7) / 8, any_occ(smem, threads));
+    SWW_TRY((set_smem(gpass_zc_kernel<DIR>, smem)));
+    gpass_zc_kernel<DIR><<<grid, threads, smem, c->stream>>>(pl, nrows, data, s->tw_c);
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define M(HH)                                                                                                     \
   {                                                                                                               \
     const size_t smem = (size_t)(WTabSize<HH, false>::value + 8 * (WGeo<HH>::RW * WGeo<HH>::ROWLEN + 8)) * 16;   \
@@ -2418,7 +2573,7 @@ static int run_zc(sww_ctx* c, Sm100State* s, double2* data) {
 int sww_fft_sm100_c2c(sww_ctx* c, const double2* in, double2* out, int inverse) {
   Sm100State* s;
   SWW_TRY(get_state(c, &s));
-  SWW_REQUIRE(sww_fft_sm100_c2c_supported(c), "complex transforms on the sm_100a passes need nz in {64,128,256,512}");
+  SWW_REQUIRE(sww_fft_sm100_c2c_supported(c), "complex transforms on the sm_100a passes: unsupported mesh (power-of-two nz must be 128, 256 or 512)");
   Geo& g = c->g;
   if (!s->tw_c) {
     std::vector<double2> t = make_tw(g.nz, g.nz);

@@ -30,13 +30,14 @@ def oracle_setup(w, which):
     return orc, orc.Setup(w.box, w.grid, w.box_center, w.nbar_r, w.alpha, w.shot_fac, kmin, kmax, dk, lmax)
 
 
-def test_backend_rejects_unsupported_mesh(eng, world):
-    w = world("toyA")
-    mesh = eng.Mesh(w.box, w.grid, w.box_center, *w.pk_bins)
-    ctx = eng.get_context(mesh, 0, ("ops", "pk_fisher", "pk_data"))
-    assert ctx.fft_backend == 0          # auto-selection fell back to cuFFT on a 32x24x20 mesh
+def test_backend_rejects_unsupported_mesh(eng):
+    shape = (700, 16, 16)                # neither a power of two nor within the any-length limit (640)
+    mesh = eng.Mesh(tuple(10.0 * s for s in shape), shape, (0.0, 0.0, 0.0), 0.0, 0.1, 0.05, 0)
+    ctx = eng.Context(mesh, 0, ("ops",))
+    assert ctx.fft_backend == 0          # auto-selection fell back to cuFFT
     with pytest.raises(Exception, match="power-of-two"):
         ctx.set_fft_backend(1)
+    ctx.close()
 
 
 @pytest.mark.parametrize("shape", [(64, 64, 128), (128, 64, 256), (64, 256, 128), (64, 64, 512), (512, 64, 1024),
