@@ -47,6 +47,11 @@ WORKLOADS = {
     # pk data path (paint + q_alpha): config C1 of SURVEY 8d; a step = one catalogue
     "C1": dict(grid=(128, 128, 128), box=(1000.0, 1000.0, 1000.0), box_center=(0.0, 0.0, 2000.0),
                bins=(0.0, 0.25, 0.01, 4), data=True, n_gal=300000, n_ran=15000000),
+    # the reference's production meshes (paramfiles/boss_nC.param:17-33): not powers of two -> any-length passes (fft_any.cuh)
+    "BOSSPK": dict(grid=(258, 496, 274), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
+                   bins=(0.0, 0.41, 0.01, 4)),
+    "BOSSBK": dict(grid=(172, 330, 182), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
+                   bins=(0.0, 0.11, 0.01, 4), bk=True),
     "S256": dict(grid=(256, 256, 256), box=(1800.0, 3450.0, 1900.0), box_center=(1200.0, 0.0, 0.0),
                  bins=(0.0, 0.20, 0.005, 4)),
 }

@@ -16,6 +16,8 @@
 //
 // Compiles for the host as well (tests/test_fft_any_cpu.py builds tools/test_fft_any.cpp against this header).
 #pragma once
+#include <math.h>
+
 #include "fft_core.cuh"
 
 #define ANY_MAX_STAGES 12
@@ -56,6 +58,9 @@ static inline AnyPlan any_make_plan(int n) {
   for (int i = p.ns; i < ANY_MAX_STAGES; ++i) p.R[i] = 1;
   return p;
 }
+
+// dense-radix work of one stage per point, in complex multiply-adds (the row-mesh cost model, rowmesh.cu)
+static inline double any_radix_cost(int R) { return (double)R; }
 
 // work items of stage 0 (4 outputs x 4 columns each): the launchers size the CTA from it
 static inline int any_stage_items(int n, int R) { return ((R + 3) / 4) * (n / R) * 2; }
@@ -112,8 +117,10 @@ FFT_HD void any_stage(const double2* in, double2* out, const double2* tw, int n,
         if (idx[i] >= n) idx[i] -= n;
 #pragma unroll
         for (int c = 0; c < ANY_CB; ++c) {
-          acc[i][c].x += x[c].x * w.x - x[c].y * w.y;
-          acc[i][c].y += x[c].x * w.y + x[c].y * w.x;
+          acc[i][c].x = fma(x[c].x, w.x, acc[i][c].x);   // four FMAs per complex multiply-add (the expression form
+          acc[i][c].x = fma(-x[c].y, w.y, acc[i][c].x);  // compiles to a multiply, an FMA and an add)
+          acc[i][c].y = fma(x[c].x, w.y, acc[i][c].y);
+          acc[i][c].y = fma(x[c].y, w.x, acc[i][c].y);
         }
       }
     }

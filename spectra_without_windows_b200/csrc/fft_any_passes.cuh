@@ -168,7 +168,7 @@ gpass_f2_kernel(AnyPlan pl, int nC, int ny, BoxAxis bA, int Kzp, const double2* 
 
 // ---- last forward pass + epilogue (modes of pass_f3_kernel) ----------------------------------------------------------------
 template <int AX, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ P,
                 const double2* __restrict__ twg, F3Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -360,7 +360,7 @@ gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
 // complex-to-real transform does); forward: X_A[k] = (Z[k] + conj Z[n-k]) / 2, X_B[k] = -i (Z[k] - conj Z[n-k]) / 2.
 // Arguments as in pass_zw_kernel (ZArgs); the real-space step between the two transforms is done in shared memory.
 template <bool INV, bool FWD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gpass_z_kernel(Geo g, AnyPlan pl, ZArgs A, const double2* __restrict__ twg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x, n = pl.n;

@@ -288,14 +288,15 @@ def test_bk_data_c3_full_size():
     ctx.close()
 
 
-def test_bk_fisher_nseries_mesh_cufft_backend():
-    """The mesh of the reference's published Nseries bispectrum outputs, 167 x 307 x 175 (no power of two: cuFFT backend):
-    symmetric, finite, quartic in the fields, and one g-map against an independent torch.fft construction."""
+def test_bk_fisher_nseries_mesh():
+    """The mesh of the reference's published Nseries bispectrum outputs, 167 x 307 x 175 (two prime axes: the any-length
+    passes of csrc/fft_any_passes.cuh): symmetric, finite, quartic in the fields, one g-map against an independent torch.fft
+    construction, and the whole Fisher matrix against the cuFFT backend."""
     import torch as t
     from spectra_without_windows_b200 import engine
     mesh = engine.Mesh((1750.0, 3220.0, 1830.0), (167, 307, 175), (1200.0, 0.0, 0.0), 0.0, 0.11, 0.01, 4)
     ctx = engine.Context(mesh, 0, ("bk_fisher",))
-    assert ctx.fft_backend == 0 and ctx.n_b_bk == 573
+    assert ctx.fft_backend == 1 and ctx.n_b_bk == 573
     dev = ctx.device
     nbar_r = survey_nbar_r([t.from_numpy(a).to(dev) for a in mesh.rax], t).contiguous()
     n = (nbar_r * ALPHA).contiguous()
@@ -318,4 +319,7 @@ def test_bk_fisher_nseries_mesh_cufft_backend():
     assert rel(g_l4, g_ref) < 1e-9
     F2, maps = ctx.bk_fisher_pair(2.0 * aA, 2.0 * aB, maps)
     assert rel(F2, 16.0 * F1) < 1e-12
+    ctx.set_fft_backend(0)
+    F0, maps = ctx.bk_fisher_pair(aA, aB, maps)
+    assert rel(F1, F0) < 1e-11
     ctx.close()
