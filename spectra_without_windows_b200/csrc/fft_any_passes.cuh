@@ -13,6 +13,16 @@
 
 #define ANY_SMEM_TILES(n) ((size_t)(n) * (2 * FFT_LDT + 1) * sizeof(double2))
 
+// 16-byte asynchronous copy global -> shared (LDGSTS); ok == false writes zeros (src-size 0).  All copies of a tile are in
+// flight at once, so the load phase costs one memory latency, not one per element (ncu on the first version: 28 % of the
+// stall samples sat on the shared-memory store behind each dependent global load).
+__device__ __forceinline__ void any_cp16(double2* dst, const double2* src, bool ok) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void any_cp_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
 struct AnyTile {
   double2 *b0, *b1, *tw;
 };
@@ -27,7 +37,7 @@ __device__ __forceinline__ AnyTile any_tile_setup(unsigned char* smem_raw, int n
 
 // ---- first inverse pass (gather) -------------------------------------------------------------------------------------
 template <int AX>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(96)
 gpass_i1_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ src, int shell,
                 const double2* __restrict__ twg, double2* __restrict__ Pbase, GatherBatch gb, BoxAxis cbx, BoxAxis cby,
                 long long pstride, double klim2) {
@@ -98,7 +108,7 @@ gpass_i1_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
 
 // ---- second inverse pass ---------------------------------------------------------------------------------------------
 template <int AX>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(96)
 gpass_i2_kernel(AnyPlan pl, int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Pbase, const double2* __restrict__ twg,
                 double2* __restrict__ Qbase, int nb, long long pstride, long long qstride, const double* __restrict__ kax_a,
                 const double* __restrict__ kax_z, double klim2) {
@@ -119,10 +129,10 @@ gpass_i2_kernel(AnyPlan pl, int nF, int ny, BoxAxis bA, int Kzp, const double2* 
     const int lim = sphere_lim(klim2, kax_z[iz0], kax_a[1], N);
     for (int e = tid; e < N * FFT_TZ; e += nthr) {
       const int ia = e >> 3, cc = e & 7;
-      double2 v = make_double2(0.0, 0.0);
-      if (bA.has(ia) && sidx_abs(ia, N) <= lim && iz0 + cc < Kzp) v = P[((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc];
-      T.b0[ia * FFT_LDT + cc] = v;
+      const bool ok = bA.has(ia) && sidx_abs(ia, N) <= lim && iz0 + cc < Kzp;
+      any_cp16(T.b0 + ia * FFT_LDT + cc, ok ? P + ((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc : P, ok);
     }
+    any_cp_wait();
     __syncthreads();
     const double2* res = any_fft_tile<-1>(T.b0, T.b1, T.tw, pl, tid, nthr);
     for (int e = tid; e < N * FFT_TZ; e += nthr) {
@@ -134,7 +144,7 @@ gpass_i2_kernel(AnyPlan pl, int nF, int ny, BoxAxis bA, int Kzp, const double2* 
 
 // ---- first forward pass ----------------------------------------------------------------------------------------------
 template <int AX>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(96)
 gpass_f2_kernel(AnyPlan pl, int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Rbase, const double2* __restrict__ twg,
                 double2* __restrict__ Pbase, int nb, long long rstride, long long pstride, const double* __restrict__ kax_a,
                 const double* __restrict__ kax_z, double klim2) {
@@ -155,8 +165,10 @@ gpass_f2_kernel(AnyPlan pl, int nC, int ny, BoxAxis bA, int Kzp, const double2* 
     __syncthreads();
     for (int e = tid; e < N * FFT_TZ; e += nthr) {
       const int ia = e >> 3, cc = e & 7;
-      T.b0[ia * FFT_LDT + cc] = iz0 + cc < Kzp ? R[row_of<AX>(ia, ic, ny) * Kzp + iz0 + cc] : make_double2(0.0, 0.0);
+      const bool ok = iz0 + cc < Kzp;
+      any_cp16(T.b0 + ia * FFT_LDT + cc, ok ? R + row_of<AX>(ia, ic, ny) * Kzp + iz0 + cc : R, ok);
     }
+    any_cp_wait();
     __syncthreads();
     const double2* res = any_fft_tile<1>(T.b0, T.b1, T.tw, pl, tid, nthr);
     for (int e = tid; e < bA.K * FFT_TZ; e += nthr) {
@@ -168,7 +180,7 @@ gpass_f2_kernel(AnyPlan pl, int nC, int ny, BoxAxis bA, int Kzp, const double2* 
 
 // ---- last forward pass + epilogue (modes of pass_f3_kernel) ----------------------------------------------------------------
 template <int AX, int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __maxnreg__(96)
 gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ P,
                 const double2* __restrict__ twg, F3Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -198,8 +210,10 @@ gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
     __syncthreads();
     for (int e = tid; e < N * FFT_TZ; e += nthr) {
       const int ia = e >> 3, cc = e & 7;
-      T.b0[ia * FFT_LDT + cc] = iz0 + cc < Kzp ? P[((long long)jo * N + ia) * Kzp + iz0 + cc] : make_double2(0.0, 0.0);
+      const bool ok = iz0 + cc < Kzp;
+      any_cp16(T.b0 + ia * FFT_LDT + cc, ok ? P + ((long long)jo * N + ia) * Kzp + iz0 + cc : P, ok);
     }
+    any_cp_wait();
     __syncthreads();
     const double2* res = any_fft_tile<1>(T.b0, T.b1, T.tw, pl, tid, nthr);
     if (MODE == 3) {
@@ -360,7 +374,7 @@ gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
 // complex-to-real transform does); forward: X_A[k] = (Z[k] + conj Z[n-k]) / 2, X_B[k] = -i (Z[k] - conj Z[n-k]) / 2.
 // Arguments as in pass_zw_kernel (ZArgs); the real-space step between the two transforms is done in shared memory.
 template <bool INV, bool FWD>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __maxnreg__(96)
 gpass_z_kernel(Geo g, AnyPlan pl, ZArgs A, const double2* __restrict__ twg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x, n = pl.n;
@@ -391,19 +405,29 @@ gpass_z_kernel(Geo g, AnyPlan pl, ZArgs A, const double2* __restrict__ twg) {
       double2* oth = T.b1;
       if (INV) {
         const double2* __restrict__ Qp = A.Q + (long long)pb * A.q_stride;
-        for (int k = m0; k < nzh; k += mstep) {
-          double2 xa = make_double2(0.0, 0.0), xb = make_double2(0.0, 0.0);
-          if (k < A.Kz_in) {
-            if (hasA) xa = Qp[rowA * A.Kzp_in + k];
-            if (hasB) xb = Qp[rowB * A.Kzp_in + k];
+        for (int kb = m0; kb < nzh; kb += 4 * mstep) {
+          double2 xa[4], xb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = kb + u * mstep;
+            xa[u] = xb[u] = make_double2(0.0, 0.0);
+            if (k < A.Kz_in) {
+              if (hasA) xa[u] = Qp[rowA * A.Kzp_in + k];
+              if (hasB) xb[u] = Qp[rowB * A.Kzp_in + k];
+            }
           }
-          const bool self = (k == 0) || (2 * k == n);
-          if (self) {
-            xa.y = 0.0;
-            xb.y = 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = kb + u * mstep;
+            if (k >= nzh) continue;
+            const bool self = (k == 0) || (2 * k == n);
+            if (self) {
+              xa[u].y = 0.0;
+              xb[u].y = 0.0;
+            }
+            T.b0[k * FFT_LDT + c] = make_double2(xa[u].x - xb[u].y, xa[u].y + xb[u].x);
+            if (!self) T.b0[(n - k) * FFT_LDT + c] = make_double2(xa[u].x + xb[u].y, xb[u].x - xa[u].y);
           }
-          T.b0[k * FFT_LDT + c] = make_double2(xa.x - xb.y, xa.y + xb.x);
-          if (!self) T.b0[(n - k) * FFT_LDT + c] = make_double2(xa.x + xb.y, xb.x - xa.y);
         }
         __syncthreads();
         double2* res = any_fft_tile<-1>(T.b0, T.b1, T.tw, pl, tid, nthr);
@@ -422,42 +446,56 @@ gpass_z_kernel(Geo g, AnyPlan pl, ZArgs A, const double2* __restrict__ twg) {
         sww_ylm_zpack(lmc, XB, YB, AcB, &oddB);
       }
       const double xy2A = XA * XA + YA * YA, xy2B = XB * XB + YB * YB;
-      for (int m = m0; m < n; m += mstep) {
-        double2 v;
-        if (INV) {
-          v = cur[m * FFT_LDT + c];
-        } else {
-          v.x = hasA ? A.real_in[rowA * n + m] : 0.0;
-          v.y = hasB ? A.real_in[rowB * n + m] : 0.0;
-        }
-        double fa = A.scale, fb = A.scale;
-        if (A.wmap) {
-          fa *= hasA ? A.wmap[rowA * n + m] : 0.0;
-          fb *= hasB ? A.wmap[rowB * n + m] : 0.0;
-        }
-        if (ymap) {
-          const double* ym = A.ymaps + (long long)(lmc - 1) * A.N;
-          fa *= hasA ? ym[rowA * n + m] : 0.0;
-          fb *= hasB ? ym[rowB * n + m] : 0.0;
-        } else if (yfly) {
-          const double Z = g.rax[2][m], w = Z * Z;
-          fa *= sww_ylm_zpacked(deg, AcA, oddA, Z, w, deg ? 1.0 / (xy2A + w) : 1.0);
-          fb *= sww_ylm_zpacked(deg, AcB, oddB, Z, w, deg ? 1.0 / (xy2B + w) : 1.0);
-        }
-        v.x *= fa;
-        v.y *= fb;
-        if (INV && !FWD) {
-          const bool add = A.accumulate || (sum_planes && pb > 0);
-          if (hasA) {
-            double* o = A.real_out + rowA * n + m;
-            *o = add ? *o + v.x : v.x;
+      // four cells per round: every global load of the round is issued before the first dependent use
+      constexpr int U = 4;
+      for (int mb = m0; mb < n; mb += U * mstep) {
+        double2 v[U];
+        double fa[U], fb[U], ya[U], yb[U], oa[U], ob[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int m = mb + u * mstep;
+          const bool in = m < n;
+          fa[u] = fb[u] = A.scale;
+          ya[u] = yb[u] = 1.0;
+          oa[u] = ob[u] = 0.0;
+          v[u] = make_double2(0.0, 0.0);
+          if (!INV) {
+            if (in && hasA) v[u].x = A.real_in[rowA * n + m];
+            if (in && hasB) v[u].y = A.real_in[rowB * n + m];
           }
-          if (hasB) {
-            double* o = A.real_out + rowB * n + m;
-            *o = add ? *o + v.y : v.y;
+          if (A.wmap) {
+            fa[u] *= (in && hasA) ? A.wmap[rowA * n + m] : 0.0;
+            fb[u] *= (in && hasB) ? A.wmap[rowB * n + m] : 0.0;
           }
-        } else {
-          cur[m * FFT_LDT + c] = v;
+          if (ymap) {
+            const double* ym = A.ymaps + (long long)(lmc - 1) * A.N;
+            ya[u] = (in && hasA) ? ym[rowA * n + m] : 0.0;
+            yb[u] = (in && hasB) ? ym[rowB * n + m] : 0.0;
+          }
+          if (INV && !FWD && (A.accumulate || (sum_planes && pb > 0))) {
+            if (in && hasA) oa[u] = A.real_out[rowA * n + m];
+            if (in && hasB) ob[u] = A.real_out[rowB * n + m];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int m = mb + u * mstep;
+          if (m >= n) continue;
+          if (INV) v[u] = cur[m * FFT_LDT + c];
+          double ga = fa[u] * ya[u], gb = fb[u] * yb[u];
+          if (yfly) {
+            const double Z = g.rax[2][m], w = Z * Z;
+            ga *= sww_ylm_zpacked(deg, AcA, oddA, Z, w, deg ? 1.0 / (xy2A + w) : 1.0);
+            gb *= sww_ylm_zpacked(deg, AcB, oddB, Z, w, deg ? 1.0 / (xy2B + w) : 1.0);
+          }
+          v[u].x *= ga;
+          v[u].y *= gb;
+          if (INV && !FWD) {
+            if (hasA) A.real_out[rowA * n + m] = oa[u] + v[u].x;
+            if (hasB) A.real_out[rowB * n + m] = ob[u] + v[u].y;
+          } else {
+            cur[m * FFT_LDT + c] = v[u];
+          }
         }
       }
       if (FWD) {
@@ -477,7 +515,7 @@ gpass_z_kernel(Geo g, AnyPlan pl, ZArgs A, const double2* __restrict__ twg) {
 
 // ---- complex z pass: in-place transforms of 8 contiguous rows of length n ------------------------------------------------
 template <int DIR>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(96)
 gpass_zc_kernel(AnyPlan pl, long long nrows, double2* __restrict__ data, const double2* __restrict__ twg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x, n = pl.n;
@@ -488,8 +526,9 @@ gpass_zc_kernel(AnyPlan pl, long long nrows, double2* __restrict__ data, const d
     for (int e = tid; e < 8 * n; e += nthr) {
       const int c = e / n, k = e - c * n;
       const long long row = tile * 8 + c;
-      T.b0[k * FFT_LDT + c] = row < nrows ? data[row * n + k] : make_double2(0.0, 0.0);
+      any_cp16(T.b0 + k * FFT_LDT + c, row < nrows ? data + row * n + k : data, row < nrows);
     }
+    any_cp_wait();
     __syncthreads();
     const double2* res = any_fft_tile<DIR>(T.b0, T.b1, T.tw, pl, tid, nthr);
     for (int e = tid; e < 8 * n; e += nthr) {

@@ -2100,13 +2100,13 @@ static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO
 // ---- launchers of the any-length column passes (fft_any_passes.cuh) ----
 static const AnyPlan& plan_of(Sm100State* s, int ax) { return ax == 0 ? s->plan_x : s->plan_y; }
 static bool any_ax(Sm100State* s, int ax) { return ax == 0 ? s->any_x : s->any_y; }
-static int any_occ(size_t smem, int threads) {
-  int o = (int)((227 * 1024) / (smem + 1024));
-  const int by_threads = 1536 / threads;   // resident threads per SM at <= 128 registers ... the kernels use more: cap at 3
-  if (o > by_threads) o = by_threads;
-  if (o > 3) o = 3;
-  if (o < 1) o = 1;
-  return o;
+// resident CTAs per SM of one of the any-length kernels (registers, shared memory, threads), from the occupancy API
+template <typename K>
+static int any_occ(K kernel, size_t smem, int threads) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+  if (nb > 8) nb = 8;
+  return nb;
 }
 template <int AX>
 static int launch_i1_any(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* src, int shell,
@@ -2115,8 +2115,8 @@ static int launch_i1_any(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int 
   const size_t smem = ANY_SMEM_TILES(pl.n);
   const int threads = any_threads_for(pl);
   long long items = (long long)bO.K * ((Kzp + FFT_TZ - 1) / FFT_TZ) * (gb.nb > 0 ? gb.nb : 1);
-  int grid = grid_for_items(items, any_occ(smem, threads));
   SWW_TRY(set_smem(gpass_i1_kernel<AX>, smem));
+  int grid = grid_for_items(items, any_occ(gpass_i1_kernel<AX>, smem, threads));
   gpass_i1_kernel<AX><<<grid, threads, smem, c->stream>>>(c->g, pl, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, gb,
                                                           box_axis_of(c->g.nx, c->g.bx), box_axis_of(c->g.ny, c->g.by), pstride,
                                                           klim2);
@@ -2130,8 +2130,8 @@ static int launch_i2_any(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp,
   const size_t smem = ANY_SMEM_TILES(pl.n);
   const int threads = any_threads_for(pl);
   long long items = (long long)nF * ((Kzp + FFT_TZ - 1) / FFT_TZ) * nb;
-  int grid = grid_for_items(items, any_occ(smem, threads));
   SWW_TRY(set_smem(gpass_i2_kernel<AX>, smem));
+  int grid = grid_for_items(items, any_occ(gpass_i2_kernel<AX>, smem, threads));
   gpass_i2_kernel<AX><<<grid, threads, smem, c->stream>>>(pl, nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride,
                                                           c->g.kax[AX], c->g.kax[2], klim2);
   return 0;
@@ -2144,8 +2144,8 @@ static int launch_f2_any(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp,
   const size_t smem = ANY_SMEM_TILES(pl.n);
   const int threads = any_threads_for(pl);
   long long items = (long long)nC * ((Kzp + FFT_TZ - 1) / FFT_TZ) * nb;
-  int grid = grid_for_items(items, any_occ(smem, threads));
   SWW_TRY(set_smem(gpass_f2_kernel<AX>, smem));
+  int grid = grid_for_items(items, any_occ(gpass_f2_kernel<AX>, smem, threads));
   gpass_f2_kernel<AX><<<grid, threads, smem, c->stream>>>(pl, nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride,
                                                           c->g.kax[AX], c->g.kax[2], klim2);
   return 0;
@@ -2159,17 +2159,17 @@ static int launch_f3_any(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxi
   const size_t smem = ANY_SMEM_TILES(pl.n) + (size_t)hist * 8;
   long long items = (long long)bO.K * ((Kzp + FFT_TZ - 1) / FFT_TZ);
   const int nrows = (mode == 2 && A.nrows > 1) ? A.nrows : 1;
-  int grid = grid_for_items(items * nrows, any_occ(smem, threads));
-  if (nrows > 1) grid = std::max(1, grid / nrows) * nrows;
-  if (mode == 2) {
-    SWW_REQUIRE(nrows <= 16, "F3 bin: too many rows in a batch");
-    SWW_REQUIRE((size_t)grid * A.n_g * c->g.n_k <= c->partial_elems, "F3 bin: partial buffer too small");
-    A.partial = c->d_partial;
-    A.counter = c->d_counter;
-  }
 #define LAUNCH_F3_ANY(MM)                                                                                                  \
   {                                                                                                                        \
     SWW_TRY((set_smem(gpass_f3_kernel<AX, MM>, smem)));                                                                    \
+    int grid = grid_for_items(items * nrows, any_occ(gpass_f3_kernel<AX, MM>, smem, threads));                             \
+    if (nrows > 1) grid = std::max(1, grid / nrows) * nrows;                                                               \
+    if (MM == 2) {                                                                                                         \
+      SWW_REQUIRE(nrows <= 16, "F3 bin: too many rows in a batch");                                                        \
+      SWW_REQUIRE((size_t)grid * A.n_g * c->g.n_k <= c->partial_elems, "F3 bin: partial buffer too small");               \
+      A.partial = c->d_partial;                                                                                            \
+      A.counter = c->d_counter;                                                                                            \
+    }                                                                                                                      \
     gpass_f3_kernel<AX, MM><<<grid, threads, smem, c->stream>>>(c->g, pl, bA, bO, Kz, Kzp, Psrc, tw_of(s, AX), A);        \
   }
   if (mode == 0) LAUNCH_F3_ANY(0)
@@ -2414,18 +2414,21 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
     const size_t smem = ANY_SMEM_TILES(pl.n);
     const int threads = any_threads_for(pl);
     const long long tiles = ((long long)c->g.nx * c->g.ny + 15) / 16;
-    const int grid = grid_for_items(tiles, any_occ(smem, threads));
+#define LAUNCH_Z_ANY(II, FF)                                                                              \
+  {                                                                                                       \
+    SWW_TRY((set_smem(gpass_z_kernel<II, FF>, smem)));                                                    \
+    const int grid = grid_for_items(tiles, any_occ(gpass_z_kernel<II, FF>, smem, threads));               \
+    gpass_z_kernel<II, FF><<<grid, threads, smem, c->stream>>>(c->g, pl, A, s->tw_c);                     \
+  }
     if (inv && fwd) {
       SWW_REQUIRE(!ylm, "fused z pass has no Y_lm variant");
-      SWW_TRY((set_smem(gpass_z_kernel<true, true>, smem)));
-      gpass_z_kernel<true, true><<<grid, threads, smem, c->stream>>>(c->g, pl, A, s->tw_c);
+      LAUNCH_Z_ANY(true, true)
     } else if (inv) {
-      SWW_TRY((set_smem(gpass_z_kernel<true, false>, smem)));
-      gpass_z_kernel<true, false><<<grid, threads, smem, c->stream>>>(c->g, pl, A, s->tw_c);
+      LAUNCH_Z_ANY(true, false)
     } else {
-      SWW_TRY((set_smem(gpass_z_kernel<false, true>, smem)));
-      gpass_z_kernel<false, true><<<grid, threads, smem, c->stream>>>(c->g, pl, A, s->tw_c);
+      LAUNCH_Z_ANY(false, true)
     }
+#undef LAUNCH_Z_ANY
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
     return 0;
@@ -2540,8 +2543,8 @@ static int run_zc(sww_ctx* c, Sm100State* s, double2* data) {
     const AnyPlan& pl = s->plan_z;
     const size_t smem = ANY_SMEM_TILES(pl.n);
     const int threads = any_threads_for(pl);
-    const int grid = grid_for_items((nrows + 7) / 8, any_occ(smem, threads));
     SWW_TRY((set_smem(gpass_zc_kernel<DIR>, smem)));
+    const int grid = grid_for_items((nrows + 7) / 8, any_occ(gpass_zc_kernel<DIR>, smem, threads));
     gpass_zc_kernel<DIR><<<grid, threads, smem, c->stream>>>(pl, nrows, data, s->tw_c);
     c->n_own++;
     SWW_CUDA(cudaGetLastError());

@@ -28,7 +28,7 @@ double test(int n, int nthr) {
   double2 *a = b0.data(), *b = b1.data();
   int Ns = 1;
   for (int s = 0; s < pl.ns; ++s) {
-    for (int tid = 0; tid < nthr; ++tid) any_stage<DIR>(a, b, tw.data(), n, pl.R[s], Ns, tid, nthr);
+    for (int tid = 0; tid < nthr; ++tid) any_stage_auto<DIR>(a, b, tw.data(), n, pl.R[s], Ns, tid, nthr);
     Ns *= pl.R[s];
     std::swap(a, b);
   }
