@@ -64,7 +64,7 @@ static inline AnyPlan any_make_plan(int n) {
 }
 
 // dense-radix work of one stage per point, in complex multiply-adds (the row-mesh cost model, rowmesh.cu)
-static inline double any_radix_cost(int R) { return (R & 1) ? 0.5 * R : (double)R; }
+static inline double any_radix_cost(int R) { return (R & 1) ? 0.5 * R : 2.0; }
 
 // Register tiles of a work item.  ncu on the first version (4 x 4 plain, 4 x 2 symmetric; profiles/r2q) showed the passes
 // latency-bound at 8-10 warps per SM -- shared memory holds one or two CTAs and a tile only has n * 8 / 16 items -- with the
@@ -78,6 +78,7 @@ static inline double any_radix_cost(int R) { return (R & 1) ? 0.5 * R : (double)
 // work items of a stage
 static inline int any_stage_items(int n, int R) {
   if (R & 1) return (((R - 1) / 2 + ANY_SQB - 1) / ANY_SQB) * (n / R) * (FFT_TZ / ANY_SCB);
+  if (R == 2 || R == 4) return (n / R) * (FFT_TZ / 2);
   return ((R + ANY_QB - 1) / ANY_QB) * (n / R) * (FFT_TZ / ANY_CB);
 }
 
@@ -152,7 +153,7 @@ FFT_HD void any_stage(const double2* in, double2* out, const double2* tw, int n,
 }
 
 // Odd radix R, symmetric form.  item = (block of 4 output pairs q / R-q, sub-transform j, 2 columns).
-template <int DIR>
+template <int DIR, bool TWID>
 FFT_HD void any_stage_sym(const double2* in, double2* out, const double2* tw, int n, int R, int Ns, int tid, int nthr) {
   constexpr int NCB = FFT_TZ / ANY_SCB;
   const int m = n / R, h = (R - 1) / 2, nqb = (h + ANY_SQB - 1) / ANY_SQB;
@@ -180,7 +181,7 @@ FFT_HD void any_stage_sym(const double2* in, double2* out, const double2* tw, in
     for (int r = 1; r <= h; ++r) {
       double2 s[ANY_SCB], d[ANY_SCB];
       double2 tl = double2{1.0, 0.0}, th = double2{1.0, 0.0};
-      if (kt) {
+      if (TWID) {
         tl = tw[ilo];
         th = tw[ihi];
         if (DIR < 0) {
@@ -195,7 +196,7 @@ FFT_HD void any_stage_sym(const double2* in, double2* out, const double2* tw, in
 #pragma unroll
       for (int c = 0; c < ANY_SCB; ++c) {
         double2 a = xlo[c], b = xhi[c];
-        if (kt) {
+        if (TWID) {
           a = c_mul(a, tl);
           b = c_mul(b, th);
         }
@@ -247,13 +248,54 @@ FFT_HD void any_stage_sym(const double2* in, double2* out, const double2* tw, in
   }
 }
 
-// one stage: the symmetric form for odd radices, the plain form for 2 and 4
+// Radix 2 and 4 as butterflies (no multiplications inside the DFT): item = (sub-transform j, 2 columns)
+template <int DIR, int R>
+FFT_HD void any_stage_bfly(const double2* in, double2* out, const double2* tw, int n, int Ns, int tid, int nthr) {
+  constexpr int CB = 2, NCB = FFT_TZ / CB;
+  const int m = n / R;
+  const int total = m * NCB;
+  const int tstep = n / (Ns * R);
+  for (int it = tid; it < total; it += nthr) {
+    const int cb = it % NCB, j = it / NCB;
+    const int k = j % Ns, kt = k * tstep;
+    double2 w[R];
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+      w[r] = tw[r * kt];               // r kt < n
+      if (DIR < 0) w[r].y = -w[r].y;
+    }
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      double2 u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) u[r] = in[(j + r * m) * FFT_LDT + cb * CB + c];
+      if (Ns > 1) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) u[r] = c_mul(u[r], w[r]);
+      }
+      dftR<R, DIR>(u);
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[(j0 + r * Ns) * FFT_LDT + cb * CB + c] = u[r];
+    }
+  }
+}
+
+// one stage: the symmetric form for odd radices, butterflies for 2 and 4 (the plain dense form serves any other even radix)
 template <int DIR>
 FFT_HD void any_stage_auto(const double2* in, double2* out, const double2* tw, int n, int R, int Ns, int tid, int nthr) {
-  if (R & 1)
-    any_stage_sym<DIR>(in, out, tw, n, R, Ns, tid, nthr);
-  else
+  if (R & 1) {
+    if (Ns == 1)
+      any_stage_sym<DIR, false>(in, out, tw, n, R, Ns, tid, nthr);
+    else
+      any_stage_sym<DIR, true>(in, out, tw, n, R, Ns, tid, nthr);
+  } else if (R == 4) {
+    any_stage_bfly<DIR, 4>(in, out, tw, n, Ns, tid, nthr);
+  } else if (R == 2) {
+    any_stage_bfly<DIR, 2>(in, out, tw, n, Ns, tid, nthr);
+  } else {
     any_stage<DIR>(in, out, tw, n, R, Ns, tid, nthr);
+  }
 }
 
 #ifdef __CUDACC__
