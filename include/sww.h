@@ -68,11 +68,13 @@ int sww_launch_counts(sww_ctx* c, uint64_t* own_kernels, uint64_t* fft_calls);
  * enable != 0 starts a fresh recording; the report is a text table (name, launches, ms). */
 int sww_profile_enable(sww_ctx* c, int enable);
 int sww_profile_report(sww_ctx* c, char* buf, uint64_t buf_bytes);
-/* choose the FFT backend: 0 = cuFFT, 1 = hand-written sm_100a passes (power-of-two meshes) */
+/* choose the FFT backend: 0 = cuFFT, 1 = hand-written sm_100a passes (power-of-two axes, or any axis of <= 640 points) */
 int sww_set_fft_backend(sww_ctx* c, int backend);
 /* Coarse row mesh of the P_l(k) Fisher rows (the n_b evaluations of applyC_alpha_single,
  * src/covariances_pk.py:404-466, that pk/compute_pk_randoms.py:220-275 loops over): the band-limited products
- * are evaluated exactly on the smallest power-of-two grid M_i >= 2 (2 b_i + 1), b_i = largest binned mode index.
+ * are evaluated exactly on a grid chosen per axis -- the mesh's own length, or the smallest power of two
+ * M_i >= 2 (2 b_i + 1), b_i = largest binned mode index, which may be smaller OR larger than the mesh (an axis length with
+ * a large prime factor: the weight map's n-periodic spectrum turns the cyclic convolution into a linear one).
  * grid[3] receives M (zeros when the rows run on the full mesh; SWW_ROW_MESH=0 disables it). */
 int sww_row_mesh(sww_ctx* c, int32_t grid[3]);
 
