@@ -126,7 +126,7 @@ gpass_i2_kernel(AnyPlan pl, int nF, int ny, BoxAxis bA, int Kzp, const double2* 
     const int f = (int)(it / ztiles), zt = (int)(it - (long long)f * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    const int lim = sphere_lim(klim2, kax_z[iz0], kax_a[1], N);
+    const int lim = klim2 > 0.0 ? sphere_lim(klim2, kax_z[iz0], kax_a[1], N) : N;
     for (int e = tid; e < N * FFT_TZ; e += nthr) {
       const int ia = e >> 3, cc = e & 7;
       const bool ok = bA.has(ia) && sidx_abs(ia, N) <= lim && iz0 + cc < Kzp;
@@ -161,7 +161,7 @@ gpass_f2_kernel(AnyPlan pl, int nC, int ny, BoxAxis bA, int Kzp, const double2* 
     double2* __restrict__ P = Pbase + (long long)bat * pstride;
     const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
-    const int lim = sphere_lim(klim2, kax_z[iz0], kax_a[1], N);
+    const int lim = klim2 > 0.0 ? sphere_lim(klim2, kax_z[iz0], kax_a[1], N) : N;
     __syncthreads();
     for (int e = tid; e < N * FFT_TZ; e += nthr) {
       const int ia = e >> 3, cc = e & 7;

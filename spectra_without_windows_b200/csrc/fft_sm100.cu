@@ -24,6 +24,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "fft_core.cuh"
@@ -176,6 +179,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   } while (!done);
 }
 
+// resident CTAs per SM the column-pass launchers size their persistent grids for (occ_for: shared memory allows 4 / 2 / 1 at
+// N <= 256 / 512 / 1024): the register allocation is held to it -- without the bound the N = 256 instantiations grew from 102 to
+// 192-220 registers when the sphere predicates were added, two CTAs fitted where the grid expected four, and the bispectrum
+// passes ran 30 % longer (bisected on C4, profiles/r2y)
+#define COL_MINB(N) ((N) <= 256 ? 4 : ((N) == 512 ? 2 : 1))
 #define FFT_LAST_RADIX(N, REV) (PlanRadix<N, REV, FftPlan<N>::NS - 1>::value)
 #define FFT_MID(N, DIR, REV, tile, tw, tid) \
   MidStages<N, DIR, REV, 1, PlanRadix<N, REV, 0>::value>::run(tile, tw, tid)
@@ -214,7 +222,7 @@ __device__ __forceinline__ long long row_of(int a, int o, int ny) {
 // First inverse pass.  Source: spectrum [nx][ny][nzh] restricted to the box; optional shell filter.
 // item = (jo, z-tile).  Rows outside the box are never read.
 template <int N, int AX>
-__global__ void __launch_bounds__(N / 2)
+__global__ void __launch_bounds__(N / 2, COL_MINB(N))
 pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __restrict__ src, int shell,
                const double2* __restrict__ twg, double2* __restrict__ Pbase, GatherBatch gb, BoxAxis cbx, BoxAxis cby,
                long long pstride, double klim2) {
@@ -296,7 +304,7 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
 
 // Second inverse pass (axis AX, box bA): P[ja][f][iz] -> Q[row][iz]; item = (f, z-tile), f < nF
 template <int N, int AX>
-__global__ void __launch_bounds__(N / 2)
+__global__ void __launch_bounds__(N / 2, COL_MINB(N))
 pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Pbase, const double2* __restrict__ twg,
                double2* __restrict__ Qbase, int nb, long long pstride, long long qstride, int q_tiled,
                const double* __restrict__ kax_a, const double* __restrict__ kax_z, double klim2) {
@@ -318,7 +326,7 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
     const int f = (int)(it / ztiles), zt = (int)(it - (long long)f * ztiles);
     const int iz0 = zt * FFT_TZ;
     __syncthreads();
-    const int lim = sphere_lim(klim2, kax_z[iz0], kax_a[1], N);
+    const int lim = klim2 > 0.0 ? sphere_lim(klim2, kax_z[iz0], kax_a[1], N) : N;   // uniform branch: no table loads without pruning
     fft_first<N, -1, false>(tile, tid, [&](int ia, int cc) {
       double2 v = make_double2(0.0, 0.0);
       // columns outside the sphere |k| < k_lim were skipped by the first pass: they are zero, not stored
@@ -345,7 +353,7 @@ pass_i2_kernel(int nF, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
 
 // First forward column pass (axis AX, box bA): R[row][iz] -> P[ja][c][iz] (box rows only); item = (c, z-tile), c < nC
 template <int N, int AX>
-__global__ void __launch_bounds__(N / 2)
+__global__ void __launch_bounds__(N / 2, COL_MINB(N))
 pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ Rbase, const double2* __restrict__ twg,
                double2* __restrict__ Pbase, int nb, long long rstride, long long pstride, int r_tiled,
                const double* __restrict__ kax_a, const double* __restrict__ kax_z, double klim2) {
@@ -366,7 +374,7 @@ pass_f2_kernel(int nC, int ny, BoxAxis bA, int Kzp, const double2* __restrict__ 
     double2* __restrict__ P = Pbase + (long long)bat * pstride;
     const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
-    const int lim = sphere_lim(klim2, kax_z[iz0], kax_a[1], N);
+    const int lim = klim2 > 0.0 ? sphere_lim(klim2, kax_z[iz0], kax_a[1], N) : N;   // uniform branch: no table loads without pruning
     __syncthreads();
     if (r_tiled) {   // tile-major R: this item's tile is one contiguous block [ia][8]
       const double2* __restrict__ Rt = R + ((long long)ic * ztiles + zt) * N * FFT_TZ;
@@ -1997,6 +2005,27 @@ static int occ_for(size_t smem) {
   if (o > 4) o = 4;
   return o;
 }
+// resident CTAs per SM of a column-pass kernel as the device will actually schedule it (registers included), at most what the
+// shared memory allows (occ_for): the persistent grids are sized from this, so a register count that drifts past a threshold
+// costs occupancy but never a second, partial wave
+static std::mutex g_occ_mutex;
+static std::map<std::tuple<const void*, int, size_t>, int> g_occ_cache;
+template <typename K>
+static int occ_of(K kernel, int threads, size_t smem) {
+  const auto key = std::make_tuple((const void*)kernel, threads, smem);
+  {
+    std::lock_guard<std::mutex> lk(g_occ_mutex);
+    auto it = g_occ_cache.find(key);
+    if (it != g_occ_cache.end()) return it->second;
+  }
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+  const int cap = occ_for(smem);
+  nb = nb < cap ? nb : cap;
+  std::lock_guard<std::mutex> lk(g_occ_mutex);
+  g_occ_cache[key] = nb;
+  return nb;
+}
 
 // ---- column-pass launchers, generic in the transformed axis -------------------------------------
 static BoxAxis box_axis_of(int n, int b) {
@@ -2025,8 +2054,8 @@ static int launch_i1(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int Kz, 
                      const GatherBatch& gb, long long pstride, double klim2) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)bO.K * (Kzp / FFT_TZ) * (gb.nb > 0 ? gb.nb : 1);
-  int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i1_kernel<N, AX>, smem));
+  int grid = grid_for_items(items, occ_of(pass_i1_kernel<N, AX>, N / 2, smem));
   pass_i1_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(c->g, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, gb,
                                                          box_axis_of(c->g.nx, c->g.bx), box_axis_of(c->g.ny, c->g.by),
                                                          pstride, klim2);
@@ -2037,8 +2066,8 @@ static int launch_i2(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp, dou
                      long long qstride, int q_tiled, double klim2) {
   size_t smem = col_smem(N, 0);
   long long items = (long long)nF * (Kzp / FFT_TZ) * nb;
-  int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_i2_kernel<N, AX>, smem));
+  int grid = grid_for_items(items, occ_of(pass_i2_kernel<N, AX>, N / 2, smem));
   pass_i2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride, q_tiled,
                                                          c->g.kax[AX], c->g.kax[2], klim2);
   return 0;
@@ -2060,8 +2089,8 @@ static int launch_f2(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp, int
       return 0;
     }
   }
-  int grid = grid_for_items(items, occ_for(smem));
   SWW_TRY(set_smem(pass_f2_kernel<N, AX>, smem));
+  int grid = grid_for_items(items, occ_of(pass_f2_kernel<N, AX>, N / 2, smem));
   pass_f2_kernel<N, AX><<<grid, N / 2, smem, c->stream>>>(nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride, r_tiled,
                                                          c->g.kax[AX], c->g.kax[2], klim2);
   return 0;
@@ -2073,7 +2102,12 @@ static int launch_f3(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO
   size_t smem = col_smem(N, hist);
   long long items = (long long)bO.K * (Kzp / FFT_TZ);
   const int nrows = (mode == 2 && A.nrows > 1) ? A.nrows : 1;
-  int grid = grid_for_items(items * nrows, occ_for(smem));
+  int occ = occ_for(smem);
+  if (mode == 0) { SWW_TRY(set_smem(pass_f3_kernel<N, AX, 0>, smem)); occ = occ_of(pass_f3_kernel<N, AX, 0>, N / 2, smem); }
+  else if (mode == 1) { SWW_TRY(set_smem(pass_f3_kernel<N, AX, 1>, smem)); occ = occ_of(pass_f3_kernel<N, AX, 1>, N / 2, smem); }
+  else if (mode == 3) { SWW_TRY(set_smem(pass_f3_kernel<N, AX, 3>, smem)); occ = occ_of(pass_f3_kernel<N, AX, 3>, N / 2, smem); }
+  else { SWW_TRY(set_smem(pass_f3_kernel<N, AX, 2>, smem)); occ = occ_of(pass_f3_kernel<N, AX, 2>, N / 2, smem); }
+  int grid = grid_for_items(items * nrows, occ);
   if (nrows > 1) grid = std::max(1, grid / nrows) * nrows;
   if (mode == 2) {
     SWW_REQUIRE(nrows <= 16, "F3 bin: too many rows in a batch");
@@ -2154,7 +2188,9 @@ template <int AX>
 static int launch_f3_any(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, F3Args A,
                          const double2* Psrc) {
   const AnyPlan& pl = plan_of(s, AX);
-  const int threads = any_threads_for(pl);
+  int threads = any_threads_for(pl);
+  // MODE 2 keeps one histogram per warp behind the tiles: fewer warps when the two do not fit the SM's shared memory
+  while (mode == 2 && threads > 64 && ANY_SMEM_TILES(pl.n) + (size_t)(threads / 32) * A.n_g * c->g.n_k * 8 > 220 * 1024) threads -= 32;
   const int hist = (mode == 2) ? (threads / 32) * A.n_g * c->g.n_k : 0;
   const size_t smem = ANY_SMEM_TILES(pl.n) + (size_t)hist * 8;
   long long items = (long long)bO.K * ((Kzp + FFT_TZ - 1) / FFT_TZ);
