@@ -607,7 +607,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--fft", type=int, default=-1, help="FFT backend: 0 cuFFT, 1 hand-written sm_100a passes (default: auto = 1 on power-of-two meshes)")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--inflight", type=int, default=3,
                     help="independent realisations in flight per GPU (one context + stream each): the tail of one "
                          "realisation's kernels overlaps the next one's; 1 = strictly one after the other")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -15,7 +15,7 @@ every Monte-Carlo seed's g / g~ maps feed their 1-field sums straight from the F
 rank 0 writes the `bk_*.txt` files compute_bk_data.py would write.  The `*_bk_bias_alpha_*.npz` files of the reference's
 contract are written asynchronously (complex64, like the reference) unless `--no-bias-maps`.
 
-`--inflight K` (default 2, P_l(k) with device-generated fields): K realisations are kept in flight per GPU, each on
+`--inflight K` (default 3, P_l(k) with device-generated fields): K realisations are kept in flight per GPU, each on
 its own context and stream, as far as the device memory holds K workspaces.
 `--per-seed` also writes the reference's per-seed checkpoint files, and seeds whose files already
 exist are skipped (the reference's idempotent re-entry, pk/compute_pk_randoms.py:121-127).
@@ -137,7 +137,7 @@ def main(argv):
     spec, paramfile = argv[1], argv[2]
     per_seed = "--per-seed" in argv
     host_rng = "--host-rng" in argv
-    inflight = int(argv[argv.index("--inflight") + 1]) if "--inflight" in argv else 2
+    inflight = int(argv[argv.index("--inflight") + 1]) if "--inflight" in argv else 3
     data_sims = [int(v) for v in argv[argv.index("--data") + 1].split(",")] if "--data" in argv else []
     write_maps = "--no-bias-maps" not in argv
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
