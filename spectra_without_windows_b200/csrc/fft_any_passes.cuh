@@ -485,8 +485,8 @@ gpass_z_kernel(Geo g, AnyPlan pl, ZArgs A, const double2* __restrict__ twg) {
           double ga = fa[u] * ya[u], gb = fb[u] * yb[u];
           if (yfly) {
             const double Z = g.rax[2][m], w = Z * Z;
-            ga *= sww_ylm_zpacked(deg, AcA, oddA, Z, w, deg ? 1.0 / (xy2A + w) : 1.0);
-            gb *= sww_ylm_zpacked(deg, AcB, oddB, Z, w, deg ? 1.0 / (xy2B + w) : 1.0);
+            ga *= sww_ylm_zpacked(deg, AcA, oddA, Z, w, deg ? sww_rcp_pos(xy2A + w) : 1.0);
+            gb *= sww_ylm_zpacked(deg, AcB, oddB, Z, w, deg ? sww_rcp_pos(xy2B + w) : 1.0);
           }
           v[u].x *= ga;
           v[u].y *= gb;

@@ -785,6 +785,18 @@ template <> struct WPlan<512> { static constexpr int NS = 3; static constexpr in
 
 __device__ __forceinline__ int zpad(int i) { return i + (i >> 3); }
 
+// 1 / x for a positive, normal x (r^2 of a mesh cell) to 1-2 ulp: hardware seed (20 bits) + two Newton steps -- five instructions
+// against the ~25 of the IEEE division sequence with its special-case branches (ncu on the forward z pass: FSEL + BRA + BSSY/BSYNC
+// of those sequences were 17 % of the instructions).  The harmonics are compared with the reference at 1e-12.
+__device__ __forceinline__ double sww_rcp_pos(double x) {
+  double q;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(x));
+  double e = fma(-x, q, 1.0);
+  q = fma(q, e, q);
+  e = fma(-x, q, 1.0);
+  return fma(q, e, q);
+}
+
 // 1 / (1e-12 + sqrt(r2))  (pk/compute_pk_randoms.py:166) through one reciprocal square root:
 // 1/(e + r) = rs (1 - e rs + O((e rs)^2)), rs = 1/r; e rs <= 1e-12/|r| so the dropped term is < 1e-24.
 __device__ __forceinline__ double inv_norm_eps(double r2) {
@@ -1106,8 +1118,8 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
                 const int m = bi + r * BPS;
                 const double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
                 const double w0 = Z0 * Z0, w1 = Z1 * Z1;
-                f0 = sww_ylm_zpacked(deg, Ac, odd, Z0, w0, deg ? 1.0 / (xy2 + w0) : 1.0);
-                f1 = sww_ylm_zpacked(deg, Ac, odd, Z1, w1, deg ? 1.0 / (xy2 + w1) : 1.0);
+                f0 = sww_ylm_zpacked(deg, Ac, odd, Z0, w0, deg ? sww_rcp_pos(xy2 + w0) : 1.0);
+                f1 = sww_ylm_zpacked(deg, Ac, odd, Z1, w1, deg ? sww_rcp_pos(xy2 + w1) : 1.0);
               }
               acc[s][r].x += f0 * u[s][r].x;
               acc[s][r].y += f1 * u[s][r].y;
@@ -1168,8 +1180,8 @@ pass_zw_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2*
           const int m = bi + r * BPS;
           const double Z0 = g.rax[2][2 * m], Z1 = g.rax[2][2 * m + 1];
           const double w0 = Z0 * Z0, w1 = Z1 * Z1;
-          f0 *= sww_ylm_zpacked(deg, Ac, odd, Z0, w0, deg ? 1.0 / (xy2 + w0) : 1.0);
-          f1 *= sww_ylm_zpacked(deg, Ac, odd, Z1, w1, deg ? 1.0 / (xy2 + w1) : 1.0);
+          f0 *= sww_ylm_zpacked(deg, Ac, odd, Z0, w0, deg ? sww_rcp_pos(xy2 + w0) : 1.0);
+          f1 *= sww_ylm_zpacked(deg, Ac, odd, Z1, w1, deg ? sww_rcp_pos(xy2 + w1) : 1.0);
         }
         u[s][r].x *= f0;
         u[s][r].y *= f1;
