@@ -2579,7 +2579,8 @@ int sww_fft_sm100_c2c_supported(const sww_ctx* c) {
   if (!sww_fft_sm100_supported(c)) return 0;
   if (nz == 128 || nz == 256 || nz == 512) return 1;
   // any-length z axis: the planes have pitch nz; a ragged last 8-column tile is only handled by the any-length column passes
-  return !z_pow2(nz) && any_len(nz) && (nz % 8 == 0 || (!col_pow2(c->g.nx) && !col_pow2(c->g.ny)));
+  // (power-of-two x / y axes of at most ANY_MAX_N points are sent through them for such a mesh)
+  return !z_pow2(nz) && any_len(nz) && (nz % 8 == 0 || (any_len(c->g.nx) && any_len(c->g.ny)));
 }
 
 template <int DIR>
@@ -2638,6 +2639,8 @@ int sww_fft_sm100_c2c(sww_ctx* c, const double2* in, double2* out, int inverse) 
   double2* save_R = s->R;
   g.nzh = g.nz;
   s->buf_elems = 3 * save_elems;
+  const bool save_ax = s->any_x, save_ay = s->any_y;
+  if (s->any_z && g.nz % 8 != 0) s->any_x = s->any_y = true;   // ragged last z tile: any-length column passes on every axis
   AxisPlan pl = make_plan(g, full_axis(g.nx), full_axis(g.ny));
   const int Kz = g.nz, Kzp = g.nz;
   int rc = 0;
@@ -2655,6 +2658,8 @@ int sww_fft_sm100_c2c(sww_ctx* c, const double2* in, double2* out, int inverse) 
   g.nzh = save_nzh;
   s->buf_elems = save_elems;
   s->R = save_R;
+  s->any_x = save_ax;
+  s->any_y = save_ay;
   return rc;
 }
 
