@@ -45,14 +45,12 @@ gpass_i1_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
   const int tid = threadIdx.x, nthr = blockDim.x, N = pl.n;
   AnyTile T = any_tile_setup(smem_raw, N, twg, tid, nthr);
   const int ztiles = (Kzp + FFT_TZ - 1) / FFT_TZ;   // a ragged last tile is allowed here (complex transforms: pitch nz)
-  const long long per = (long long)bO.K * ztiles;
-  const long long items = per * (gb.nb > 0 ? gb.nb : 1);
-  for (long long it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
-    const int bat = (int)(it0 / per);
-    const long long it = it0 - (long long)bat * per;
+  const unsigned per = (unsigned)bO.K * ztiles, items = per * (gb.nb > 0 ? gb.nb : 1);
+  for (unsigned it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
+    const unsigned bat = it0 / per, it = it0 - bat * per;
     const GatherArgs& ga = gb.ga[bat];
     double2* __restrict__ P = Pbase + (long long)bat * pstride;
-    const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
+    const int jo = (int)(it / ztiles), zt = (int)(it - (unsigned)jo * ztiles);
     const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
     if (klim2 > 0.0) {
       const int n_o = AX == 0 ? g.ny : g.nx;
@@ -116,28 +114,35 @@ gpass_i2_kernel(AnyPlan pl, int nF, int ny, BoxAxis bA, int Kzp, const double2* 
   const int tid = threadIdx.x, nthr = blockDim.x, N = pl.n;
   AnyTile T = any_tile_setup(smem_raw, N, twg, tid, nthr);
   const int ztiles = (Kzp + FFT_TZ - 1) / FFT_TZ;   // a ragged last tile is allowed here (complex transforms: pitch nz)
-  const long long per = (long long)nF * ztiles;
-  const long long items = per * nb;
-  for (long long it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
-    const int bat = (int)(it0 / per);
-    const long long it = it0 - (long long)bat * per;
+  const unsigned per = (unsigned)nF * ztiles, items = per * nb;   // 32-bit item arithmetic (checked by the launcher)
+  const int cc = tid & 7, ia0 = tid >> 3, ias = nthr >> 3;        // a thread keeps its z column; its rows advance by nthr / 8
+  for (unsigned it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
+    const unsigned bat = it0 / per, it = it0 - bat * per;
     const double2* __restrict__ P = Pbase + (long long)bat * pstride;
     double2* __restrict__ Q = Qbase + (long long)bat * qstride;
-    const int f = (int)(it / ztiles), zt = (int)(it - (long long)f * ztiles);
+    const int f = (int)(it / ztiles), zt = (int)(it - (unsigned)f * ztiles);
     const int iz0 = zt * FFT_TZ;
+    const bool colok = iz0 + cc < Kzp;
     __syncthreads();
     const int lim = klim2 > 0.0 ? sphere_lim(klim2, kax_z[iz0], kax_a[1], N) : N;
-    for (int e = tid; e < N * FFT_TZ; e += nthr) {
-      const int ia = e >> 3, cc = e & 7;
-      const bool ok = bA.has(ia) && sidx_abs(ia, N) <= lim && iz0 + cc < Kzp;
-      any_cp16(T.b0 + ia * FFT_LDT + cc, ok ? P + ((long long)bA.pos(ia) * nF + f) * Kzp + iz0 + cc : P, ok);
+    {
+      // box rows: asynchronous copies from P (one pointer increment per row); the rows outside the box are zero
+      const double2* src = P + ((long long)ia0 * nF + f) * Kzp + iz0 + cc;
+      const long long sstep = (long long)ias * nF * Kzp;
+      for (int ja = ia0; ja < bA.K; ja += ias, src += sstep) {
+        const int ia = bA.idx(ja);
+        const bool ok = colok && sidx_abs(ia, N) <= lim;
+        any_cp16(T.b0 + ia * FFT_LDT + cc, ok ? src : P, ok);
+      }
+      for (int ia = bA.b + 1 + ia0; ia < N - (bA.K - bA.b - 1); ia += ias) T.b0[ia * FFT_LDT + cc] = make_double2(0.0, 0.0);
     }
     any_cp_wait();
     __syncthreads();
     const double2* res = any_fft_tile<-1>(T.b0, T.b1, T.tw, pl, tid, nthr);
-    for (int e = tid; e < N * FFT_TZ; e += nthr) {
-      const int ia = e >> 3, cc = e & 7;
-      if (iz0 + cc < Kzp) Q[row_of<AX>(ia, f, ny) * Kzp + iz0 + cc] = res[ia * FFT_LDT + cc];
+    if (colok) {
+      double2* dst = Q + row_of<AX>(ia0, f, ny) * Kzp + iz0 + cc;
+      const long long dstep = (AX == 0 ? (long long)ias * ny : (long long)ias) * Kzp;
+      for (int ia = ia0; ia < N; ia += ias, dst += dstep) *dst = res[ia * FFT_LDT + cc];
     }
   }
 }
@@ -152,28 +157,32 @@ gpass_f2_kernel(AnyPlan pl, int nC, int ny, BoxAxis bA, int Kzp, const double2* 
   const int tid = threadIdx.x, nthr = blockDim.x, N = pl.n;
   AnyTile T = any_tile_setup(smem_raw, N, twg, tid, nthr);
   const int ztiles = (Kzp + FFT_TZ - 1) / FFT_TZ;   // a ragged last tile is allowed here (complex transforms: pitch nz)
-  const long long per = (long long)nC * ztiles;
-  const long long items = per * nb;
-  for (long long it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
-    const int bat = (int)(it0 / per);
-    const long long it = it0 - (long long)bat * per;
+  const unsigned per = (unsigned)nC * ztiles, items = per * nb;
+  const int cc = tid & 7, ia0 = tid >> 3, ias = nthr >> 3;
+  for (unsigned it0 = blockIdx.x; it0 < items; it0 += gridDim.x) {
+    const unsigned bat = it0 / per, it = it0 - bat * per;
     const double2* __restrict__ R = Rbase + (long long)bat * rstride;
     double2* __restrict__ P = Pbase + (long long)bat * pstride;
-    const int ic = (int)(it / ztiles), zt = (int)(it - (long long)ic * ztiles);
+    const int ic = (int)(it / ztiles), zt = (int)(it - (unsigned)ic * ztiles);
     const int iz0 = zt * FFT_TZ;
+    const bool colok = iz0 + cc < Kzp;
     const int lim = klim2 > 0.0 ? sphere_lim(klim2, kax_z[iz0], kax_a[1], N) : N;
     __syncthreads();
-    for (int e = tid; e < N * FFT_TZ; e += nthr) {
-      const int ia = e >> 3, cc = e & 7;
-      const bool ok = iz0 + cc < Kzp;
-      any_cp16(T.b0 + ia * FFT_LDT + cc, ok ? R + row_of<AX>(ia, ic, ny) * Kzp + iz0 + cc : R, ok);
+    {
+      const double2* src = R + row_of<AX>(ia0, ic, ny) * Kzp + iz0 + cc;
+      const long long sstep = (AX == 0 ? (long long)ias * ny : (long long)ias) * Kzp;
+      for (int ia = ia0; ia < N; ia += ias, src += sstep) any_cp16(T.b0 + ia * FFT_LDT + cc, colok ? src : R, colok);
     }
     any_cp_wait();
     __syncthreads();
     const double2* res = any_fft_tile<1>(T.b0, T.b1, T.tw, pl, tid, nthr);
-    for (int e = tid; e < bA.K * FFT_TZ; e += nthr) {
-      const int ja = e >> 3, cc = e & 7, ia = bA.idx(ja);
-      if (sidx_abs(ia, N) <= lim && iz0 + cc < Kzp) P[((long long)ja * nC + ic) * Kzp + iz0 + cc] = res[ia * FFT_LDT + cc];
+    if (colok) {
+      double2* dst = P + ((long long)ia0 * nC + ic) * Kzp + iz0 + cc;
+      const long long dstep = (long long)ias * nC * Kzp;
+      for (int ja = ia0; ja < bA.K; ja += ias, dst += dstep) {
+        const int ia = bA.idx(ja);
+        if (sidx_abs(ia, N) <= lim) *dst = res[ia * FFT_LDT + cc];
+      }
     }
   }
 }
@@ -194,34 +203,37 @@ gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
   if (MODE == 2)
     for (int i = tid; i < NW * nb; i += nthr) hist[i] = 0.0;
   const int ztiles = (Kzp + FFT_TZ - 1) / FFT_TZ;   // a ragged last tile is allowed here (complex transforms: pitch nz)
-  const long long items = (long long)bO.K * ztiles;
+  const unsigned items = (unsigned)bO.K * ztiles;
   const bool nz_even = (g.nz % 2) == 0;
   const int nrows = (MODE == 2 && A.nrows > 1) ? A.nrows : 1;
   const int row = (int)(blockIdx.x % (unsigned)nrows), blk = (int)(blockIdx.x / (unsigned)nrows);
   const int nblk = (int)(gridDim.x / (unsigned)nrows);
   if (MODE == 2 && nrows > 1) P += (long long)row * A.row_pstride;
-  for (long long it = blk; it < items; it += nblk) {
-    const int jo = (int)(it / ztiles), zt = (int)(it - (long long)jo * ztiles);
+  for (unsigned it = blk; it < items; it += nblk) {
+    const int jo = (int)(it / ztiles), zt = (int)(it - (unsigned)jo * ztiles);
     const int io = bO.idx(jo), iz0 = zt * FFT_TZ;
     if (A.klim2 > 0.0) {
       const int n_o = AX == 0 ? g.ny : g.nx;
       if (sidx_abs(io, n_o) > sphere_lim(A.klim2, g.kax[2][iz0], g.kax[AX == 0 ? 1 : 0][1], n_o)) continue;
     }
     __syncthreads();
-    for (int e = tid; e < N * FFT_TZ; e += nthr) {
-      const int ia = e >> 3, cc = e & 7;
-      const bool ok = iz0 + cc < Kzp;
-      any_cp16(T.b0 + ia * FFT_LDT + cc, ok ? P + ((long long)jo * N + ia) * Kzp + iz0 + cc : P, ok);
+    const int cc0 = tid & 7, ia0 = tid >> 3, ias = nthr >> 3;
+    {
+      const bool colok = iz0 + cc0 < Kzp;
+      const double2* src = P + ((long long)jo * N + ia0) * Kzp + iz0 + cc0;
+      const long long sstep = (long long)ias * Kzp;
+      for (int ia = ia0; ia < N; ia += ias, src += sstep) any_cp16(T.b0 + ia * FFT_LDT + cc0, colok ? src : P, colok);
     }
     any_cp_wait();
     __syncthreads();
     const double2* res = any_fft_tile<1>(T.b0, T.b1, T.tw, pl, tid, nthr);
     if (MODE == 3) {
-      for (int e = tid; e < bA.K * FFT_TZ; e += nthr) {
-        const int ja = e >> 3, cc = e & 7, iz = iz0 + cc;
-        if (iz < Kz) {
-          const int p = __ldg(&A.perm[((long long)jo * bA.K + ja) * Kzp + iz]);
-          if (p >= 0) A.sorted_dst[p] = res[bA.idx(ja) * FFT_LDT + cc];
+      if (iz0 + cc0 < Kz) {
+        const int* pp = A.perm + ((long long)jo * bA.K + ia0) * Kzp + iz0 + cc0;
+        const long long pstep = (long long)ias * Kzp;
+        for (int ja = ia0; ja < bA.K; ja += ias, pp += pstep) {
+          const int p = __ldg(pp);
+          if (p >= 0) A.sorted_dst[p] = res[bA.idx(ja) * FFT_LDT + cc0];
         }
       }
     } else if (MODE != 2) {

@@ -208,3 +208,32 @@ def test_enlarged_row_mesh_matches_goldens(eng, world, golden, name, dims):
         assert relerr(F.cpu().numpy(), g["pk_fish_%d" % r]) < TOL
         assert relerr(qbar.cpu().numpy(), g["pk_qbar_%d" % r]) < TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("row_mesh", ["auto", "off"])
+@pytest.mark.parametrize("shape,kmax,dk", [((258, 496, 274), 0.41, 0.08), ((167, 307, 175), 0.11, 0.02),
+                                          ((172, 330, 182), 0.16, 0.04)])
+def test_production_meshes_against_oracle_golden(eng, golden, shape, kmax, dk, row_mesh):
+    """q-bar and F of one realisation at the FULL size of the reference's production meshes against the numpy restatement of the
+    reference (oracle/make_golden_production.py -> tests/golden/production_meshes.npz; 1e-9 like every golden), with the rows on
+    the row mesh the cost model picks and on the mesh itself (the any-length fused z pass: 274 = 2 * 137, 175 = 7 * 5 * 5)."""
+    from oracle import make_golden_production as mg
+    g = golden("production_meshes")
+    tag = "%dx%dx%d" % shape
+    bc, nbar_r = mg.inputs(shape)
+    mesh = eng.Mesh(mg.BOX, shape, bc, 0.0, kmax, dk, 4)
+    if row_mesh == "off":
+        os.environ["SWW_ROW_MESH"] = "0"
+    try:
+        ctx = eng.Context(mesh, 0, ("pk_fisher",))
+    finally:
+        os.environ.pop("SWW_ROW_MESH", None)
+    assert ctx.fft_backend == 1
+    if row_mesh == "off":
+        assert ctx.row_mesh_shape() is None
+    nbar_A = ctx.set_fields_from_randoms_density(nbar_r, mg.ALPHA, mg.SHOT)
+    a = np.random.default_rng(mg.SEED).normal(size=shape) * np.sqrt(nbar_A)
+    F, qbar = ctx.pk_fisher(a)
+    assert relerr(F.cpu().numpy(), g["F_" + tag]) < TOL
+    assert relerr(qbar.cpu().numpy(), g["qbar_" + tag]) < TOL
+    ctx.close()
