@@ -2389,6 +2389,130 @@ static int launch_z32(sww_ctx* c, Sm100State* s, ZArgs A) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// pass_z16f_kernel: the FORWARD half of pass_z16p_fused_kernel on its own (nz = 512, outputs below nz/4): the 2M + 1 transforms
+// FT[f Y_lm(r^)] at the head of every realisation.  A half-warp owns a row: lane b loads x[2m], x[2m+1] at m = b + 16 r straight
+// into the registers of forward stage 0, multiplies by the weight map and by Y_lm(r^) evaluated along the row (Horner in z
+// with the row's coefficients, 1 / r^2 by sww_rcp_pos; the z table sits in shared memory), and runs 16 x 16 with ONE exchange and
+// the table-driven r2c post-processing.  The three-stage warp-per-row kernel it replaces spent 67 % of the shared-memory
+// bandwidth on its two exchanges (ncu, profiles/r3f).
+// ------------------------------------------------------------------------------------------
+template <bool YLM>
+__global__ void __launch_bounds__(128, 4)
+pass_z16f_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = Z16_H, ROW = Z16_ROW, WARPS = 4;
+  double2* postA = reinterpret_cast<double2*>(smem_raw);   // [128]
+  double2* postB = postA + 128;                           // [128]
+  double2* tab = postB + 128;                             // [16][16] inter-stage twiddles W_256^(b r) at [r * 16 + b]
+  double2* zt = tab + 256;                                // [256] (z[2m], z[2m+1]) of the mesh axis
+  double2* bufs = zt + 256;                               // [WARPS][2 * ROW] exchange buffers
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rho = lane >> 4, b = lane & 15;
+  double2* buf = bufs + warp * 2 * ROW + rho * ROW;
+  const double half = 0.5 * A.scale;
+  for (int i = tid; i < 128; i += WARPS * 32) {
+    const double2 w = twn_g[i];                          // (c, -s)
+    postA[i] = make_double2(half * (1.0 + w.y), -half * w.x);
+    postB[i] = make_double2(half * (1.0 - w.y), half * w.x);
+  }
+  for (int i = tid; i < 256; i += WARPS * 32) {
+    tab[i] = twh_g[((i >> 4) * (i & 15)) & (H - 1)];
+    zt[i] = make_double2(g.rax[2][2 * i], g.rax[2][2 * i + 1]);
+  }
+  __syncthreads();
+  const long long ngroups = (long long)g.nx * g.ny / 2;
+  const long long gstep = (long long)gridDim.x * WARPS;
+  const int Kz_out = A.Kz_out;
+  const bool ymap = YLM && A.lm >= 1 && A.ymaps != nullptr;
+  for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += gstep) {
+    const long long row = grp * 2 + rho;
+    double2 u[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = *reinterpret_cast<const double2*>(A.real_in + row * g.nz + 2 * b + 32 * r);
+    if (A.wmap) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 w = *reinterpret_cast<const double2*>(A.wmap + row * g.nz + 2 * b + 32 * r);
+        u[r].x *= w.x;
+        u[r].y *= w.y;
+      }
+    }
+    if (ymap) {
+      const double* ym = A.ymaps + (long long)(A.lm - 1) * A.N + row * g.nz + 2 * b;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 y = *reinterpret_cast<const double2*>(ym + 32 * r);
+        u[r].x *= y.x;
+        u[r].y *= y.y;
+      }
+    } else if (YLM) {
+      const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+      const double X = g.rax[0][ix], Y = g.rax[1][iy], xy2 = X * X + Y * Y;
+      double Ac[3];
+      bool odd = false;
+      sww_ylm_zpack(A.lm, X, Y, Ac, &odd);
+      const int deg = SWW_YLM_ZDEG(A.lm);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 z = zt[b + 16 * r];
+        const double w0 = z.x * z.x, w1 = z.y * z.y;
+        u[r].x *= sww_ylm_zpacked(deg, Ac, odd, z.x, w0, deg ? sww_rcp_pos(xy2 + w0) : 1.0);
+        u[r].y *= sww_ylm_zpacked(deg, Ac, odd, z.y, w1, deg ? sww_rcp_pos(xy2 + w1) : 1.0);
+      }
+    }
+    // ---- forward: stage 0 from the registers, one exchange, stage 1
+    dft16<1>(u);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+    twiddle16_tab<1>(u, tab, b);
+    dft16<1>(u);
+    // ---- r2c post-processing: T[k] = V[k] postA[k] + conj(V[H-k]) postB[k]; V[H-k] sits in lane 16 - b, register 15 - r
+    double2* __restrict__ dst = A.R + row * A.Kzp_out;
+    const int src_lane = (rho << 4) | ((16 - b) & 15);
+#pragma unroll
+    for (int h4 = 0; h4 < 8; h4 += 4) {
+      double2 v2[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v2[q].x = __shfl_sync(0xffffffffu, u[15 - h4 - q].x, src_lane);
+        v2[q].y = __shfl_sync(0xffffffffu, u[15 - h4 - q].y, src_lane);
+      }
+      if (b == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v2[q] = u[(16 - h4 - q) & 15];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = b + 16 * (h4 + q);
+        const double2 v1 = u[h4 + q], pa = postA[k], pb = postB[k];
+        double2 t;
+        t.x = v1.x * pa.x - v1.y * pa.y + (v2[q].x * pb.x + v2[q].y * pb.y);
+        t.y = v1.x * pa.y + v1.y * pa.x + (v2[q].x * pb.y - v2[q].y * pb.x);
+        if (k < Kz_out) dst[k] = t;
+      }
+    }
+  }
+}
+
+template <bool YLM>
+static int launch_z16f(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)(128 + 128 + 256 + 256 + WARPS * 2 * Z16_ROW) * sizeof(double2);
+  const long long ngroups = (long long)c->g.nx * c->g.ny / 2;
+  const long long ctas = (ngroups + WARPS - 1) / WARPS;
+  SWW_TRY((set_smem(pass_z16f_kernel<YLM>, smem)));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_z16f_kernel<YLM>, WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm * grid_oversub());
+  pass_z16f_kernel<YLM><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n);
+  return 0;
+}
+
 template <int NBI, bool WREG, int MINB>
 static int launch_z16p_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   constexpr int WARPS = 4;
@@ -2493,6 +2617,14 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
   if (inv && fwd && !ylm && H == Z16_H && A.wmap && A.Kz_out <= 128 && A.Kz_in <= Z16_H + 1 && !no_z16 &&
       (c->g.nx * (long long)c->g.ny) % 2 == 0) {
     SWW_TRY(launch_z16(c, s, A));
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (!inv && fwd && H == Z16_H && A.Kz_out <= 128 && (c->g.nx * (long long)c->g.ny) % 2 == 0 && !no_z16 && !env_on("SWW_NO_Z16F")) {
+    // forward-only transforms at nz = 512: the 16 x 16 kernel with one exchange (pass_z16f_kernel)
+    if (ylm) SWW_TRY(launch_z16f<true>(c, s, A));
+    else SWW_TRY(launch_z16f<false>(c, s, A));
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
     return 0;
