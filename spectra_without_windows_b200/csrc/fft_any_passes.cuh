@@ -84,8 +84,7 @@ gpass_i1_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
             double f = ga.coef;
             if (ga.lm >= 0) {
               double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
-              double rr = sqrt(kx * kx + ky * ky + kz * kz);
-              double inv = 1.0 / (1e-12 + rr);
+              double inv = inv_norm_eps(kx * kx + ky * ky + kz * kz);
               f *= sww_ylm_dyn(ga.lm, kx * inv, ky * inv, kz * inv);
             }
             v.x *= f;
@@ -247,8 +246,7 @@ gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
           A.dst[cell] = t;
         } else {
           double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
-          double rr = sqrt(kx * kx + ky * ky + kz * kz);
-          double inv = 1.0 / (1e-12 + rr);
+          double inv = inv_norm_eps(kx * kx + ky * ky + kz * kz);
           double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
           double2 o = A.first ? make_double2(0.0, 0.0) : A.dst[cell];
           o.x += t.x * yk;

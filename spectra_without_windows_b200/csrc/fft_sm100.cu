@@ -203,6 +203,26 @@ struct BoxAxis {
 //     inverse:  first pass (gather)  spectrum -> P[Ko][nA][Kzp],   second pass  P -> Q[nx][ny][Kzp]
 //     forward:  first pass           R -> P[K_B][nC][Kzp],          last pass    P -> epilogue
 // ------------------------------------------------------------------------------------------
+// 1 / x for a positive, normal x (r^2 of a mesh cell) to 1-2 ulp: hardware seed (20 bits) + two Newton steps -- five instructions
+// against the ~25 of the IEEE division sequence with its special-case branches (ncu on the forward z pass: FSEL + BRA + BSSY/BSYNC
+// of those sequences were 17 % of the instructions).  The harmonics are compared with the reference at 1e-12.
+__device__ __forceinline__ double sww_rcp_pos(double x) {
+  double q;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(x));
+  double e = fma(-x, q, 1.0);
+  q = fma(q, e, q);
+  e = fma(-x, q, 1.0);
+  return fma(q, e, q);
+}
+
+// 1 / (1e-12 + sqrt(r2))  (pk/compute_pk_randoms.py:166) through one reciprocal square root:
+// 1/(e + r) = rs (1 - e rs + O((e rs)^2)), rs = 1/r; e rs <= 1e-12/|r| so the dropped term is < 1e-24.
+__device__ __forceinline__ double inv_norm_eps(double r2) {
+  if (r2 <= 0.0) return 1e12;
+  const double rs = rsqrt(r2);
+  return rs - 1e-12 * rs * rs;
+}
+
 // Sphere pruning of the column passes: within the z tile starting at k_z0 only the indices |i| <= lim along an axis with
 // fundamental kF can hold a mode with |k|^2 < klim2 (one index of margin against rounding).  All four passes use this one
 // function, so a column skipped by the pass that would write it is skipped by the pass that would read it.
@@ -276,8 +296,7 @@ pass_i1_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
             double f = ga.coef;
             if (ga.lm >= 0) {
               double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
-              double rr = sqrt(kx * kx + ky * ky + kz * kz);
-              double inv = 1.0 / (1e-12 + rr);
+              double inv = inv_norm_eps(kx * kx + ky * ky + kz * kz);
               f *= sww_ylm_dyn(ga.lm, kx * inv, ky * inv, kz * inv);
             }
             v.x *= f;
@@ -587,8 +606,7 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
             if (inb) A.dst[cell] = t;
           } else if (inb) {
             double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
-            double rr = sqrt(kx * kx + ky * ky + kz * kz);
-            double inv = 1.0 / (1e-12 + rr);
+            double inv = inv_norm_eps(kx * kx + ky * ky + kz * kz);
             double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
             double2 o = A.first ? make_double2(0.0, 0.0) : A.dst[cell];
             o.x += t.x * yk;
@@ -784,26 +802,6 @@ template <> struct WPlan<256> { static constexpr int NS = 3; static constexpr in
 template <> struct WPlan<512> { static constexpr int NS = 3; static constexpr int R[3] = {8, 8, 8}; };
 
 __device__ __forceinline__ int zpad(int i) { return i + (i >> 3); }
-
-// 1 / x for a positive, normal x (r^2 of a mesh cell) to 1-2 ulp: hardware seed (20 bits) + two Newton steps -- five instructions
-// against the ~25 of the IEEE division sequence with its special-case branches (ncu on the forward z pass: FSEL + BRA + BSSY/BSYNC
-// of those sequences were 17 % of the instructions).  The harmonics are compared with the reference at 1e-12.
-__device__ __forceinline__ double sww_rcp_pos(double x) {
-  double q;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(x));
-  double e = fma(-x, q, 1.0);
-  q = fma(q, e, q);
-  e = fma(-x, q, 1.0);
-  return fma(q, e, q);
-}
-
-// 1 / (1e-12 + sqrt(r2))  (pk/compute_pk_randoms.py:166) through one reciprocal square root:
-// 1/(e + r) = rs (1 - e rs + O((e rs)^2)), rs = 1/r; e rs <= 1e-12/|r| so the dropped term is < 1e-24.
-__device__ __forceinline__ double inv_norm_eps(double r2) {
-  if (r2 <= 0.0) return 1e12;
-  const double rs = rsqrt(r2);
-  return rs - 1e-12 * rs * rs;
-}
 
 template <int H, bool REV, int S>
 struct WRadix {
