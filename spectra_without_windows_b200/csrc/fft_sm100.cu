@@ -595,12 +595,25 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
 #pragma unroll
       for (int s = 0; s < 16 / RL; ++s) {
         const int w_ = tid + s * NT, bi = w_ >> 3, cc = w_ & 7, iz = iz0 + cc;
+        // MODE 1 accumulates into dst: all previous values of the batch are loaded before the first store (the stores to dst would
+        // otherwise order every load behind them: one memory latency per element)
+        long long cells[RL];
+        double2 old[RL];
 #pragma unroll
         for (int r = 0; r < RL; ++r) {
           const int ia = bi + r * (N / RL);
           const bool inb = bA.has(ia) && iz < Kz;
           const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
-          const long long cell = inb ? remap_cell(g, A, ix, iy, iz) : 0;
+          cells[r] = inb ? remap_cell(g, A, ix, iy, iz) : -1;
+          old[r] = make_double2(0.0, 0.0);
+          if (MODE == 1 && inb && !A.first) old[r] = A.dst[cells[r]];
+        }
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          const int ia = bi + r * (N / RL);
+          const bool inb = cells[r] >= 0;
+          const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
+          const long long cell = cells[r];
           const double2 t = u[s][r];
           if (MODE == 0) {
             if (inb) A.dst[cell] = t;
@@ -608,7 +621,7 @@ pass_f3_kernel(Geo g, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, const double2* __
             double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
             double inv = inv_norm_eps(kx * kx + ky * ky + kz * kz);
             double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
-            double2 o = A.first ? make_double2(0.0, 0.0) : A.dst[cell];
+            double2 o = old[r];
             o.x += t.x * yk;
             o.y += t.y * yk;
             if (A.coef != 0.0) {
