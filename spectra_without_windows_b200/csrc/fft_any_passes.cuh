@@ -236,32 +236,52 @@ gpass_f3_kernel(Geo g, AnyPlan pl, BoxAxis bA, BoxAxis bO, int Kz, int Kzp, cons
         }
       }
     } else if (MODE != 2) {
-      for (int e = tid; e < bA.K * FFT_TZ; e += nthr) {
-        const int ja = e >> 3, cc = e & 7, iz = iz0 + cc, ia = bA.idx(ja);
-        if (iz >= Kz) continue;
-        const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
-        const long long cell = remap_cell(g, A, ix, iy, iz);
-        const double2 t = res[ia * FFT_LDT + cc];
-        if (MODE == 0) {
-          A.dst[cell] = t;
-        } else {
-          double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
-          double inv = inv_norm_eps(kx * kx + ky * ky + kz * kz);
-          double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
-          double2 o = A.first ? make_double2(0.0, 0.0) : A.dst[cell];
-          o.x += t.x * yk;
-          o.y += t.y * yk;
-          if (A.coef != 0.0) {
-            if (A.mas_power) {
-              double m = g.mas[0][ix] * g.mas[1][iy] * g.mas[2][iz];
-              if (A.mas_power == 2) m = m * m;
-              o.x *= m;
-              o.y *= m;
+      // four box rows per round; MODE 1 loads the previous values of the round before its first store (see pass_f3_kernel)
+      const int iz = iz0 + cc0;
+      if (iz < Kz) {
+        constexpr int U = 4;
+        for (int jb = ia0; jb < bA.K; jb += U * ias) {
+          long long cells[U];
+          double2 old[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int ja = jb + u * ias;
+            cells[u] = -1;
+            old[u] = make_double2(0.0, 0.0);
+            if (ja < bA.K) {
+              const int ia = bA.idx(ja);
+              cells[u] = remap_cell(g, A, AX == 0 ? ia : io, AX == 0 ? io : ia, iz);
+              if (MODE == 1 && !A.first) old[u] = A.dst[cells[u]];
             }
-            o.x *= A.coef;
-            o.y *= A.coef;
           }
-          A.dst[cell] = o;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (cells[u] < 0) continue;
+            const int ia = bA.idx(jb + u * ias);
+            const int ix = AX == 0 ? ia : io, iy = AX == 0 ? io : ia;
+            const double2 t = res[ia * FFT_LDT + cc0];
+            if (MODE == 0) {
+              A.dst[cells[u]] = t;
+            } else {
+              double kx = g.kax[0][ix], ky = g.kax[1][iy], kz = g.kax[2][iz];
+              double inv = inv_norm_eps(kx * kx + ky * ky + kz * kz);
+              double yk = sww_ylm_dyn(A.lm, kx * inv, ky * inv, kz * inv);
+              double2 o = old[u];
+              o.x += t.x * yk;
+              o.y += t.y * yk;
+              if (A.coef != 0.0) {
+                if (A.mas_power) {
+                  double m = g.mas[0][ix] * g.mas[1][iy] * g.mas[2][iz];
+                  if (A.mas_power == 2) m = m * m;
+                  o.x *= m;
+                  o.y *= m;
+                }
+                o.x *= A.coef;
+                o.y *= A.coef;
+              }
+              A.dst[cells[u]] = o;
+            }
+          }
         }
       }
     } else {
