@@ -2524,6 +2524,133 @@ static int launch_z16f(sww_ctx* c, Sm100State* s, ZArgs A) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// pass_z32f_kernel: the same for nz = 1024 -- the forward half of pass_z32_fused_kernel on its own.  A warp owns a row: half-warp
+// p transforms the samples x_c[2q + p] = (x[4q + 2p], x[4q + 2p + 1]) (q = b + 16 r) with the 16 x 16 kernel, the two 256-point
+// results are joined by one radix-2 step through an xor-16 shuffle, and the p = 0 lanes post-process and store k < K_z,out.
+// ------------------------------------------------------------------------------------------
+template <bool YLM>
+__global__ void __launch_bounds__(128, 4)
+pass_z32f_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = Z32_H, ROW = Z16_ROW, WARPS = 4;
+  double2* twn = reinterpret_cast<double2*>(smem_raw);   // [H + 8]  exp(-2 pi i j / nz), j <= H
+  double2* tab = twn + (H + 8);                          // [16][16] inter-stage twiddles W_512^(2 b r) at [r * 16 + b]
+  double2* zt = tab + 256;                               // [512] (z[2i], z[2i+1]) of the mesh axis
+  double2* bufs = zt + 512;                              // [WARPS][2 * ROW] exchange buffers (one per half-warp)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p = lane >> 4, b = lane & 15;
+  double2* buf = bufs + warp * 2 * ROW + p * ROW;
+  for (int i = tid; i <= H; i += WARPS * 32) twn[i] = twn_g[i];
+  for (int i = tid; i < 256; i += WARPS * 32) tab[i] = twh_g[(2 * (i >> 4) * (i & 15)) & (H - 1)];
+  for (int i = tid; i < 512; i += WARPS * 32) zt[i] = make_double2(g.rax[2][2 * i], g.rax[2][2 * i + 1]);
+  __syncthreads();
+  const long long nrows = (long long)g.nx * g.ny;
+  const long long gstep = (long long)gridDim.x * WARPS;
+  const int Kz_out = A.Kz_out;
+  const double half = 0.5 * A.scale;
+  const bool ymap = YLM && A.lm >= 1 && A.ymaps != nullptr;
+  for (long long row = (long long)blockIdx.x * WARPS + warp; row < nrows; row += gstep) {
+    const long long off = row * g.nz + 4 * b + 2 * p;
+    double2 u[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = *reinterpret_cast<const double2*>(A.real_in + off + 64 * r);
+    if (A.wmap) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 w = *reinterpret_cast<const double2*>(A.wmap + off + 64 * r);
+        u[r].x *= w.x;
+        u[r].y *= w.y;
+      }
+    }
+    if (ymap) {
+      const double* ym = A.ymaps + (long long)(A.lm - 1) * A.N + off;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 y = *reinterpret_cast<const double2*>(ym + 64 * r);
+        u[r].x *= y.x * half;
+        u[r].y *= y.y * half;
+      }
+    } else if (YLM) {
+      const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+      const double X = g.rax[0][ix], Y = g.rax[1][iy], xy2 = X * X + Y * Y;
+      double Ac[3];
+      bool odd = false;
+      sww_ylm_zpack(A.lm, X, Y, Ac, &odd);
+      const int deg = SWW_YLM_ZDEG(A.lm);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 z = zt[2 * (b + 16 * r) + p];
+        const double w0 = z.x * z.x, w1 = z.y * z.y;
+        u[r].x *= half * sww_ylm_zpacked(deg, Ac, odd, z.x, w0, deg ? sww_rcp_pos(xy2 + w0) : 1.0);
+        u[r].y *= half * sww_ylm_zpacked(deg, Ac, odd, z.y, w1, deg ? sww_rcp_pos(xy2 + w1) : 1.0);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        u[r].x *= half;
+        u[r].y *= half;
+      }
+    }
+    // ---- forward: E (p = 0) and O (p = 1), 16 x 16 with one exchange
+    dft16<1>(u);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[17 * b + r] = u[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = buf[b + 17 * r];
+    twiddle16_tab<1>(u, tab, b);
+    dft16<1>(u);
+    // ---- radix-2 join: V[j] = E[j] + W_512^j O[j] (p = 0),  V[j + 256] = E[j] - W_512^j O[j] (p = 1),  j = b + 16 r
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double2 o;
+      o.x = __shfl_xor_sync(0xffffffffu, u[r].x, 16);
+      o.y = __shfl_xor_sync(0xffffffffu, u[r].y, 16);
+      const double2 e = p == 0 ? u[r] : o;
+      const double2 od = p == 0 ? o : u[r];
+      const double2 t = c_mul(od, twn[2 * (b + 16 * r)]);
+      u[r] = p == 0 ? make_double2(e.x + t.x, e.y + t.y) : make_double2(e.x - t.x, e.y - t.y);
+    }
+    // ---- r2c post-processing on the p = 0 lanes (see pass_z32_fused_kernel)
+    double2* __restrict__ dst = A.R + row * A.Kzp_out;
+    const int src_lane = 16 | ((16 - b) & 15);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (16 * r < Kz_out) {                          // warp-uniform
+        const double2 offer = (lane == 16) ? u[(16 - r) & 15] : u[15 - r];
+        double2 v2;
+        v2.x = __shfl_sync(0xffffffffu, offer.x, src_lane);
+        v2.y = __shfl_sync(0xffffffffu, offer.y, src_lane);
+        const int k = b + 16 * r;
+        if (k == 0) v2 = u[0];                        // V[512] = V[0]
+        if (p == 0 && k < Kz_out) {
+          const double2 v1 = u[r];
+          const double2 ev = make_double2(v1.x + v2.x, v1.y - v2.y);
+          const double2 dv = make_double2(v1.x - v2.x, v1.y + v2.y);
+          const double2 od = c_mul(make_double2(dv.y, -dv.x), twn[k]);
+          dst[k] = make_double2(ev.x + od.x, ev.y + od.y);
+        }
+      }
+    }
+  }
+}
+
+template <bool YLM>
+static int launch_z32f(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)(Z32_H + 8 + 256 + 512 + WARPS * 2 * Z16_ROW) * sizeof(double2);
+  const long long nrows = (long long)c->g.nx * c->g.ny;
+  const long long ctas = (nrows + WARPS - 1) / WARPS;
+  SWW_TRY((set_smem(pass_z32f_kernel<YLM>, smem)));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_z32f_kernel<YLM>, WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm * grid_oversub());
+  pass_z32f_kernel<YLM><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n);
+  return 0;
+}
+
 template <int NBI, bool WREG, int MINB>
 static int launch_z16p_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   constexpr int WARPS = 4;
@@ -2636,6 +2763,14 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
     // forward-only transforms at nz = 512: the 16 x 16 kernel with one exchange (pass_z16f_kernel)
     if (ylm) SWW_TRY(launch_z16f<true>(c, s, A));
     else SWW_TRY(launch_z16f<false>(c, s, A));
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (!inv && fwd && H == Z32_H && A.Kz_out <= 256 && !no_z16 && !env_on("SWW_NO_Z16F")) {
+    // forward-only transforms at nz = 1024: two 16 x 16 halves per row and a radix-2 join (pass_z32f_kernel)
+    if (ylm) SWW_TRY(launch_z32f<true>(c, s, A));
+    else SWW_TRY(launch_z32f<false>(c, s, A));
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
     return 0;

@@ -269,3 +269,40 @@ def test_complex_transforms_on_own_passes(eng, shape):
     ctx.set_fft_backend(0)
     assert relerr(ctx.fft_c2c(x).cpu().numpy(), X) < 1e-13
     ctx.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 512), (64, 128, 1024)])
+def test_forward_only_16x16_z_kernels(eng, shape):
+    """The forward transforms FT[f Y_lm(r^)] of a realisation's head on pass_z16f_kernel (nz = 512) / pass_z32f_kernel (nz = 1024):
+    a mesh whose k_max box stays below nz / 4, P_l Fisher matrix and q-bar against the cuFFT backend and against the
+    three-stage warp-per-row kernel they replace (SWW_NO_Z16F=1)."""
+    import os
+    from spectra_without_windows_b200 import synthetic as syn
+    box = tuple(6.0 * s for s in shape)
+    bc = (2.0 * box[0], 30.0, -20.0)
+    mesh = eng.Mesh(box, shape, bc, 0.0, 0.12, 0.03, 4)
+    ctx = eng.Context(mesh, 0, ("pk_fisher",))
+    assert ctx.fft_backend == 1
+    n_gal = syn.survey_nbar(box, shape, bc, n0=3e-4)
+    nbar_r = n_gal / 0.05
+    nbar_A = ctx.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)
+    a = np.random.default_rng(4).normal(size=shape) * np.sqrt(nbar_A)
+    F1, q1 = ctx.pk_fisher(a)
+    F1, q1 = F1.cpu().numpy(), q1.cpu().numpy()
+    os.environ["SWW_NO_Z16F"] = "1"
+    try:
+        F2, q2 = ctx.pk_fisher(a)
+    finally:
+        del os.environ["SWW_NO_Z16F"]
+    assert relerr(F1, F2.cpu().numpy()) < 1e-12 and relerr(q1, q2.cpu().numpy()) < 1e-12
+    ctx.close()
+    os.environ["SWW_ROW_MESH"] = "0"          # the cuFFT context lays its workspace out for the full mesh
+    try:
+        ref = eng.Context(mesh, 0, ("pk_fisher",))
+    finally:
+        del os.environ["SWW_ROW_MESH"]
+    ref.set_fft_backend(0)
+    ref.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)
+    F0, q0 = ref.pk_fisher(a)
+    assert relerr(F1, F0.cpu().numpy()) < 1e-11 and relerr(q1, q0.cpu().numpy()) < 1e-11
+    ref.close()
