@@ -2172,6 +2172,7 @@ static int launch_i1_any(sww_ctx* c, Sm100State* s, BoxAxis bA, BoxAxis bO, int 
   const size_t smem = ANY_SMEM_TILES(pl.n);
   const int threads = any_threads_for(pl);
   long long items = (long long)bO.K * ((Kzp + FFT_TZ - 1) / FFT_TZ) * (gb.nb > 0 ? gb.nb : 1);
+  SWW_REQUIRE(items < (1LL << 31), "any-length pass: too many work items");
   SWW_TRY(set_smem(gpass_i1_kernel<AX>, smem));
   int grid = grid_for_items(items, any_occ(gpass_i1_kernel<AX>, smem, threads));
   gpass_i1_kernel<AX><<<grid, threads, smem, c->stream>>>(c->g, pl, bA, bO, Kz, Kzp, src, shell, tw_of(s, AX), s->P, gb,
@@ -2187,6 +2188,7 @@ static int launch_i2_any(sww_ctx* c, Sm100State* s, int nF, BoxAxis bA, int Kzp,
   const size_t smem = ANY_SMEM_TILES(pl.n);
   const int threads = any_threads_for(pl);
   long long items = (long long)nF * ((Kzp + FFT_TZ - 1) / FFT_TZ) * nb;
+  SWW_REQUIRE(items < (1LL << 31), "any-length pass: too many work items");
   SWW_TRY(set_smem(gpass_i2_kernel<AX>, smem));
   int grid = grid_for_items(items, any_occ(gpass_i2_kernel<AX>, smem, threads));
   gpass_i2_kernel<AX><<<grid, threads, smem, c->stream>>>(pl, nF, c->g.ny, bA, Kzp, s->P, tw_of(s, AX), Qdst, nb, pstride, qstride,
@@ -2201,6 +2203,7 @@ static int launch_f2_any(sww_ctx* c, Sm100State* s, int nC, BoxAxis bA, int Kzp,
   const size_t smem = ANY_SMEM_TILES(pl.n);
   const int threads = any_threads_for(pl);
   long long items = (long long)nC * ((Kzp + FFT_TZ - 1) / FFT_TZ) * nb;
+  SWW_REQUIRE(items < (1LL << 31), "any-length pass: too many work items");
   SWW_TRY(set_smem(gpass_f2_kernel<AX>, smem));
   int grid = grid_for_items(items, any_occ(gpass_f2_kernel<AX>, smem, threads));
   gpass_f2_kernel<AX><<<grid, threads, smem, c->stream>>>(pl, nC, c->g.ny, bA, Kzp, s->R, tw_of(s, AX), s->P, nb, rstride, pstride,
@@ -2218,6 +2221,7 @@ static int launch_f3_any(sww_ctx* c, Sm100State* s, int mode, BoxAxis bA, BoxAxi
   const size_t smem = ANY_SMEM_TILES(pl.n) + (size_t)hist * 8;
   long long items = (long long)bO.K * ((Kzp + FFT_TZ - 1) / FFT_TZ);
   const int nrows = (mode == 2 && A.nrows > 1) ? A.nrows : 1;
+  SWW_REQUIRE(items < (1LL << 31), "any-length pass: too many work items");
 #define LAUNCH_F3_ANY(MM)                                                                                                  \
   {                                                                                                                        \
     SWW_TRY((set_smem(gpass_f3_kernel<AX, MM>, smem)));                                                                    \
@@ -2651,6 +2655,129 @@ static int launch_z32f(sww_ctx* c, Sm100State* s, ZArgs A) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// pass_z8f_kernel: forward-only z pass for nz = 256 (the bispectrum meshes), 128 = 16 x 8 with ONE exchange.  A quarter-warp owns a
+// row: lane b (0..7) loads x_c[m] = (x[2m], x[2m+1]) at m = b + 8 r into 16 registers, runs the 16-point stage over r, multiplies
+// by W_128^(b q), exchanges so that lane c holds q = c and q = c + 8 for all eight b, and finishes with two 8-point transforms:
+// V[q + 16 s].  The few outputs below nz/8 are post-processed from a natural-order copy in shared memory.
+// ------------------------------------------------------------------------------------------
+#define Z8_ROW 152   // 16 * 9 exchange slots (pitch 9: conflict-free transposed reads), reused for V[0..128]
+template <bool YLM>
+__global__ void __launch_bounds__(128, 4)
+pass_z8f_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = 128, WARPS = 4;
+  double2* postA = reinterpret_cast<double2*>(smem_raw);   // [64]
+  double2* postB = postA + 64;                            // [64]
+  double2* tab = postB + 64;                              // [16][8]  W_128^(b q) at [q * 8 + b]
+  double2* zt = tab + 128;                                // [128] (z[2m], z[2m+1])
+  double2* bufs = zt + 128;                               // [WARPS][4 rows][Z8_ROW]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rho = lane >> 3, b = lane & 7;
+  double2* buf = bufs + (warp * 4 + rho) * Z8_ROW;
+  const double half = 0.5 * A.scale;
+  for (int i = tid; i < 64; i += WARPS * 32) {
+    const double2 w = twn_g[i];                          // (c, -s) of 2 pi i / nz
+    postA[i] = make_double2(half * (1.0 + w.y), -half * w.x);
+    postB[i] = make_double2(half * (1.0 - w.y), half * w.x);
+  }
+  for (int i = tid; i < 128; i += WARPS * 32) {
+    tab[i] = twh_g[((i >> 3) * (i & 7)) & (H - 1)];
+    zt[i] = make_double2(g.rax[2][2 * i], g.rax[2][2 * i + 1]);
+  }
+  __syncthreads();
+  const long long ngroups = (long long)g.nx * g.ny / 4;
+  const long long gstep = (long long)gridDim.x * WARPS;
+  const int Kz_out = A.Kz_out;
+  const bool ymap = YLM && A.lm >= 1 && A.ymaps != nullptr;
+  for (long long grp = (long long)blockIdx.x * WARPS + warp; grp < ngroups; grp += gstep) {
+    const long long row = grp * 4 + rho;
+    const long long off = row * g.nz + 2 * b;
+    double2 u[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = *reinterpret_cast<const double2*>(A.real_in + off + 16 * r);
+    if (A.wmap) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 w = *reinterpret_cast<const double2*>(A.wmap + off + 16 * r);
+        u[r].x *= w.x;
+        u[r].y *= w.y;
+      }
+    }
+    if (ymap) {
+      const double* ym = A.ymaps + (long long)(A.lm - 1) * A.N + off;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 y = *reinterpret_cast<const double2*>(ym + 16 * r);
+        u[r].x *= y.x;
+        u[r].y *= y.y;
+      }
+    } else if (YLM) {
+      const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+      const double X = g.rax[0][ix], Y = g.rax[1][iy], xy2 = X * X + Y * Y;
+      double Ac[3];
+      bool odd = false;
+      sww_ylm_zpack(A.lm, X, Y, Ac, &odd);
+      const int deg = SWW_YLM_ZDEG(A.lm);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const double2 z = zt[b + 8 * r];
+        const double w0 = z.x * z.x, w1 = z.y * z.y;
+        u[r].x *= sww_ylm_zpacked(deg, Ac, odd, z.x, w0, deg ? sww_rcp_pos(xy2 + w0) : 1.0);
+        u[r].y *= sww_ylm_zpacked(deg, Ac, odd, z.y, w1, deg ? sww_rcp_pos(xy2 + w1) : 1.0);
+      }
+    }
+    // ---- stage 0: 16-point transforms over r; twiddle W_128^(b q); exchange
+    dft16<1>(u);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) u[q] = c_mul(u[q], tab[q * 8 + b]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) buf[q * 9 + b] = u[q];
+    __syncwarp();
+    double2 v0[8], v1[8];
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) {
+      v0[bb] = buf[b * 9 + bb];            // q = b
+      v1[bb] = buf[(b + 8) * 9 + bb];      // q = b + 8
+    }
+    // ---- stage 1: 8-point transforms over the old lane index -> V[q + 16 s]
+    dft8<1>(v0);
+    dft8<1>(v1);
+    __syncwarp();
+#pragma unroll
+    for (int sft = 0; sft < 8; ++sft) {
+      buf[b + 16 * sft] = v0[sft];
+      buf[b + 8 + 16 * sft] = v1[sft];
+    }
+    __syncwarp();
+    // ---- r2c post-processing: T[k] = V[k] postA[k] + conj(V[H-k]) postB[k], V[H] = V[0]
+    double2* __restrict__ dst = A.R + row * A.Kzp_out;
+    for (int k = b; k < Kz_out; k += 8) {
+      const double2 va = buf[k], vb = buf[k == 0 ? 0 : H - k], pa = postA[k], pb = postB[k];
+      double2 t;
+      t.x = va.x * pa.x - va.y * pa.y + (vb.x * pb.x + vb.y * pb.y);
+      t.y = va.x * pa.y + va.y * pa.x + (vb.x * pb.y - vb.y * pb.x);
+      dst[k] = t;
+    }
+    __syncwarp();
+  }
+}
+
+template <bool YLM>
+static int launch_z8f(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)(64 + 64 + 128 + 128 + WARPS * 4 * Z8_ROW) * sizeof(double2);
+  const long long ngroups = (long long)c->g.nx * c->g.ny / 4;
+  const long long ctas = (ngroups + WARPS - 1) / WARPS;
+  SWW_TRY((set_smem(pass_z8f_kernel<YLM>, smem)));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_z8f_kernel<YLM>, WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm * grid_oversub());
+  pass_z8f_kernel<YLM><<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n);
+  return 0;
+}
+
 template <int NBI, bool WREG, int MINB>
 static int launch_z16p_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   constexpr int WARPS = 4;
@@ -2763,6 +2890,14 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
     // forward-only transforms at nz = 512: the 16 x 16 kernel with one exchange (pass_z16f_kernel)
     if (ylm) SWW_TRY(launch_z16f<true>(c, s, A));
     else SWW_TRY(launch_z16f<false>(c, s, A));
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (!inv && fwd && H == 128 && A.Kz_out <= 64 && (c->g.nx * (long long)c->g.ny) % 4 == 0 && !no_z16 && !env_on("SWW_NO_Z16F")) {
+    // forward-only transforms at nz = 256: 16 x 8 with one exchange (pass_z8f_kernel)
+    if (ylm) SWW_TRY(launch_z8f<true>(c, s, A));
+    else SWW_TRY(launch_z8f<false>(c, s, A));
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
     return 0;

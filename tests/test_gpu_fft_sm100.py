@@ -271,9 +271,9 @@ def test_complex_transforms_on_own_passes(eng, shape):
     ctx.close()
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 512), (64, 128, 1024)])
+@pytest.mark.parametrize("shape", [(64, 64, 256), (64, 64, 512), (64, 128, 1024)])
 def test_forward_only_16x16_z_kernels(eng, shape):
-    """The forward transforms FT[f Y_lm(r^)] of a realisation's head on pass_z16f_kernel (nz = 512) / pass_z32f_kernel (nz = 1024):
+    """The forward transforms FT[f Y_lm(r^)] of a realisation's head on pass_z8f_kernel (nz = 256) / pass_z16f_kernel (512) / pass_z32f_kernel (1024):
     a mesh whose k_max box stays below nz / 4, P_l Fisher matrix and q-bar against the cuFFT backend and against the
     three-stage warp-per-row kernel they replace (SWW_NO_Z16F=1)."""
     import os
