@@ -2778,6 +2778,209 @@ static int launch_z8f(sww_ctx* c, Sm100State* s, ZArgs A) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// pass_z8i_kernel: inverse-only z pass for nz = 256 with K_z,in <= 64 -- the batched inverse of the bispectrum phi maps
+// (sum over planes of Y_lm(r^) IFT[...], times weights, one write).  Geometry of pass_z8f_kernel run backwards: lane c of a
+// quarter-warp gathers Y[q + 16 s] for q = c, c + 8 (table-driven Hermitian pre-processing straight from the complex rows: at
+// most one of Z[k], Z[H-k] is kept), two 8-point transforms over s, twiddle, ONE exchange, a 16-point transform over q:
+// x_c[b + 8 r] in 16 registers.  The harmonic planes (one degree l) are summed as row polynomials in z -- r^l Y_lm = P_lm(x, y; z),
+// three FMAs per cell and plane -- and multiplied by r^-l once per cell, then the plain planes are added: no cached harmonic maps
+// (3/4 of the old pass's traffic), no division per plane.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 3)
+pass_z8i_kernel(Geo g, ZArgs A, const double2* __restrict__ twh_g, const double2* __restrict__ twn_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int H = 128, WARPS = 4;
+  double2* preA = reinterpret_cast<double2*>(smem_raw);   // [64]
+  double2* preB = preA + 64;                             // [72]
+  double2* tab = preB + 72;                              // [16][8]  W_128^(b q) at [q * 8 + b]
+  double2* zt = tab + 128;                               // [128] (z[2m], z[2m+1])
+  double2* bufs = zt + 128;                              // [WARPS][4 rows][Z8_ROW]
+  double2* stgs = bufs + WARPS * 4 * Z8_ROW;             // [WARPS][4 rows][64] staged complex input rows (cp.async)
+  __shared__ int ord[SWW_MAX_ZBATCH];                    // planes in processing order: harmonic planes first
+  __shared__ int n_harm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rho = lane >> 3, b = lane & 7;
+  double2* buf = bufs + (warp * 4 + rho) * Z8_ROW;
+  double2* stg = stgs + (warp * 4 + rho) * 64;
+  for (int i = tid; i <= 64; i += WARPS * 32) {
+    const double2 w = twn_g[i];                          // (c, -s)
+    preB[i] = make_double2(1.0 - w.y, w.x);
+    if (i < 64) preA[i] = make_double2(1.0 + w.y, w.x);
+  }
+  if (tid == 0) {
+    const int np_ = A.nb > 1 ? A.nb : 1;
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int bq = 0; bq < np_; ++bq) {
+        const int lmb = A.nb > 1 ? A.lms[bq] : A.lm;
+        if ((lmb >= 0) == (pass == 0)) ord[n++] = bq;
+        if (pass == 0 && bq == np_ - 1) n_harm = n;
+      }
+  }
+  for (int i = tid; i < 128; i += WARPS * 32) {
+    tab[i] = twh_g[((i >> 3) * (i & 7)) & (H - 1)];
+    zt[i] = make_double2(g.rax[2][2 * i], g.rax[2][2 * i + 1]);
+  }
+  __syncthreads();
+  const long long ngroups = (long long)g.nx * g.ny / 4;
+  const long long gstep = (long long)gridDim.x * WARPS;
+  const int Kz_in = A.Kz_in;
+  const int npl = A.nb > 1 ? A.nb : 1;
+  // the complex row of plane `pl` for this quarter-warp's row -> staging buffer (asynchronous; 8 lanes x 16 bytes per step)
+  auto prefetch = [&](int pl, long long r_) {
+    const double2* src = A.Q + (long long)pl * A.q_stride + r_ * A.Kzp_in;
+    for (int k = b; k < Kz_in; k += 8) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(stg + k);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + k));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  long long grp = (long long)blockIdx.x * WARPS + warp;
+  if (grp < ngroups) prefetch(ord[0], grp * 4 + rho);
+  for (; grp < ngroups; grp += gstep) {
+    const long long row = grp * 4 + rho;
+    const int ix = (int)(row / g.ny), iy = (int)(row - (long long)ix * g.ny);
+    const double X = g.rax[0][ix], Y = g.rax[1][iy], xy2 = X * X + Y * Y;
+    double2 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = make_double2(0.0, 0.0);
+    int deg_s = 0;
+    for (int i = 0; i < npl; ++i) {
+      const int bq = ord[i];
+      const bool harm = i < n_harm;
+      const int lmb = A.nb > 1 ? A.lms[bq] : A.lm;
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncwarp();
+      // ---- gather Y[q + 16 s], q = b + 8 j, from the staged row: one table product per kept element
+      double2 y[2][8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int sft = 0; sft < 8; ++sft) {
+          const int k = b + 8 * j + 16 * sft;
+          double2 o = make_double2(0.0, 0.0);
+          if (k < Kz_in) {
+            double2 v = stg[k];
+            if (k == 0) v.y = 0.0;
+            const double2 cw = preA[k];
+            o = make_double2(v.x * cw.x - v.y * cw.y, v.x * cw.y + v.y * cw.x);
+          } else if (H - k < Kz_in) {
+            const double2 v = stg[H - k], cw = preB[H - k];
+            o = make_double2(v.x * cw.x + v.y * cw.y, v.x * cw.y - v.y * cw.x);
+          }
+          y[j][sft] = o;
+        }
+      __syncwarp();
+      {
+        // the staging buffer is free again: start the copy of the next plane (or of the next row group's first plane)
+        const bool wrap = i + 1 >= npl;
+        const long long ngrp = wrap ? grp + gstep : grp;
+        if (ngrp < ngroups) prefetch(ord[wrap ? 0 : i + 1], ngrp * 4 + rho);
+      }
+      dft8<-1>(y[0]);
+      dft8<-1>(y[1]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) {
+          double2 w = tab[(b + 8 * j) * 8 + bb];
+          w.y = -w.y;
+          buf[(b + 8 * j) * 9 + bb] = c_mul(y[j][bb], w);
+        }
+      __syncwarp();
+      double2 u[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) u[q] = buf[q * 9 + b];
+      __syncwarp();
+      dft16<-1>(u);
+      // ---- u[r] = (x[2m], x[2m+1]) at m = b + 8 r
+      if (harm) {
+        double Ac[3];
+        bool odd = false;
+        sww_ylm_zpack(lmb, X, Y, Ac, &odd);
+        deg_s = SWW_YLM_ZDEG(lmb);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const double2 z = zt[b + 8 * r];
+          const double w0 = z.x * z.x, w1 = z.y * z.y;
+          double p0 = (Ac[2] * w0 + Ac[1]) * w0 + Ac[0], p1 = (Ac[2] * w1 + Ac[1]) * w1 + Ac[0];
+          if (odd) {
+            p0 *= z.x;
+            p1 *= z.y;
+          }
+          acc[r].x += p0 * u[r].x;
+          acc[r].y += p1 * u[r].y;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          acc[r].x += u[r].x;
+          acc[r].y += u[r].y;
+        }
+      }
+      if (i == n_harm - 1 && deg_s > 0) {
+        // r^-l once per cell, after the last harmonic plane
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const double2 z = zt[b + 8 * r];
+          double q0 = sww_rcp_pos(xy2 + z.x * z.x), q1 = sww_rcp_pos(xy2 + z.y * z.y);
+          if (deg_s == 4) {
+            q0 *= q0;
+            q1 *= q1;
+          }
+          acc[r].x *= q0;
+          acc[r].y *= q1;
+        }
+      }
+    }
+    // ---- weights, scale, one write
+    double* __restrict__ out = A.real_out + row * g.nz + 2 * b;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double f0 = A.scale, f1 = A.scale;
+      if (A.wmap) {
+        const double2 w = *reinterpret_cast<const double2*>(A.wmap + row * g.nz + 2 * b + 16 * r);
+        f0 *= w.x;
+        f1 *= w.y;
+      }
+      double2 o = make_double2(acc[r].x * f0, acc[r].y * f1);
+      if (A.accumulate) {
+        const double2 old = *reinterpret_cast<const double2*>(out + 16 * r);
+        o.x += old.x;
+        o.y += old.y;
+      }
+      *reinterpret_cast<double2*>(out + 16 * r) = o;
+    }
+  }
+}
+
+static int launch_z8i(sww_ctx* c, Sm100State* s, ZArgs A) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)(64 + 72 + 128 + 128 + WARPS * 4 * Z8_ROW + WARPS * 4 * 64) * sizeof(double2);
+  const long long ngroups = (long long)c->g.nx * c->g.ny / 4;
+  const long long ctas = (ngroups + WARPS - 1) / WARPS;
+  SWW_TRY((set_smem(pass_z8i_kernel, smem)));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass_z8i_kernel, WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int grid = (int)std::min<long long>(ctas, (long long)SMS * per_sm * grid_oversub());
+  pass_z8i_kernel<<<grid, WARPS * 32, smem, c->stream>>>(c->g, A, s->tw_h, s->tw_n);
+  return 0;
+}
+
+// the harmonic planes of a batched inverse share one polynomial degree (the planes of one phi map do): pass_z8i_kernel's sum
+static bool one_harmonic_degree(const ZArgs& A) {
+  if (A.nb <= 1) return true;
+  int deg = -1;
+  for (int b = 0; b < A.nb; ++b)
+    if (A.lms[b] >= 0) {
+      const int d = SWW_YLM_ZDEG(A.lms[b]);
+      if (deg >= 0 && d != deg) return false;
+      deg = d;
+    }
+  return true;
+}
+
 template <int NBI, bool WREG, int MINB>
 static int launch_z16p_v(sww_ctx* c, Sm100State* s, ZArgs A) {
   constexpr int WARPS = 4;
@@ -2890,6 +3093,17 @@ static int run_z(sww_ctx* c, Sm100State* s, bool inv, bool fwd, ZArgs A) {
     // forward-only transforms at nz = 512: the 16 x 16 kernel with one exchange (pass_z16f_kernel)
     if (ylm) SWW_TRY(launch_z16f<true>(c, s, A));
     else SWW_TRY(launch_z16f<false>(c, s, A));
+    c->n_own++;
+    SWW_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (inv && !fwd && H == 128 && A.Kz_in <= 64 && (c->g.nx * (long long)c->g.ny) % 4 == 0 && !no_z16 && env_on("SWW_Z8I") &&
+      one_harmonic_degree(A)) {
+    // inverse-only transforms at nz = 256 (bispectrum phi maps): 8 x 16 with one exchange, polynomial harmonics (pass_z8i_kernel).
+    // OPT-IN (SWW_Z8I=1): validated against the warp-per-row kernel, but measured slower on the C4 pair -- 442 ms against 340 ms
+    // (558 ms before the cp.async staging of the next plane's rows): 16 values per lane cost 168 registers, 12 warps per SM, and
+    // the pass is bound by its per-plane latencies, not by the cached-harmonics traffic this kernel removes (profiles/r3s)
+    SWW_TRY(launch_z8i(c, s, A));
     c->n_own++;
     SWW_CUDA(cudaGetLastError());
     return 0;

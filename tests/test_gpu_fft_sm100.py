@@ -306,3 +306,33 @@ def test_forward_only_16x16_z_kernels(eng, shape):
     F0, q0 = ref.pk_fisher(a)
     assert relerr(F1, F0.cpu().numpy()) < 1e-11 and relerr(q1, q0.cpu().numpy()) < 1e-11
     ref.close()
+
+
+def test_inverse_only_z8_kernel(eng):
+    """The opt-in batched inverse z pass of the bispectrum phi maps at nz = 256 (SWW_Z8I=1, pass_z8i_kernel: one exchange,
+    harmonics as row polynomials with one reciprocal per cell) against the default warp-per-row kernel with cached harmonics:
+    the whole B_l Fisher matrix of one pair, l <= 4."""
+    import os
+    from spectra_without_windows_b200 import synthetic as syn
+    shape = (64, 64, 256)
+    box = tuple(6.0 * s for s in shape)
+    bc = (2.0 * box[0], 30.0, -20.0)
+    mesh = eng.Mesh(box, shape, bc, 0.0, 0.12, 0.03, 4)
+    ctx = eng.Context(mesh, 0, ("bk_fisher",))
+    assert ctx.fft_backend == 1
+    n_gal = syn.survey_nbar(box, shape, bc, n0=3e-4)
+    nbar_r = n_gal / 0.05
+    nbar_A = ctx.set_fields_from_randoms_density(nbar_r, 0.05, 1.05)
+    rng = np.random.default_rng(6)
+    aA = rng.normal(size=shape) * np.sqrt(nbar_A)
+    aB = rng.normal(size=shape) * np.sqrt(nbar_A)
+    F1, maps = ctx.bk_fisher_pair(aA, aB)               # default: the warp-per-row kernel with cached harmonics
+    F1 = F1.cpu().numpy().copy()
+    os.environ["SWW_Z8I"] = "1"                         # opt-in kernel (measured slower, kept for the record: DESIGN.md)
+    try:
+        F2, maps = ctx.bk_fisher_pair(aA, aB, maps)
+    finally:
+        del os.environ["SWW_Z8I"]
+    F2 = F2.cpu().numpy()
+    assert np.isfinite(F1).all() and relerr(F1, F2) < 1e-11
+    ctx.close()
