@@ -716,6 +716,17 @@ extern "C" int sww_bk_delta(sww_ctx* c, sww_devptr delta_out) {
   return 0;
 }
 
+// q[t][l] = T[a, b, (l, c)] of the triangle (a, b, c)
+__global__ void q3_gather_kernel(const int* __restrict__ tris, int n_tri, int n_l, int n_k, const double* __restrict__ T,
+                                 double* __restrict__ q) {
+  const int nz = n_l * n_k;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_tri * n_l; idx += gridDim.x * blockDim.x) {
+    const int t = idx / n_l, l = idx - t * n_l;
+    const int a = tris[3 * t], b = tris[3 * t + 1], c = tris[3 * t + 2];
+    q[idx] = T[((long long)a * n_k + b) * nz + l * n_k + c];
+  }
+}
+
 // 3-field term (bk/compute_bk_data.py:350-367): q[t][l] = sum_x g_a^0 g_b^0 g_c^l
 extern "C" int sww_bk_q3(sww_ctx* c, sww_devptr g_, sww_devptr q_out) {
   CHECK_READY(c);
@@ -725,6 +736,21 @@ extern "C" int sww_bk_q3(sww_ctx* c, sww_devptr g_, sww_devptr q_out) {
   const size_t N = c->g.N;
   const int n_k = c->g.n_k;
   double* q = (double*)q_out;
+  if (n_k >= 4 && n_k <= 32 && N % 2 == 0) {
+    // ONE trilinear Gram on the FP64 tensor cores, T[i, j, (l, c)] = sum_x g_i^0 g_j^0 g_c^l: every map is streamed once per operand
+    // (2x the compulsory traffic) instead of three maps per triangle term (n_tri n_l terms: ~35x); the triangles pick their entries
+    const int nz = c->n_l * n_k;
+    const size_t tsz = (size_t)n_k * n_k * nz;
+    if (c->q1_scratch_elems < 3 * tsz) {
+      if (c->d_q1_scratch) cudaFree(c->d_q1_scratch);
+      SWW_CUDA(cudaMalloc(&c->d_q1_scratch, 3 * tsz * sizeof(double)));
+      c->q1_scratch_elems = 3 * tsz;
+    }
+    double* T = c->d_q1_scratch;
+    SWW_TRY(sww_gram3(c, g, g, g, n_k, n_k, nz, (long long)N, T));
+    q3_gather_kernel<<<sww_grid_for((long long)c->n_tri * c->n_l, 128), 128, 0, c->stream>>>(c->d_tris, c->n_tri, c->n_l, n_k, T, q);
+    return launch_ok(c);
+  }
   SWW_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * (size_t)c->n_tri * c->n_l, c->stream));
   TermBatcher tb(c, q);
   for (int t = 0; t < c->n_tri; ++t) {
